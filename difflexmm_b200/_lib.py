@@ -1,0 +1,155 @@
+"""ctypes binding of libdfx.so (the C ABI declared in include/dfx.h).
+
+Importing this module loads the CUDA library or raises: the solver has no CPU or eager fallback.
+Device buffers come from torch (allocation, streams); the library itself never sees a torch type.
+"""
+
+import ctypes as C
+import os
+import subprocess
+
+import numpy as np
+import torch
+
+from . import _abi
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+_SO = os.path.join(_HERE, "libdfx.so")
+_SRC = os.path.join(_HERE, "csrc")
+NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
+              "-Xcompiler", "-fPIC", "-shared"]
+
+
+def build(force=False, verbose=False):
+    """Compile csrc/dfx_api.cu -> libdfx.so for sm_100a (nvcc cross-compiles without a GPU)."""
+    srcs = [os.path.join(_SRC, f) for f in os.listdir(_SRC)] + [os.path.join(_HERE, "..", "include", "dfx.h")]
+    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs):
+        return _SO
+    cmd = ["nvcc", *NVCC_FLAGS, "-o", _SO, os.path.join(_SRC, "dfx_api.cu")]
+    if verbose:
+        cmd.insert(1, "-Xptxas=-v")
+    subprocess.check_call(cmd)
+    return _SO
+
+
+if not os.path.exists(_SO):
+    raise ImportError(
+        f"{_SO} is missing: build it with `python -c 'import __graft_entry__ as g; g.build()'` "
+        "(difflexmm_b200 has no CPU path)")
+
+lib = C.CDLL(_SO)
+lib.dfx_last_error.restype = C.c_char_p
+lib.dfx_version.restype = C.c_char_p
+lib.dfx_forward_workspace_bytes.restype = C.c_size_t
+lib.dfx_adjoint_workspace_bytes.restype = C.c_size_t
+
+EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free", "dfx_drive_n_params",
+           "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
+           "dfx_expand_fields", "dfx_last_error", "dfx_version")
+
+
+def _check(rc, what):
+    if rc != 0:
+        raise RuntimeError(f"{what} failed (code {rc}): {lib.dfx_last_error().decode()}")
+
+
+class Topology:
+    """Owns one `DfxTopology*` on one device."""
+
+    def __init__(self, spec: _abi.TopologySpec, device_index: int):
+        self.spec, self.device_index = spec, int(device_index)
+        self._desc = spec.to_desc()
+        self._h = C.c_void_p()
+        _check(lib.dfx_topology_create(C.byref(self._desc), self.device_index, C.byref(self._h)), "dfx_topology_create")
+        assert lib.dfx_topology_n_free(self._h) == spec.n_free
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.dfx_topology_destroy(h)
+
+
+def _stream_ptr(device):
+    return C.c_void_p(torch.cuda.current_stream(device).cuda_stream)
+
+
+def _dev(t):
+    return t.device
+
+
+def forward(topo: Topology, ps: _abi.ParamSet, y0, ts, rtol, atol, options: _abi.DfxOptions):
+    """-> ys (B, n_t, 2 n_free) device tensor, stats (B,) numpy structured array (synchronises)."""
+    spec, B = topo.spec, ps.batch
+    N = 2 * spec.n_free
+    dev = y0.device
+    assert y0.is_cuda and y0.dtype == torch.float64 and ts.dtype == torch.float64
+    n_t = ts.shape[-1]
+    y0 = y0.contiguous()
+    ts = ts.contiguous()
+    if y0.shape[-1] != N:
+        raise ValueError(f"state0 has {y0.shape[-1]} free entries, expected {N}")
+    ys = torch.empty((B, n_t, N), dtype=torch.float64, device=dev)
+    stats = torch.zeros((B, _abi.STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    p = ps.to_struct()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.dfx_forward_workspace_bytes(topo._h, B)
+        ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
+        _check(lib.dfx_forward(topo._h, C.byref(p), B, C.c_void_p(y0.data_ptr()), C.c_int64(N if y0.dim() == 2 else 0),
+                               C.c_void_p(ts.data_ptr()), C.c_int64(n_t if ts.dim() == 2 else 0), n_t,
+                               C.c_double(rtol), C.c_double(atol), C.byref(options),
+                               C.c_void_p(ys.data_ptr()), C.c_void_p(stats.data_ptr()),
+                               C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes), _stream_ptr(dev)), "dfx_forward")
+    return ys, _Stats(stats)
+
+
+def adjoint(topo: Topology, ps: _abi.ParamSet, ys, ts, g, rtol, atol, aug_size, options: _abi.DfxOptions):
+    """-> y0_bar (B, 2 n_free), ts_bar (B, n_t), grads {leaf: (B,)+shape}, stats."""
+    spec, B = topo.spec, ps.batch
+    N = 2 * spec.n_free
+    dev = ys.device
+    n_t = ts.shape[-1]
+    ys, ts, g = ys.contiguous(), ts.contiguous(), g.contiguous()
+    y0_bar = torch.zeros((B, N), dtype=torch.float64, device=dev)
+    ts_bar = torch.zeros((B, n_t), dtype=torch.float64, device=dev)
+    grads = {n: torch.zeros((B,) + ps.base_shapes[n], dtype=torch.float64, device=dev) for n in ps.leaves}
+    gs = _abi.DfxParamGrads()
+    for n, t in grads.items():
+        setattr(gs, n, t.data_ptr())
+    stats = torch.zeros((B, _abi.STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    p = ps.to_struct()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.dfx_adjoint_workspace_bytes(topo._h, B)
+        ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
+        _check(lib.dfx_adjoint(topo._h, C.byref(p), B, C.c_void_p(ys.data_ptr()), C.c_void_p(ts.data_ptr()),
+                               C.c_int64(n_t if ts.dim() == 2 else 0), n_t, C.c_void_p(g.data_ptr()),
+                               C.c_double(rtol), C.c_double(atol), C.c_int64(int(aug_size)), C.byref(options),
+                               C.c_void_p(y0_bar.data_ptr()), C.c_void_p(ts_bar.data_ptr()), C.byref(gs),
+                               C.c_void_p(stats.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes),
+                               _stream_ptr(dev)), "dfx_adjoint")
+    return y0_bar, ts_bar, grads, _Stats(stats)
+
+
+def expand_fields(topo: Topology, ps: _abi.ParamSet, ys, ts):
+    spec, B = topo.spec, ps.batch
+    dev = ys.device
+    n_t = ts.shape[-1]
+    fields = torch.empty((B, n_t, 2, spec.n_blocks, 3), dtype=torch.float64, device=dev)
+    p = ps.to_struct()
+    with torch.cuda.device(dev):
+        _check(lib.dfx_expand_fields(topo._h, C.byref(p), B, C.c_void_p(ys.contiguous().data_ptr()),
+                                     C.c_void_p(ts.contiguous().data_ptr()), C.c_int64(n_t if ts.dim() == 2 else 0), n_t,
+                                     C.c_void_p(fields.data_ptr()), _stream_ptr(dev)), "dfx_expand_fields")
+    return fields
+
+
+class _Stats:
+    """Per-design solver statistics; stays on the device until read (reading synchronises)."""
+
+    def __init__(self, raw):
+        self._raw = raw
+
+    def numpy(self):
+        return self._raw.cpu().numpy().view(_abi.STATS_DTYPE).reshape(-1)
+
+    def __getitem__(self, k):
+        return self.numpy()[k]

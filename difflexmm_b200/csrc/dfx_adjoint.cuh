@@ -1,0 +1,599 @@
+// dfx_adjoint.cuh -- continuous adjoint of the forward solve: what jax.grad derives for the
+// odeint call at dynamics.py:166 (jax.experimental.ode._odeint_rev).
+//
+// One persistent CTA per design walks the stored outputs ys[i] backwards.  On every output
+// interval it restarts a fresh adaptive Dopri5 solve (own initial step size) of the augmented
+// system in negated time s = -t
+//     z = (y, y_bar, t0_bar, args_bar)      dz/ds = (-f, vjp_y, vjp_t, vjp_args)
+// whose RMS error norm runs over ALL entries of z, parameter cotangents included.  The stored
+// outputs act as checkpoints: the forward state is recomputed from ys[i] inside each interval.
+//
+// Augmented RHS (three phases, two CTA barriers), with w = lambda_v / m:
+//   A  per block-DOF : stage values of u, v, lambda_u, lambda_v; sin/cos(theta); w
+//   B  per bond      : analytic gradient evaluated on dual numbers seeded with w
+//                      -> force slots, (H w) slots, parameter cotangent integrands
+//   C  per block-DOF : gather slots;  dv/ds = -(F - c v + load)/m,  dlambda_u/ds = -(H w),
+//                      dlambda_v/ds = lambda_u - c w,  quadrature integrands for inertia, damping,
+//                      centroid_node_vectors (contact chain), drive parameters and t0_bar
+// Parameter cotangents are pure quadratures: their stage values never feed the RHS, so only the
+// running solution / error / midpoint combinations are kept (k1 and k7 for FSAL and the dense
+// output).  Scalar leaves (k_stretch, ..., contact and drive parameters, t0_bar) are reduced with
+// warp shuffles into per-warp partials and combined once per step.
+#pragma once
+
+#include "dfx_forward.cuh"
+
+namespace dfx {
+
+// arrays of the adjoint kernel in placement-priority order
+enum {
+  AA_US = 0, AA_WS, AA_VS, AA_LUS, AA_LVS,  // stage communication
+  AA_FS, AA_HS, AA_GS, AA_GA,               // node slots
+  AA_SC,                                    // scalar leaves (small)
+  AA_INVM, AA_CD,
+  AA_U0, AA_V0, AA_LU0, AA_LV0,
+  AA_KV, AA_KLU, AA_KLV,
+  AA_BONDC, AA_CNV, AA_ALPHA,
+  AA_QSOL, AA_QERR, AA_QMID, AA_QK1, AA_QK7, AA_Q0, AA_QNEW,
+  AA_COUNT
+};
+
+struct PlacementA { long long off[AA_COUNT]; };
+
+constexpr int NSCAL = 13;  // 0 t0_bar | 1-3 k_stretch,k_shear,k_rot | 4 damping | 5-7 contact | 8-12 drive
+constexpr int SC_T0 = 0, SC_KS = 1, SC_KSH = 2, SC_KR = 3, SC_DAMP = 4, SC_CONTACT = 5, SC_DRIVE = 8;
+
+struct AdjArgs {
+  DevTopo topo;
+  DfxParams p;
+  Tableau tab;
+  PlacementA place;
+  const double* ys; const double* ts; long long ts_bstride; int n_t;
+  const double* g;
+  double rtol, atol;
+  long long aug_size;
+  int init_step_variant; long long max_steps;
+  double* y0_bar; double* ts_bar;
+  DfxParamGrads grads;
+  DfxStats* stats;
+  double* scratch; long long scratch_per_design;
+  // quadrature layout (entries)
+  int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, nq;
+};
+
+struct QuadCtx {
+  double *q0, *qnew, *k1, *k7, *asol, *aerr, *amid;
+  double h, atol, rtol, x;
+  int mode;  // 0: k1 at interval start | 2..5: stage | 6: last stage | 7: initial-step probe
+  bool crossing;
+  double cs, ce, cm, cs0, ce0, cm0;  // tableau weights of this stage (and of k1 for mode 2)
+};
+
+__device__ __forceinline__ double interp_eval(double y0, double y1, double ymid, double d0, double d1, double x) {
+  const double ca = -2. * d0 + 2. * d1 - 8. * y0 - 8. * y1 + 16. * ymid;
+  const double cb = 5. * d0 - 3. * d1 + 18. * y0 + 14. * y1 - 32. * ymid;
+  const double cc = -4. * d0 + d1 - 11. * y0 - 5. * y1 + 16. * ymid;
+  return (((ca * x + cb) * x + cc) * x + d0) * x + y0;
+}
+
+// one elementwise quadrature entry receives its integrand value for the current stage
+__device__ __forceinline__ void quad_update(const QuadCtx& c, int idx, double val, double& acc) {
+  switch (c.mode) {
+    case 0: c.k1[idx] = val; break;
+    case 7: {
+      const double sc = c.atol + fabs(c.q0[idx]) * c.rtol;
+      const double d = (val - c.k1[idx]) / sc;
+      acc += d * d;
+    } break;
+    case 2: {
+      const double k1 = c.k1[idx];
+      c.asol[idx] = c.cs0 * k1 + c.cs * val;
+      c.aerr[idx] = c.ce0 * k1 + c.ce * val;
+      c.amid[idx] = c.cm0 * k1 + c.cm * val;
+    } break;
+    case 6: {
+      const double aerr = c.aerr[idx] + c.ce * val, amid = c.amid[idx] + c.cm * val;
+      const double q0 = c.q0[idx], q1 = q0 + c.h * c.asol[idx];
+      const double tol = c.atol + c.rtol * fmax(fabs(q0), fabs(q1));
+      const double r = c.h * aerr / tol;
+      acc += r * r;
+      c.k7[idx] = val;
+      c.qnew[idx] = c.crossing ? interp_eval(q0, q1, q0 + c.h * amid, c.h * c.k1[idx], c.h * val, c.x) : q1;
+    } break;
+    default:
+      c.asol[idx] += c.cs * val;
+      c.aerr[idx] += c.ce * val;
+      c.amid[idx] += c.cm * val;
+      break;
+  }
+}
+
+// scalar leaves: per-warp partial sums of the same linear recurrences (combined once per step)
+struct ScalCtx {
+  double *wk1, *wk7, *wsol, *werr, *wmid;  // [NSCAL][32]
+};
+__device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, int which, double partial) {
+  const double v = warp_sum(partial);
+  if ((threadIdx.x & 31) != 0) return;
+  const int idx = which * 32 + (threadIdx.x >> 5);
+  switch (c.mode) {
+    case 0: s.wk1[idx] = v; break;
+    case 7: s.wk7[idx] = v; break;
+    case 2: {
+      const double k1 = s.wk1[idx];
+      s.wsol[idx] = c.cs0 * k1 + c.cs * v;
+      s.werr[idx] = c.ce0 * k1 + c.ce * v;
+      s.wmid[idx] = c.cm0 * k1 + c.cm * v;
+    } break;
+    case 6:
+      s.werr[idx] += c.ce * v;
+      s.wmid[idx] += c.cm * v;
+      s.wk7[idx] = v;
+      break;
+    default:
+      s.wsol[idx] += c.cs * v;
+      s.werr[idx] += c.ce * v;
+      s.wmid[idx] += c.cm * v;
+      break;
+  }
+}
+
+__global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
+  extern __shared__ double smem[];
+  const DevTopo& T = a.topo;
+  const Tableau& tab = a.tab;
+  const int design = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x, nwarp = (nthr + 31) >> 5;
+  const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;
+  const int NQ = a.nq;
+  double* red = smem;
+  double* scratch = a.scratch ? a.scratch + (long long)design * a.scratch_per_design : nullptr;
+  auto P = [&](int i) -> double* {
+    const long long o = a.place.off[i];
+    return o >= 0 ? smem + o : scratch + (-(o + 1));
+  };
+  double *Us = P(AA_US), *Ws = P(AA_WS), *Vs = P(AA_VS), *Lus = P(AA_LUS), *Lvs = P(AA_LVS);
+  double *Fs = P(AA_FS), *Hs = P(AA_HS), *Gs = P(AA_GS), *Ga = T.contact ? P(AA_GA) : nullptr;
+  double* SC = P(AA_SC);  // [2][NSCAL] q0,qnew + [5][NSCAL][32] per-warp partials
+  double *invm = P(AA_INVM), *cd = P(AA_CD);
+  double *u0 = P(AA_U0), *v0 = P(AA_V0), *lu0 = P(AA_LU0), *lv0 = P(AA_LV0);
+  double *kv = P(AA_KV), *klu = P(AA_KLU), *klv = P(AA_KLV);
+  double *bondc = P(AA_BONDC), *cnv = P(AA_CNV), *alpha = T.contact ? P(AA_ALPHA) : nullptr;
+  QuadCtx qc;
+  qc.asol = P(AA_QSOL); qc.aerr = P(AA_QERR); qc.amid = P(AA_QMID);
+  qc.k1 = P(AA_QK1); qc.k7 = P(AA_QK7); qc.q0 = P(AA_Q0); qc.qnew = P(AA_QNEW);
+  qc.atol = a.atol; qc.rtol = a.rtol; qc.crossing = false; qc.x = 0; qc.h = 0; qc.mode = 0;
+  double* Sq0 = SC;
+  double* Sqnew = SC + NSCAL;
+  ScalCtx sc;
+  sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * 32; sc.wsol = sc.wk7 + NSCAL * 32;
+  sc.werr = sc.wsol + NSCAL * 32; sc.wmid = sc.werr + NSCAL * 32;
+
+  const double* g_ks = leaf_ptr(a.p.k_stretch, design);
+  const double* g_ksh = leaf_ptr(a.p.k_shear, design);
+  const double* g_kr = leaf_ptr(a.p.k_rot, design);
+  const double* g_contact = leaf_ptr(a.p.contact, design);
+  const double* g_drive = leaf_ptr(a.p.drive, design);
+  const double* ts = a.ts + (long long)design * a.ts_bstride;
+  const double* ys = a.ys + (long long)design * a.n_t * 2 * nf;
+  const double* gg = a.g + (long long)design * a.n_t * 2 * nf;
+  const double rtol = a.rtol, atol = a.atol;
+  const bool ks_pb = a.p.k_per_bond[0], ksh_pb = a.p.k_per_bond[1], kr_pb = a.p.k_per_bond[2];
+  const bool damp_pd = a.p.damping_per_dof != 0, has_damp = T.n_damped > 0 && a.p.damping.ptr != nullptr;
+  const int ndp = T.n_drive_params;
+
+  setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd);
+  for (int i = tid; i < 3 * NN; i += nthr) { Fs[i] = 0.0; Hs[i] = 0.0; }
+  for (int i = tid; i < 2 * NN; i += nthr) { Gs[i] = 0.0; if (Ga) Ga[i] = 0.0; }
+  for (int i = tid; i < NQ; i += nthr) { qc.q0[i] = 0.0; qc.k1[i] = 0.0; qc.k7[i] = 0.0; qc.qnew[i] = 0.0; qc.asol[i] = 0.0; qc.aerr[i] = 0.0; qc.amid[i] = 0.0; }
+  for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * 32; i += nthr) SC[i] = 0.0;
+  double cmin = 0, ccut = 0, ckc = 0;
+  if (T.contact) { cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
+  // y_bar = g[-1]
+  for (int e = tid; e < ND; e += nthr) {
+    const int j = e / NB, blk = e - j * NB;
+    const int f = T.free_of_dof[3 * blk + j];
+    lu0[e] = f >= 0 ? gg[(long long)(a.n_t - 1) * 2 * nf + f] : 0.0;
+    lv0[e] = f >= 0 ? gg[(long long)(a.n_t - 1) * 2 * nf + nf + f] : 0.0;
+  }
+  __syncthreads();
+
+  // ---- augmented RHS, phases B and C.  kidx: which k-slot (0..6) receives the dynamic derivatives
+  auto aug_BC = [&](double time, double* kv_out, double* klu_out, double* klv_out) {
+    const bool want_q = qc.mode != 1;
+    __syncthreads();
+    double p_ks = 0, p_ksh = 0, p_kr = 0, p_c0 = 0, p_c1 = 0, p_c2 = 0, probe = 0;
+    for (int b = tid; b < NBONDS; b += nthr) {
+      const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
+      BlockState<Dual> s1, s2;
+      s1.x = Dual(Us[bl.x], Ws[bl.x]); s1.y = Dual(Us[NB + bl.x], Ws[NB + bl.x]);
+      s1.th = Dual(Us[2 * NB + bl.x], Ws[2 * NB + bl.x]);
+      {
+        const double sn = Us[3 * NB + bl.x], cs = Us[4 * NB + bl.x];
+        s1.s = Dual(sn, cs * s1.th.d); s1.c = Dual(cs, -sn * s1.th.d);
+      }
+      s2.x = Dual(Us[bl.y], Ws[bl.y]); s2.y = Dual(Us[NB + bl.y], Ws[NB + bl.y]);
+      s2.th = Dual(Us[2 * NB + bl.y], Ws[2 * NB + bl.y]);
+      {
+        const double sn = Us[3 * NB + bl.y], cs = Us[4 * NB + bl.y];
+        s2.s = Dual(sn, cs * s2.th.d); s2.c = Dual(cs, -sn * s2.th.d);
+      }
+      BondConst bc = {bondc[b], bondc[NBONDS + b], bondc[2 * NBONDS + b], bondc[3 * NBONDS + b]};
+      const double ks = g_ks[ks_pb ? b : 0], ksh = g_ksh[ksh_pb ? b : 0], kr = g_kr[kr_pb ? b : 0];
+      BondOut<Dual> o;
+      if (want_q) bond_gradient<Dual, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
+      else bond_gradient<Dual, false>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
+      if (T.contact) {
+        Dual psi1 = wrapT(s1.th - s2.th + (alpha[nd.x] - alpha[NN + nd.y]));
+        Dual psi2 = wrapT(s2.th - s1.th + (alpha[nd.y] - alpha[NN + nd.x]));
+        Dual e1, e2, m1, m2, c1, c2, k1, k2;
+        contact_term<Dual>(psi1, cmin, ccut, ckc, e1, m1, c1, k1);
+        contact_term<Dual>(psi2, cmin, ccut, ckc, e2, m2, c2, k2);
+        o.f1[2] = o.f1[2] + e1 - e2;
+        o.f2[2] = o.f2[2] + e2 - e1;
+        if (want_q) {
+          // dS/dalpha = -(dual part of dE/dalpha): alpha_1next:+e1, alpha_1prev:-e2, alpha_2next:+e2, alpha_2prev:-e1
+          Ga[nd.x] = -e1.d; Ga[NN + nd.x] = e2.d; Ga[nd.y] = -e2.d; Ga[NN + nd.y] = e1.d;
+          p_c0 -= m1.d + m2.d; p_c1 -= c1.d + c2.d; p_c2 -= k1.d + k2.d;
+        }
+      }
+      Fs[nd.x] = -o.f1[0].v; Fs[NN + nd.x] = -o.f1[1].v; Fs[2 * NN + nd.x] = -o.f1[2].v;
+      Fs[nd.y] = -o.f2[0].v; Fs[NN + nd.y] = -o.f2[1].v; Fs[2 * NN + nd.y] = -o.f2[2].v;
+      Hs[nd.x] = o.f1[0].d; Hs[NN + nd.x] = o.f1[1].d; Hs[2 * NN + nd.x] = o.f1[2].d;
+      Hs[nd.y] = o.f2[0].d; Hs[NN + nd.y] = o.f2[1].d; Hs[2 * NN + nd.y] = o.f2[2].d;
+      if (want_q) {
+        // d(w.F)/dp = -(dual part of dE/dp)
+        Gs[nd.x] = -o.gr1[0].d; Gs[NN + nd.x] = -o.gr1[1].d;
+        Gs[nd.y] = -o.gr2[0].d; Gs[NN + nd.y] = -o.gr2[1].d;
+        quad_update(qc, a.qo_ref + b, -o.gr0[0].d, probe);
+        quad_update(qc, a.qo_ref + NBONDS + b, -o.gr0[1].d, probe);
+        if (ks_pb) quad_update(qc, a.qo_ks + b, -o.gks.d, probe); else p_ks -= o.gks.d;
+        if (ksh_pb) quad_update(qc, a.qo_ksh + b, -o.gksh.d, probe); else p_ksh -= o.gksh.d;
+        if (kr_pb) quad_update(qc, a.qo_kr + b, -o.gkr.d, probe); else p_kr -= o.gkr.d;
+      }
+    }
+    if (want_q) {
+      if (!ks_pb) scal_update(qc, sc, SC_KS, p_ks);
+      if (!ksh_pb) scal_update(qc, sc, SC_KSH, p_ksh);
+      if (!kr_pb) scal_update(qc, sc, SC_KR, p_kr);
+      if (T.contact) { scal_update(qc, sc, SC_CONTACT, p_c0); scal_update(qc, sc, SC_CONTACT + 1, p_c1); scal_update(qc, sc, SC_CONTACT + 2, p_c2); }
+    }
+    __syncthreads();
+    double ls = 0.0, lsd = 0.0;
+    if (T.load_kind != DFX_LOAD_NONE) load_eval(T.load_kind, time, T.load_consts, ls, lsd);
+    double p_t0 = 0, p_damp = 0, p_dr[DFX_MAX_DRIVE_PARAMS] = {0, 0, 0, 0, 0};
+    for (int e = tid; e < ND; e += nthr) {
+      const int j = e / NB, blk = e - j * NB, dof = 3 * blk + j;
+      double F = 0.0, HW = 0.0;
+      {
+        const double* fslot = Fs + (long long)j * NN + blk * npb;
+        const double* hslot = Hs + (long long)j * NN + blk * npb;
+        for (int l = 0; l < npb; ++l) { F += fslot[l]; HW += hslot[l]; }
+      }
+      const double im = invm[e];
+      if (im != 0.0) {
+        const double w = Ws[e], v = Vs[e], c = cd[e];
+        double lm = 0.0;
+        if (T.load_kind != DFX_LOAD_NONE) { lm = T.load_mul[dof]; F += lm * ls; }
+        const double acc = (F - c * v) * im;
+        kv_out[e] = -acc;
+        klu_out[e] = -HW;
+        klv_out[e] = Lus[e] - c * w;
+        if (want_q) {
+          quad_update(qc, a.qo_inertia + e, -w * acc, probe);
+          if (has_damp && T.damp_slot[dof] >= 0) { if (damp_pd) quad_update(qc, a.qo_damp + e, -w * v, probe); else p_damp -= w * v; }
+          p_t0 += w * lm * lsd;
+        }
+      } else {
+        kv_out[e] = 0.0; klu_out[e] = 0.0; klv_out[e] = 0.0;
+        if (want_q) {
+          quad_update(qc, a.qo_inertia + e, 0.0, probe);
+          const int c = T.cons_slot[dof];
+          if (c >= 0 && T.drive_kind != DFX_DRIVE_ZERO) {
+            DriveEval de;
+            drive_eval(T.drive_kind, time, g_drive, true, de);
+            const double v0_ = T.drive_vec0[c], v1_ = T.drive_vec1[c];
+            p_t0 -= HW * (v0_ * de.sdot[0] + v1_ * de.sdot[1]);
+            for (int q = 0; q < ndp; ++q) p_dr[q] -= HW * (v0_ * de.dsdp[0][q] + v1_ * de.dsdp[1][q]);
+          }
+        }
+      }
+      if (want_q && j < 2) {
+        // centroid_node_vectors cotangent integrand of every node of this block, component j
+        for (int l = 0; l < npb; ++l) {
+          const int n = blk * npb + l;
+          double val = Gs[j * NN + n];
+          if (T.contact) {
+            const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
+            const double rx = cnv[n], ry = cnv[NN + n];
+            const double e1x = cnv[nn] - rx, e1y = cnv[NN + nn] - ry;   // own next edge (also nn's prev edge, reversed)
+            const double e2x = cnv[np] - rx, e2y = cnv[NN + np] - ry;   // own prev edge (also np's next edge, reversed)
+            const double i1 = 1.0 / (e1x * e1x + e1y * e1y), i2 = 1.0 / (e2x * e2x + e2y * e2y);
+            // d atan2(e)/d e = (-e_y, e_x)/|e|^2 ; component j
+            const double d1 = (j == 0 ? -e1y : e1x) * i1, d2 = (j == 0 ? -e2y : e2x) * i2;
+            // own edges: d/dr_n = -d/de ; as far end of nn's prev edge (e = r_n - r_nn = -e1): d/dr_n = +(-(-e1y), -e1x)/|e1|^2 = -d1
+            val += -Ga[n] * d1 - Ga[NN + n] * d2 - Ga[NN + nn] * d1 - Ga[np] * d2;
+          }
+          quad_update(qc, a.qo_cnv + j * NN + n, val, probe);
+        }
+      }
+    }
+    if (want_q) {
+      scal_update(qc, sc, SC_T0, p_t0);
+      if (has_damp && !damp_pd) scal_update(qc, sc, SC_DAMP, p_damp);
+      for (int q = 0; q < ndp; ++q) scal_update(qc, sc, SC_DRIVE + q, p_dr[q]);
+    }
+    return probe;
+  };
+
+  // stage values of DOF e -> shared stage arrays (time = real time of the stage)
+  auto put_stage = [&](int e, double u, double v, double lu, double lv, double time) {
+    const int j = e / NB, blk = e - j * NB;
+    const double im = invm[e];
+    if (im == 0.0) {
+      v = 0.0; lu = 0.0; lv = 0.0; u = 0.0;
+      const int c = T.cons_slot[3 * blk + j];
+      if (c >= 0 && T.drive_kind != DFX_DRIVE_ZERO) {
+        DriveEval de;
+        drive_eval(T.drive_kind, time, g_drive, false, de);
+        u = T.drive_vec0[c] * de.s[0] + T.drive_vec1[c] * de.s[1];
+      }
+    }
+    Us[e] = u; Vs[e] = v; Lus[e] = lu; Lvs[e] = lv; Ws[e] = lv * im;
+    if (j == 2) {
+      double sn, cs;
+      sincos(u, &sn, &cs);
+      Us[3 * NB + blk] = sn; Us[4 * NB + blk] = cs;
+    }
+  };
+
+  // total of a scalar leaf's per-warp partials
+  auto wtotal = [&](const double* wa, int which) {
+    double s = 0.0;
+    for (int w = 0; w < nwarp; ++w) s += wa[which * 32 + w];
+    return s;
+  };
+
+  long long n_steps = 0, n_acc = 0, n_rhs = 0;
+  int status = 0;
+  double h = 0.0;
+  const long long n_pad_total = a.aug_size;  // full size of the reference's augmented state
+  const double inv_n = 1.0 / (double)n_pad_total;
+
+  for (int i = a.n_t - 1; i >= 1 && status == 0; --i) {
+    // ---- restart: z0 = (ys[i], y_bar, t0_bar, args_bar) at s0 = -ts[i] --------------------------
+    const double s0 = -ts[i], s_target = -ts[i - 1];
+    const double* yi = ys + (long long)i * 2 * nf;
+    const double* gi = gg + (long long)i * 2 * nf;
+    for (int e = tid; e < ND; e += nthr) {
+      const int j = e / NB, blk = e - j * NB;
+      const int f = T.free_of_dof[3 * blk + j];
+      u0[e] = f >= 0 ? yi[f] : 0.0;
+      v0[e] = f >= 0 ? yi[nf + f] : 0.0;
+      put_stage(e, u0[e], v0[e], lu0[e], lv0[e], -s0);
+    }
+    qc.mode = 0;
+    aug_BC(-s0, kv, klu, klv);
+    n_rhs++;
+    // t_bar = func(ys[i], ts[i]) . g[i];  func = (v, acc) = (v0, -kv[0])
+    double pt = 0.0;
+    for (int e = tid; e < ND; e += nthr) {
+      if (invm[e] == 0.0) continue;
+      const int j = e / NB, blk = e - j * NB;
+      const int f = T.free_of_dof[3 * blk + j];
+      pt += v0[e] * gi[f] - kv[e] * gi[nf + f];
+    }
+    const double t_bar = block_sum(pt, red);
+    if (tid == 0) {
+      if (a.ts_bar) a.ts_bar[(long long)design * a.n_t + i] = t_bar;
+      Sq0[SC_T0] -= t_bar;
+    }
+    __syncthreads();
+    // ---- initial_step_size over the whole augmented vector ---------------------------------------
+    {
+      double sd0 = 0, sd1 = 0;
+      for (int e = tid; e < ND; e += nthr) {
+        if (invm[e] == 0.0) continue;
+        const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
+        const double slu = atol + fabs(lu0[e]) * rtol, slv = atol + fabs(lv0[e]) * rtol;
+        const double a0 = u0[e] / su, a1 = v0[e] / sv, a2 = lu0[e] / slu, a3 = lv0[e] / slv;
+        const double b0 = -v0[e] / su, b1 = kv[e] / sv, b2 = klu[e] / slu, b3 = klv[e] / slv;
+        sd0 += a0 * a0 + a1 * a1 + a2 * a2 + a3 * a3;
+        sd1 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+      }
+      for (int q = tid; q < NQ; q += nthr) {
+        const double s = atol + fabs(qc.q0[q]) * rtol;
+        const double a0 = qc.q0[q] / s, b0 = qc.k1[q] / s;
+        sd0 += a0 * a0; sd1 += b0 * b0;
+      }
+      if (tid < NSCAL) {
+        const double s = atol + fabs(Sq0[tid]) * rtol;
+        const double a0 = Sq0[tid] / s, b0 = wtotal(sc.wk1, tid) / s;
+        sd0 += a0 * a0; sd1 += b0 * b0;
+      }
+      const double d0 = sqrt(block_sum(sd0, red));
+      const double d1 = sqrt(block_sum(sd1, red));
+      const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+      for (int e = tid; e < ND; e += nthr)
+        put_stage(e, u0[e] - h0 * v0[e], v0[e] + h0 * kv[e], lu0[e] + h0 * klu[e], lv0[e] + h0 * klv[e], -(s0 + h0));
+      qc.mode = 7;
+      double sd2 = aug_BC(-(s0 + h0), kv + ND, klu + ND, klv + ND);
+      n_rhs++;
+      for (int e = tid; e < ND; e += nthr) {
+        if (invm[e] == 0.0) continue;
+        const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
+        const double slu = atol + fabs(lu0[e]) * rtol, slv = atol + fabs(lv0[e]) * rtol;
+        const double b0 = (-Vs[e] + v0[e]) / su, b1 = (kv[ND + e] - kv[e]) / sv;
+        const double b2 = (klu[ND + e] - klu[e]) / slu, b3 = (klv[ND + e] - klv[e]) / slv;
+        sd2 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
+      }
+      __syncthreads();  // per-warp probe partials (wk7) complete
+      if (tid < NSCAL) {
+        const double s = atol + fabs(Sq0[tid]) * rtol;
+        const double b0 = (wtotal(sc.wk7, tid) - wtotal(sc.wk1, tid)) / s;
+        sd2 += b0 * b0;
+      }
+      const double d2 = sqrt(block_sum(sd2, red)) / h0;
+      double h1;
+      if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+      else h1 = pow(0.01 / (a.init_step_variant == 0 ? d1 + d2 : fmax(d1, d2)), 0.2);
+      h = fmin(100.0 * h0, h1);
+    }
+    // ---- adaptive steps until s >= s_target --------------------------------------------------------
+    double s_cur = s0;
+    long long istep = 0;
+    bool done = !(s_cur < s_target);
+    while (!done) {
+      if (!(h > 0.0)) { status |= DFX_STATUS_DT_UNDERFLOW; break; }
+      if (istep >= a.max_steps) { status |= DFX_STATUS_MAX_STEPS; break; }
+      const double s_new = s_cur + h;
+      qc.h = h;
+      qc.crossing = !(s_new < s_target);
+      qc.x = (s_target - s_cur) / (s_new - s_cur);
+      double se = 0.0;
+#pragma unroll 1
+      for (int st = 0; st < 6; ++st) {
+        const double ha = h * tab.alpha[st], h2 = h * h, s_stage = s_cur + ha;
+        for (int e = tid; e < ND; e += nthr) {
+          double au = 0.0, av = 0.0, alu = 0.0, alv = 0.0;
+          for (int l = 0; l <= st; ++l) {
+            const double b = tab.beta[st][l];
+            const double k = kv[l * ND + e];
+            au = fma(tab.a2[st][l], k, au);
+            av = fma(b, k, av);
+            alu = fma(b, klu[l * ND + e], alu);
+            alv = fma(b, klv[l * ND + e], alv);
+          }
+          put_stage(e, u0[e] - ha * v0[e] - h2 * au, v0[e] + h * av, lu0[e] + h * alu, lv0[e] + h * alv, -s_stage);
+        }
+        const int kidx = st + 1;
+        qc.mode = kidx;
+        qc.cs = tab.c_sol[kidx]; qc.ce = tab.c_err[kidx]; qc.cm = tab.c_mid[kidx];
+        qc.cs0 = tab.c_sol[0]; qc.ce0 = tab.c_err[0]; qc.cm0 = tab.c_mid[0];
+        se += aug_BC(-s_stage, kv + kidx * ND, klu + kidx * ND, klv + kidx * ND);
+      }
+      n_rhs += 6;
+      // error of the dynamic entries
+      for (int e = tid; e < ND; e += nthr) {
+        if (invm[e] == 0.0) continue;
+        double eu = 0.0, ev = 0.0, elu = 0.0, elv = 0.0;
+#pragma unroll
+        for (int l = 0; l < 7; ++l) {
+          const double k = kv[l * ND + e];
+          eu = fma(tab.e2[l], k, eu);
+          ev = fma(tab.c_err[l], k, ev);
+          elu = fma(tab.c_err[l], klu[l * ND + e], elu);
+          elv = fma(tab.c_err[l], klv[l * ND + e], elv);
+        }
+        eu = -h * (tab.sum_err * v0[e] + h * eu);
+        ev *= h; elu *= h; elv *= h;
+        const double r0 = eu / (atol + rtol * fmax(fabs(u0[e]), fabs(Us[e])));
+        const double r1 = ev / (atol + rtol * fmax(fabs(v0[e]), fabs(Vs[e])));
+        const double r2 = elu / (atol + rtol * fmax(fabs(lu0[e]), fabs(Lus[e])));
+        const double r3 = elv / (atol + rtol * fmax(fabs(lv0[e]), fabs(Lvs[e])));
+        se += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
+      }
+      __syncthreads();  // per-warp scalar partials of the last stage complete
+      if (tid < NSCAL) {
+        const double q0 = Sq0[tid], k1 = wtotal(sc.wk1, tid), k7 = wtotal(sc.wk7, tid);
+        const double q1 = q0 + h * wtotal(sc.wsol, tid);
+        const double r = h * wtotal(sc.werr, tid) / (atol + rtol * fmax(fabs(q0), fabs(q1)));
+        se += r * r;
+        Sqnew[tid] = qc.crossing ? interp_eval(q0, q1, q0 + h * wtotal(sc.wmid, tid), h * k1, h * k7, qc.x) : q1;
+      }
+      const double ratio = sqrt(block_sum(se, red) * inv_n);
+      ++n_steps; ++istep;
+      if (!isfinite(ratio)) { status |= DFX_STATUS_NONFINITE; break; }
+      if (ratio <= 1.0) {
+        ++n_acc;
+        if (qc.crossing) {
+          // interval finished: keep the interpolated cotangents at s_target, add g[i-1]
+          const double* gp = gg + (long long)(i - 1) * 2 * nf;
+          for (int e = tid; e < ND; e += nthr) {
+            if (invm[e] == 0.0) continue;
+            const int j = e / NB, blk = e - j * NB;
+            const int f = T.free_of_dof[3 * blk + j];
+            double mlu = 0.0, mlv = 0.0;
+#pragma unroll
+            for (int l = 0; l < 7; ++l) {
+              mlu = fma(tab.c_mid[l], klu[l * ND + e], mlu);
+              mlv = fma(tab.c_mid[l], klv[l * ND + e], mlv);
+            }
+            const double nlu = interp_eval(lu0[e], Lus[e], lu0[e] + h * mlu, h * klu[e], h * klu[6 * ND + e], qc.x);
+            const double nlv = interp_eval(lv0[e], Lvs[e], lv0[e] + h * mlv, h * klv[e], h * klv[6 * ND + e], qc.x);
+            lu0[e] = nlu + gp[f];
+            lv0[e] = nlv + gp[nf + f];
+          }
+          done = true;
+        } else {
+          for (int e = tid; e < ND; e += nthr) {
+            u0[e] = Us[e]; v0[e] = Vs[e]; lu0[e] = Lus[e]; lv0[e] = Lvs[e];
+            kv[e] = kv[6 * ND + e]; klu[e] = klu[6 * ND + e]; klv[e] = klv[6 * ND + e];
+          }
+          if (tid < NSCAL) for (int w = 0; w < nwarp; ++w) sc.wk1[tid * 32 + w] = sc.wk7[tid * 32 + w];
+          double* tmp = qc.k1; qc.k1 = qc.k7; qc.k7 = tmp;
+        }
+        if (tid < NSCAL) Sq0[tid] = Sqnew[tid];
+        double* tmp = qc.q0; qc.q0 = qc.qnew; qc.qnew = tmp;
+        s_cur = s_new;
+      }
+      const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
+      const double factor = fmin(10.0, fmax(pow(ratio, -0.2) * 0.9, dfactor));
+      h = (ratio == 0.0) ? h * 10.0 : h * factor;
+      __syncthreads();
+    }
+  }
+
+  // ---- outputs ---------------------------------------------------------------------------------------
+  __syncthreads();
+  const double nanv = nan("");
+  const bool bad = status != 0;
+  for (int e = tid; e < ND; e += nthr) {
+    const int j = e / NB, blk = e - j * NB, dof = 3 * blk + j;
+    const int f = T.free_of_dof[dof];
+    if (a.grads.damping && has_damp && damp_pd) {
+      // entries of the damping leaf that sit on constrained DOFs have zero cotangent (q0 stays 0 there)
+      const int ds = T.damp_slot[dof];
+      if (ds >= 0) a.grads.damping[(long long)design * T.n_damped * 3 + ds] = bad ? nanv : qc.q0[a.qo_damp + e];
+    }
+    if (f < 0) continue;
+    if (a.y0_bar) {
+      a.y0_bar[(long long)design * 2 * nf + f] = bad ? nanv : lu0[e];
+      a.y0_bar[(long long)design * 2 * nf + nf + f] = bad ? nanv : lv0[e];
+    }
+    if (a.grads.inertia) a.grads.inertia[(long long)design * nf + f] = bad ? nanv : qc.q0[a.qo_inertia + e];
+  }
+  if (a.grads.centroid_node_vectors)
+    for (int n = tid; n < NN; n += nthr) {
+      a.grads.centroid_node_vectors[((long long)design * NN + n) * 2] = bad ? nanv : qc.q0[a.qo_cnv + n];
+      a.grads.centroid_node_vectors[((long long)design * NN + n) * 2 + 1] = bad ? nanv : qc.q0[a.qo_cnv + NN + n];
+    }
+  if (a.grads.reference_vector)
+    for (int b = tid; b < NBONDS; b += nthr) {
+      a.grads.reference_vector[((long long)design * NBONDS + b) * 2] = bad ? nanv : qc.q0[a.qo_ref + b];
+      a.grads.reference_vector[((long long)design * NBONDS + b) * 2 + 1] = bad ? nanv : qc.q0[a.qo_ref + NBONDS + b];
+    }
+  {
+    double* outs[3] = {a.grads.k_stretch, a.grads.k_shear, a.grads.k_rot};
+    const bool pb[3] = {ks_pb, ksh_pb, kr_pb};
+    const int qo[3] = {a.qo_ks, a.qo_ksh, a.qo_kr};
+    for (int k = 0; k < 3; ++k) {
+      if (!outs[k]) continue;
+      if (pb[k]) { for (int b = tid; b < NBONDS; b += nthr) outs[k][(long long)design * NBONDS + b] = bad ? nanv : qc.q0[qo[k] + b]; }
+      else if (tid == 0) outs[k][design] = bad ? nanv : Sq0[SC_KS + k];
+    }
+  }
+  if (tid == 0) {
+    if (a.grads.damping && has_damp && !damp_pd) a.grads.damping[design] = bad ? nanv : Sq0[SC_DAMP];
+    if (a.grads.contact && T.contact) for (int k = 0; k < 3; ++k) a.grads.contact[(long long)design * 3 + k] = bad ? nanv : Sq0[SC_CONTACT + k];
+    if (a.grads.drive) for (int k = 0; k < ndp; ++k) a.grads.drive[(long long)design * ndp + k] = bad ? nanv : Sq0[SC_DRIVE + k];
+    if (a.ts_bar) a.ts_bar[(long long)design * a.n_t] = bad ? nanv : Sq0[SC_T0];
+    if (a.stats) {
+      DfxStats st;
+      st.steps = n_steps; st.accepted = n_acc; st.rhs_evals = n_rhs; st.status = status; st.reserved = 0; st.last_dt = h;
+      a.stats[design] = st;
+    }
+  }
+}
+
+}  // namespace dfx

@@ -1,0 +1,400 @@
+// dfx_api.cu -- C ABI of libdfx.so (see include/dfx.h): topology handles, shared-memory
+// placement planning and kernel launches.  No torch / C++ types cross the boundary.
+#include <cstdarg>
+#include <cstdio>
+#include <cstring>
+#include <new>
+#include <vector>
+
+#include "dfx_adjoint.cuh"
+
+using namespace dfx;
+
+namespace {
+
+thread_local char g_err[512] = "";
+
+int fail(int code, const char* fmt, ...) {
+  va_list ap;
+  va_start(ap, fmt);
+  vsnprintf(g_err, sizeof(g_err), fmt, ap);
+  va_end(ap);
+  return code;
+}
+
+#define CUDA_TRY(x)                                                                                   \
+  do {                                                                                                \
+    cudaError_t e_ = (x);                                                                             \
+    if (e_ != cudaSuccess) return fail(DFX_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));    \
+  } while (0)
+
+constexpr size_t kSmemBytes = 232448;  // 227 KB: the opt-in maximum of one CTA on sm_100
+constexpr int kRedDoubles = 40;
+
+template <class T>
+cudaError_t upload(const std::vector<T>& h, T** d) {
+  *d = nullptr;
+  if (h.empty()) return cudaSuccess;
+  cudaError_t e = cudaMalloc((void**)d, h.size() * sizeof(T));
+  if (e != cudaSuccess) return e;
+  return cudaMemcpy(*d, h.data(), h.size() * sizeof(T), cudaMemcpyHostToDevice);
+}
+
+}  // namespace
+
+struct DfxTopology {
+  int device;
+  DevTopo dev;
+  std::vector<void*> allocs;
+  int sm_count;
+};
+
+namespace {
+
+int n_drive_params_of(int kind) {
+  switch (kind) {
+    case DFX_DRIVE_PULSE:
+    case DFX_DRIVE_HARMONIC: return 3;
+    case DFX_DRIVE_RAMP: return 2;
+    case DFX_DRIVE_STATIC_PULSE: return 5;
+    default: return 0;
+  }
+}
+
+// greedy placement: arrays in priority order go to shared memory while they fit
+template <int N>
+void plan(const long long (&sizes)[N], long long* off, size_t* smem_bytes, long long* scratch_doubles) {
+  long long s = kRedDoubles, g = 0;
+  const long long cap = (long long)(kSmemBytes / sizeof(double));
+  for (int i = 0; i < N; ++i) {
+    const long long n = (sizes[i] + 1) & ~1LL;  // keep 16-byte alignment
+    if (n == 0) { off[i] = 0; continue; }
+    if (s + n <= cap) { off[i] = s; s += n; }
+    else { off[i] = -(g + 1); g += n; }
+  }
+  *smem_bytes = (size_t)s * sizeof(double);
+  *scratch_doubles = g;
+}
+
+void forward_sizes(const DevTopo& T, long long (&sz)[FA_COUNT]) {
+  const long long NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds;
+  sz[FA_US] = 5 * NB; sz[FA_VS] = 3 * NB; sz[FA_FS] = 3 * NN; sz[FA_U0] = 3 * NB; sz[FA_V0] = 3 * NB;
+  sz[FA_KV] = 21 * NB; sz[FA_INVM] = 3 * NB; sz[FA_CD] = 3 * NB; sz[FA_BONDC] = 4 * NBONDS; sz[FA_CNV] = 2 * NN;
+  sz[FA_ALPHA] = T.contact ? 2 * NN : 0;
+}
+
+struct QuadLayout { int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, nq; };
+
+QuadLayout quad_layout(const DevTopo& T, const DfxParams& p) {
+  QuadLayout q;
+  int o = 0;
+  q.qo_cnv = o; o += 2 * T.n_nodes;
+  q.qo_ref = o; o += 2 * T.n_bonds;
+  q.qo_ks = o; o += p.k_per_bond[0] ? T.n_bonds : 0;
+  q.qo_ksh = o; o += p.k_per_bond[1] ? T.n_bonds : 0;
+  q.qo_kr = o; o += p.k_per_bond[2] ? T.n_bonds : 0;
+  q.qo_damp = o; o += (T.n_damped > 0 && p.damping_per_dof) ? 3 * T.n_blocks : 0;
+  q.qo_inertia = o; o += 3 * T.n_blocks;
+  q.nq = o;
+  return q;
+}
+
+void adjoint_sizes(const DevTopo& T, const QuadLayout& q, long long (&sz)[AA_COUNT]) {
+  const long long NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds;
+  sz[AA_US] = 5 * NB; sz[AA_WS] = 3 * NB; sz[AA_VS] = 3 * NB; sz[AA_LUS] = 3 * NB; sz[AA_LVS] = 3 * NB;
+  sz[AA_FS] = 3 * NN; sz[AA_HS] = 3 * NN; sz[AA_GS] = 2 * NN; sz[AA_GA] = T.contact ? 2 * NN : 0;
+  sz[AA_SC] = 2 * NSCAL + 5 * NSCAL * 32;
+  sz[AA_INVM] = 3 * NB; sz[AA_CD] = 3 * NB;
+  sz[AA_U0] = 3 * NB; sz[AA_V0] = 3 * NB; sz[AA_LU0] = 3 * NB; sz[AA_LV0] = 3 * NB;
+  sz[AA_KV] = 21 * NB; sz[AA_KLU] = 21 * NB; sz[AA_KLV] = 21 * NB;
+  sz[AA_BONDC] = 4 * NBONDS; sz[AA_CNV] = 2 * NN; sz[AA_ALPHA] = T.contact ? 2 * NN : 0;
+  for (int i = AA_QSOL; i <= AA_QNEW; ++i) sz[i] = q.nq;
+}
+
+int pick_threads(const DevTopo& T, int requested) {
+  int t = requested;
+  if (t <= 0) {
+    // bonds dominate the cost: choose the CTA size (multiple of 32, <= 512) that wastes the fewest
+    // lanes in the bond loop, breaking ties towards more threads
+    double best = 1e30;
+    t = 128;
+    for (int c = 128; c <= 512; c += 32) {
+      const int rounds_b = (T.n_bonds + c - 1) / c, rounds_d = (3 * T.n_blocks + c - 1) / c;
+      const double cost = 3.0 * rounds_b + 1.0 * rounds_d;  // relative phase weights
+      if (cost <= best) { best = cost; t = c; }
+    }
+  }
+  t = (t + 31) / 32 * 32;
+  if (t < 32) t = 32;
+  if (t > 512) t = 512;
+  return t;
+}
+
+int check_params(const DevTopo& T, const DfxParams* p) {
+  if (!p) return fail(DFX_ERR_INVALID, "params is NULL");
+  if (!p->centroid_node_vectors.ptr || !p->reference_vector.ptr || !p->k_stretch.ptr || !p->k_shear.ptr || !p->k_rot.ptr ||
+      !p->inertia.ptr)
+    return fail(DFX_ERR_INVALID, "a required parameter leaf is NULL");
+  if (T.contact && !p->contact.ptr) return fail(DFX_ERR_INVALID, "topology has contact but params.contact is NULL");
+  if (T.n_drive_params > 0 && !p->drive.ptr) return fail(DFX_ERR_INVALID, "drive signal needs params.drive");
+  return DFX_OK;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* dfx_last_error(void) { return g_err; }
+const char* dfx_version(void) { return "difflexmm_b200 libdfx 0.1 (sm_100a)"; }
+int dfx_drive_n_params(int kind) { return n_drive_params_of(kind); }
+int dfx_topology_n_free(const DfxTopology* t) { return t ? t->dev.n_free : -1; }
+
+int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out) {
+  if (!d || !out) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (d->n_blocks <= 0 || d->n_npb < 2 || d->n_bonds < 0) return fail(DFX_ERR_INVALID, "bad sizes");
+  if (d->bond_energy != DFX_BOND_LIGAMENT && d->bond_energy != DFX_BOND_LINEARIZED)
+    return fail(DFX_ERR_UNSUPPORTED, "unknown bond energy %d", d->bond_energy);
+  if (d->drive_kind < DFX_DRIVE_ZERO || d->drive_kind > DFX_DRIVE_STATIC_PULSE)
+    return fail(DFX_ERR_UNSUPPORTED, "unknown drive kind %d", d->drive_kind);
+  if (d->load_kind < DFX_LOAD_NONE || d->load_kind > DFX_LOAD_SECH2)
+    return fail(DFX_ERR_UNSUPPORTED, "unknown load kind %d", d->load_kind);
+  const int n_dof = 3 * d->n_blocks, n_nodes = d->n_blocks * d->n_npb;
+  std::vector<int> cons_slot(n_dof, -1), free_of_dof(n_dof, -1), damp_slot(n_dof, -1), free_dofs, node_used(n_nodes, 0);
+  std::vector<double> v0(d->n_constrained > 0 ? d->n_constrained : 1, 0.0), v1(v0), load_mul(n_dof, 0.0);
+  for (int c = 0; c < d->n_constrained; ++c) {
+    const int dof = d->constrained_dofs[c];
+    if (dof < 0 || dof >= n_dof) return fail(DFX_ERR_INVALID, "constrained DOF %d out of range", dof);
+    if (cons_slot[dof] >= 0) return fail(DFX_ERR_INVALID, "constrained DOF %d listed twice", dof);
+    cons_slot[dof] = c;
+    if (d->drive_vec0) v0[c] = d->drive_vec0[c];
+    if (d->drive_vec1) v1[c] = d->drive_vec1[c];
+  }
+  for (int i = 0; i < n_dof; ++i)
+    if (cons_slot[i] < 0) { free_of_dof[i] = (int)free_dofs.size(); free_dofs.push_back(i); }
+  for (int k = 0; k < d->n_damped; ++k) {
+    const int blk = d->damped_blocks[k];
+    if (blk < 0 || blk >= d->n_blocks) return fail(DFX_ERR_INVALID, "damped block %d out of range", blk);
+    for (int j = 0; j < 3; ++j) damp_slot[3 * blk + j] = 3 * k + j;
+  }
+  if (d->load_kind != DFX_LOAD_NONE)
+    for (int l = 0; l < d->n_loaded; ++l) {
+      const int dof = d->loaded_dofs[l];
+      if (dof < 0 || dof >= n_dof) return fail(DFX_ERR_INVALID, "loaded DOF %d out of range", dof);
+      load_mul[dof] = d->load_vec ? d->load_vec[l] : 1.0;
+    }
+  std::vector<int2> bn(d->n_bonds), bb(d->n_bonds);
+  for (int b = 0; b < d->n_bonds; ++b) {
+    const int na = d->bond_nodes[2 * b], nb = d->bond_nodes[2 * b + 1];
+    if (na < 0 || na >= n_nodes || nb < 0 || nb >= n_nodes) return fail(DFX_ERR_INVALID, "bond %d refers to a node out of range", b);
+    if (node_used[na]++ || node_used[nb]++)
+      return fail(DFX_ERR_UNSUPPORTED,
+                  "a polygon vertex belongs to more than one bond (bond %d); the slot-based force assembly "
+                  "requires at most one bond per vertex, as in every geometry class of the reference", b);
+    bn[b] = make_int2(na, nb);
+    bb[b] = make_int2(na / d->n_npb, nb / d->n_npb);
+  }
+  int cur = 0;
+  CUDA_TRY(cudaGetDevice(&cur));
+  CUDA_TRY(cudaSetDevice(device));
+  DfxTopology* t = new (std::nothrow) DfxTopology();
+  if (!t) return fail(DFX_ERR_INVALID, "out of host memory");
+  t->device = device;
+  DevTopo& D = t->dev;
+  std::memset(&D, 0, sizeof(D));
+  D.n_blocks = d->n_blocks; D.n_npb = d->n_npb; D.n_bonds = d->n_bonds; D.n_nodes = n_nodes; D.n_dof = n_dof;
+  D.n_free = (int)free_dofs.size(); D.n_cons = d->n_constrained;
+  D.bond_energy = d->bond_energy; D.contact = d->contact ? 1 : 0; D.drive_kind = d->drive_kind;
+  D.load_kind = d->load_kind; D.n_drive_params = n_drive_params_of(d->drive_kind); D.n_damped = d->n_damped;
+  for (int i = 0; i < DFX_MAX_LOAD_CONSTS; ++i) D.load_consts[i] = d->load_consts[i];
+  int2 *dbn, *dbb; int *dfo, *dcs, *dds, *dfd; double *dv0, *dv1, *dlm;
+  cudaError_t e = cudaSuccess;
+  if (e == cudaSuccess) e = upload(bn, &dbn);
+  if (e == cudaSuccess) e = upload(bb, &dbb);
+  if (e == cudaSuccess) e = upload(free_of_dof, &dfo);
+  if (e == cudaSuccess) e = upload(cons_slot, &dcs);
+  if (e == cudaSuccess) e = upload(damp_slot, &dds);
+  if (e == cudaSuccess) e = upload(free_dofs, &dfd);
+  if (e == cudaSuccess) e = upload(v0, &dv0);
+  if (e == cudaSuccess) e = upload(v1, &dv1);
+  if (e == cudaSuccess) e = upload(load_mul, &dlm);
+  if (e != cudaSuccess) { delete t; cudaSetDevice(cur); return fail(DFX_ERR_CUDA, "topology upload failed: %s", cudaGetErrorString(e)); }
+  D.bond_nodes = dbn; D.bond_blocks = dbb; D.free_of_dof = dfo; D.cons_slot = dcs; D.damp_slot = dds; D.free_dofs = dfd;
+  D.drive_vec0 = dv0; D.drive_vec1 = dv1; D.load_mul = dlm;
+  t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm};
+  cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
+  cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaFuncSetAttribute(adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaSetDevice(cur);
+  *out = t;
+  return DFX_OK;
+}
+
+void dfx_topology_destroy(DfxTopology* t) {
+  if (!t) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(t->device);
+  for (void* p : t->allocs) if (p) cudaFree(p);
+  cudaSetDevice(cur);
+  delete t;
+}
+
+size_t dfx_forward_workspace_bytes(const DfxTopology* t, int batch) {
+  if (!t) return 0;
+  long long sz[FA_COUNT], off[FA_COUNT], g;
+  size_t smem;
+  forward_sizes(t->dev, sz);
+  plan(sz, off, &smem, &g);
+  return (size_t)g * sizeof(double) * (size_t)batch;
+}
+
+size_t dfx_adjoint_workspace_bytes(const DfxTopology* t, int batch) {
+  if (!t) return 0;
+  // worst case over the leaf forms (per-bond stiffnesses, per-DOF damping)
+  DfxParams p;
+  std::memset(&p, 0, sizeof(p));
+  p.k_per_bond[0] = p.k_per_bond[1] = p.k_per_bond[2] = 1;
+  p.damping_per_dof = 1;
+  QuadLayout q = quad_layout(t->dev, p);
+  long long sz[AA_COUNT], off[AA_COUNT], g;
+  size_t smem;
+  adjoint_sizes(t->dev, q, sz);
+  plan(sz, off, &smem, &g);
+  return (size_t)g * sizeof(double) * (size_t)batch;
+}
+
+int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const double* y0, int64_t y0_bstride,
+                const double* ts, int64_t ts_bstride, int n_t, double rtol, double atol, const DfxOptions* opt,
+                double* ys, DfxStats* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!t || !y0 || !ts || !ys) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (batch <= 0 || n_t < 1) return fail(DFX_ERR_INVALID, "batch and n_t must be positive");
+  if (int rc = check_params(t->dev, params)) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  FwdArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.topo = t->dev; a.p = *params; a.tab = make_tableau();
+  long long sz[FA_COUNT], g;
+  size_t smem;
+  forward_sizes(t->dev, sz);
+  plan(sz, a.place.off, &smem, &g);
+  a.y0 = y0; a.y0_bstride = y0_bstride; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t;
+  a.rtol = rtol; a.atol = atol;
+  a.init_step_variant = opt ? opt->init_step_variant : 0;
+  a.max_steps = (opt && opt->max_steps > 0) ? opt->max_steps : (1LL << 40);
+  a.ys = ys; a.stats = stats;
+  a.scratch_per_design = g;
+  bool own_ws = false;
+  if (g > 0) {
+    const size_t need = (size_t)g * sizeof(double) * (size_t)batch;
+    if (workspace) {
+      if (workspace_bytes < need) return fail(DFX_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, need);
+      a.scratch = (double*)workspace;
+    } else {
+      CUDA_TRY(cudaMallocAsync((void**)&a.scratch, need, stream));
+      own_ws = true;
+    }
+  }
+  const int threads = pick_threads(t->dev, opt ? opt->threads : 0);
+  forward_kernel<<<batch, threads, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (own_ws) cudaFreeAsync(a.scratch, stream);
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "forward_kernel launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
+
+int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
+                int64_t ts_bstride, int n_t, const double* g_, double rtol, double atol, int64_t aug_size,
+                const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
+                void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!t || !ys || !ts || !g_) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (batch <= 0 || n_t < 1) return fail(DFX_ERR_INVALID, "batch and n_t must be positive");
+  if (int rc = check_params(t->dev, params)) return rc;
+  cudaStream_t stream = (cudaStream_t)stream_;
+  const DevTopo& T = t->dev;
+  AdjArgs a;
+  std::memset(&a, 0, sizeof(a));
+  a.topo = T; a.p = *params; a.tab = make_tableau();
+  QuadLayout q = quad_layout(T, *params);
+  a.qo_cnv = q.qo_cnv; a.qo_ref = q.qo_ref; a.qo_ks = q.qo_ks; a.qo_ksh = q.qo_ksh; a.qo_kr = q.qo_kr;
+  a.qo_damp = q.qo_damp; a.qo_inertia = q.qo_inertia; a.nq = q.nq;
+  long long sz[AA_COUNT], g;
+  size_t smem;
+  adjoint_sizes(T, q, sz);
+  plan(sz, a.place.off, &smem, &g);
+  a.ys = ys; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t; a.g = g_;
+  a.rtol = rtol; a.atol = atol;
+  if (aug_size <= 0) {
+    // count the leaves listed in DfxParams: y, y_bar, t0_bar, then every leaf
+    long long n = 4LL * T.n_free + 1;
+    n += 2LL * T.n_nodes + 2LL * T.n_bonds + T.n_free;
+    for (int k = 0; k < 3; ++k) n += params->k_per_bond[k] ? T.n_bonds : 1;
+    if (T.n_damped > 0 && params->damping.ptr) n += params->damping_per_dof ? 3LL * T.n_damped : 1;
+    if (T.contact) n += 3;
+    n += T.n_drive_params;
+    aug_size = n;
+  }
+  a.aug_size = aug_size;
+  a.init_step_variant = opt ? opt->init_step_variant : 0;
+  a.max_steps = (opt && opt->max_steps > 0) ? opt->max_steps : (1LL << 40);
+  a.y0_bar = y0_bar; a.ts_bar = ts_bar;
+  if (grads) a.grads = *grads;
+  a.stats = stats;
+  a.scratch_per_design = g;
+  bool own_ws = false;
+  if (g > 0) {
+    const size_t need = (size_t)g * sizeof(double) * (size_t)batch;
+    if (workspace) {
+      if (workspace_bytes < need) return fail(DFX_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, need);
+      a.scratch = (double*)workspace;
+    } else {
+      CUDA_TRY(cudaMallocAsync((void**)&a.scratch, need, stream));
+      own_ws = true;
+    }
+  }
+  const int threads = pick_threads(T, opt ? opt->threads : 0);
+  adjoint_kernel<<<batch, threads, smem, stream>>>(a);
+  cudaError_t e = cudaGetLastError();
+  if (own_ws) cudaFreeAsync(a.scratch, stream);
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "adjoint_kernel launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
+
+}  // extern "C"
+
+// ---- field reconstruction (dynamics.py:129-136, 169-182 without the dense Jacobian) ------------
+namespace {
+__global__ void expand_fields_kernel(DevTopo T, DfxLeaf drive, const double* ys, const double* ts, long long ts_bstride, int n_t,
+                                     double* fields) {
+  const int design = blockIdx.y, i = blockIdx.x;
+  const int nf = T.n_free, nd = T.n_dof;
+  const double* y = ys + ((long long)design * n_t + i) * 2 * nf;
+  double* o = fields + ((long long)design * n_t + i) * 2 * nd;
+  const double t = ts[(long long)design * ts_bstride + i];
+  const double* dp = drive.ptr ? drive.ptr + (long long)design * drive.bstride : nullptr;
+  DriveEval de;
+  drive_eval(T.drive_kind, t, dp, true, de);
+  for (int dof = threadIdx.x; dof < nd; dof += blockDim.x) {
+    const int f = T.free_of_dof[dof];
+    double u, v;
+    if (f >= 0) { u = y[f]; v = y[nf + f]; }
+    else {
+      const int c = T.cons_slot[dof];
+      u = T.drive_vec0[c] * de.s[0] + T.drive_vec1[c] * de.s[1];
+      v = T.drive_vec0[c] * de.sdot[0] + T.drive_vec1[c] * de.sdot[1];
+    }
+    o[dof] = u;
+    o[nd + dof] = v;
+  }
+}
+}  // namespace
+
+extern "C" int dfx_expand_fields(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
+                                 int64_t ts_bstride, int n_t, double* fields, void* stream_) {
+  if (!t || !params || !ys || !ts || !fields) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (t->dev.n_drive_params > 0 && !params->drive.ptr) return fail(DFX_ERR_INVALID, "drive signal needs params.drive");
+  dim3 grid(n_t, batch);
+  expand_fields_kernel<<<grid, 256, 0, (cudaStream_t)stream_>>>(t->dev, params->drive, ys, ts, ts_bstride, n_t, fields);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "expand_fields launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}

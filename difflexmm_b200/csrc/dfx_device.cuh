@@ -1,0 +1,339 @@
+// dfx_device.cuh -- device-side building blocks shared by the forward and adjoint kernels:
+// dual numbers, the analytic per-bond energy gradient (reference energy.py:120-176, :70-117,
+// :204-219, :333-361 written out in closed form), drive / load signals
+//  and the Dormand-Prince tableau of jax.experimental.ode.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <math.h>
+#include <stdint.h>
+
+#include "../../include/dfx.h"
+
+namespace dfx {
+
+constexpr double kPi = 3.14159265358979323846;
+
+// ------------------------------------------------------------------------------------------
+// Dormand-Prince 5(4) as used by jax.experimental.ode (runge_kutta_step / interp_fit_dopri).
+// Because du/dt = v, the displacement stages are expressed through the stored velocity
+// derivatives only:  u_s = u0 + h*ALPHA[s]*v0 + h^2 * sum_l A2[s][l]*kv_l   (A2 = beta*beta),
+// which removes the seven displacement k-vectors from on-chip storage.
+// ------------------------------------------------------------------------------------------
+struct Tableau {
+  double alpha[6];
+  double beta[6][6];
+  double c_sol[7], c_err[7], c_mid[7];
+  double a2[6][6];                    // u-stage coefficients on kv_l (h^2)
+  double s2[7], e2[7], m2[7];         // same for solution / error / midpoint combos
+  double sum_sol, sum_err, sum_mid;   // sums of c_* (coefficient of h*v0)
+};
+
+__host__ inline Tableau make_tableau() {
+  Tableau t = {};
+  const double alpha[6] = {1 / 5., 3 / 10., 4 / 5., 8 / 9., 1., 1.};
+  const double beta[6][6] = {
+      {1 / 5., 0, 0, 0, 0, 0},
+      {3 / 40., 9 / 40., 0, 0, 0, 0},
+      {44 / 45., -56 / 15., 32 / 9., 0, 0, 0},
+      {19372 / 6561., -25360 / 2187., 64448 / 6561., -212 / 729., 0, 0},
+      {9017 / 3168., -355 / 33., 46732 / 5247., 49 / 176., -5103 / 18656., 0},
+      {35 / 384., 0, 500 / 1113., 125 / 192., -2187 / 6784., 11 / 84.}};
+  const double c_sol[7] = {35 / 384., 0, 500 / 1113., 125 / 192., -2187 / 6784., 11 / 84., 0};
+  const double c_err[7] = {35 / 384. - 1951 / 21600., 0, 500 / 1113. - 22642 / 50085., 125 / 192. - 451 / 720.,
+                           -2187 / 6784. - -12231 / 42400., 11 / 84. - 649 / 6300., -1. / 60.};
+  const double c_mid[7] = {6025192743. / 30085553152. / 2, 0, 51252292925. / 65400821598. / 2,
+                           -2691868925. / 45128329728. / 2, 187940372067. / 1594534317056. / 2,
+                           -1776094331. / 19743644256. / 2, 11237099. / 235043384. / 2};
+  for (int i = 0; i < 6; ++i) {
+    t.alpha[i] = alpha[i];
+    for (int j = 0; j < 6; ++j) t.beta[i][j] = beta[i][j];
+  }
+  for (int j = 0; j < 7; ++j) { t.c_sol[j] = c_sol[j]; t.c_err[j] = c_err[j]; t.c_mid[j] = c_mid[j]; }
+  // ku_1 = v0 ; ku_j = v0 + h * sum_l beta[j-2][l] kv_l   (j = 2..7, 1-based k index)
+  // => sum_j w_j ku_j = (sum_j w_j) v0 + h * sum_l (sum_{j>l} w_j beta[j-2][l-1]) kv_l
+  auto fold = [&](const double* w, int nw, double* out, double& wsum) {
+    long double s = 0;
+    for (int j = 0; j < nw; ++j) s += w[j];
+    wsum = (double)s;
+    for (int l = 0; l < 7; ++l) {
+      long double acc = 0;
+      for (int j = l + 1; j < nw; ++j) acc += (long double)w[j] * (long double)(l < 6 ? beta[j - 1][l] : 0.0);
+      out[l] = (double)acc;
+    }
+  };
+  for (int s = 0; s < 6; ++s) {
+    double w[7] = {0, 0, 0, 0, 0, 0, 0}, out[7], ws;
+    for (int j = 0; j <= s; ++j) w[j] = beta[s][j];
+    fold(w, s + 1, out, ws);
+    for (int l = 0; l < 6; ++l) t.a2[s][l] = out[l];
+  }
+  fold(c_sol, 7, t.s2, t.sum_sol);
+  fold(c_err, 7, t.e2, t.sum_err);
+  fold(c_mid, 7, t.m2, t.sum_mid);
+  return t;
+}
+
+// ------------------------------------------------------------------------------------------
+// dual numbers: value + one directional derivative (forward mode over the analytic gradient)
+// ------------------------------------------------------------------------------------------
+struct Dual {
+  double v, d;
+  __device__ __forceinline__ Dual() {}
+  __device__ __forceinline__ Dual(double v_) : v(v_), d(0.0) {}
+  __device__ __forceinline__ Dual(double v_, double d_) : v(v_), d(d_) {}
+};
+__device__ __forceinline__ Dual operator+(Dual a, Dual b) { return Dual(a.v + b.v, a.d + b.d); }
+__device__ __forceinline__ Dual operator-(Dual a, Dual b) { return Dual(a.v - b.v, a.d - b.d); }
+__device__ __forceinline__ Dual operator-(Dual a) { return Dual(-a.v, -a.d); }
+__device__ __forceinline__ Dual operator*(Dual a, Dual b) { return Dual(a.v * b.v, fma(a.v, b.d, a.d * b.v)); }
+__device__ __forceinline__ Dual operator*(Dual a, double b) { return Dual(a.v * b, a.d * b); }
+__device__ __forceinline__ Dual operator*(double b, Dual a) { return Dual(a.v * b, a.d * b); }
+__device__ __forceinline__ Dual operator+(Dual a, double b) { return Dual(a.v + b, a.d); }
+__device__ __forceinline__ Dual operator-(Dual a, double b) { return Dual(a.v - b, a.d); }
+__device__ __forceinline__ Dual operator/(Dual a, Dual b) {
+  double inv = 1.0 / b.v;
+  double q = a.v * inv;
+  return Dual(q, (a.d - q * b.d) * inv);
+}
+__device__ __forceinline__ double val(double a) { return a; }
+__device__ __forceinline__ double val(Dual a) { return a.v; }
+__device__ __forceinline__ double dot_part(double) { return 0.0; }
+__device__ __forceinline__ double dot_part(Dual a) { return a.d; }
+
+// reciprocal and reciprocal square root helpers
+__device__ __forceinline__ double recipT(double a) { return 1.0 / a; }
+__device__ __forceinline__ Dual recipT(Dual a) {
+  double inv = 1.0 / a.v;
+  return Dual(inv, -a.d * inv * inv);
+}
+__device__ __forceinline__ double sqrtT(double a) { return sqrt(a); }
+__device__ __forceinline__ Dual sqrtT(Dual a) {
+  double s = sqrt(a.v);
+  return Dual(s, 0.5 * a.d / s);
+}
+// atan2 with the derivative expressed through a supplied 1/(x^2+y^2)
+__device__ __forceinline__ double atan2T(double y, double x, double) { return atan2(y, x); }
+__device__ __forceinline__ Dual atan2T(Dual y, Dual x, Dual inv_r2) {
+  return Dual(atan2(y.v, x.v), (x.v * y.d - y.v * x.d) * inv_r2.v);
+}
+// jnp.mod(a + pi, 2 pi) - pi on the value; derivative 1
+__device__ __forceinline__ double wrap_value(double a) {
+  const double two_pi = 2.0 * kPi;
+  double m = a + kPi;
+  m = m - two_pi * floor(m / two_pi);
+  return m - kPi;
+}
+__device__ __forceinline__ double wrapT(double a) { return wrap_value(a); }
+__device__ __forceinline__ Dual wrapT(Dual a) { return Dual(wrap_value(a.v), a.d); }
+
+// ------------------------------------------------------------------------------------------
+// per-bond gradient
+// ------------------------------------------------------------------------------------------
+template <class T>
+struct BlockState {  // one rigid unit at the current stage: displacement, rotation, sin/cos
+  T x, y, th, s, c;
+};
+
+struct BondConst {  // per design and bond, precomputed once per launch
+  double r0x, r0y, L0, phi0;
+};
+
+template <class T>
+struct BondOut {
+  T f1[3], f2[3];        // dE/d(x,y,theta) of block 1 and block 2
+  T gr1[2], gr2[2];      // dE/d(centroid_node_vector) of node 1 / node 2
+  T gr0[2];              // dE/d(reference_vector)
+  T gks, gksh, gkr;      // dE/d(k_stretch, k_shear, k_rot)
+};
+
+// contact energy of one void angle psi (reference energy.py:333-361) -- derivative w.r.t. psi and,
+// optionally, w.r.t. (min_angle, cutoff_angle, k_contact).  jnp.where semantics: inactive => 0.
+template <class T>
+__device__ __forceinline__ bool contact_term(T psi, double tmin, double tcut, double kc, T& dpsi, T& dmin, T& dcut, T& dkc) {
+  const double pv = val(psi);
+  if (!(pv < tmin) && pv < tcut) {
+    const double w = tcut - tmin;
+    T x = (psi - tcut) * (1.0 / w);
+    T ip = recipT(x + 1.0), im = recipT(x - 1.0);
+    T h = ip - im - 2.0;
+    T hp = im * im - ip * ip;
+    dpsi = hp * (kc * 0.25 * w);
+    dkc = h * (w * w * 0.25);
+    dcut = (h * (2.0 * w) - hp * (x + 1.0) * w) * (kc * 0.25);
+    dmin = (hp * x * w - h * (2.0 * w)) * (kc * 0.25);
+    return true;
+  }
+  dpsi = T(0.0); dmin = T(0.0); dcut = T(0.0); dkc = T(0.0);
+  return false;
+}
+
+template <class T, bool PARAMS>
+__device__ __forceinline__ void bond_gradient(int energy_kind, const BlockState<T>& b1, const BlockState<T>& b2,
+                                              double r1x, double r1y, double r2x, double r2y, const BondConst& bc,
+                                              double ks, double ksh, double kr, BondOut<T>& o) {
+  // node displacements u = u_c + (R(theta) - I) r   (kinematics.py:24-31)
+  T c1m = b1.c - 1.0, c2m = b2.c - 1.0;
+  T n1x = b1.x + c1m * r1x - b1.s * r1y;
+  T n1y = b1.y + b1.s * r1x + c1m * r1y;
+  T n2x = b2.x + c2m * r2x - b2.s * r2y;
+  T n2y = b2.y + b2.s * r2x + c2m * r2y;
+  T dUx = n2x - n1x, dUy = n2y - n1y;
+  // d(node)/d(theta) = R'(theta) r
+  T t1x = -(b1.s * r1x) - b1.c * r1y, t1y = b1.c * r1x - b1.s * r1y;
+  T t2x = -(b2.s * r2x) - b2.c * r2y, t2y = b2.c * r2x - b2.s * r2y;
+  T dth = b2.th - b1.th;
+  T mean = (b2.th + b1.th) * 0.5;
+  const double L0 = bc.L0, L0sq = L0 * L0;
+  T gdx, gdy, tq;  // dE/d(dU) and dE/d(mean rotation)
+  if (energy_kind == DFX_BOND_LIGAMENT) {
+    T dx = dUx + bc.r0x, dy = dUy + bc.r0y;
+    T L2 = dx * dx + dy * dy;
+    T iL2 = recipT(L2);
+    T L = sqrtT(L2);
+    T gam = wrapT(atan2T(dy, dx, iL2) - bc.phi0 - mean);
+    T ext = L - L0;
+    T A = ext * ks * L * iL2;  // ks (L-L0)/L
+    T M = gam * (ksh * L0sq);  // dE/dgamma
+    T Bc = M * iL2;
+    gdx = A * dx - Bc * dy;
+    gdy = A * dy + Bc * dx;
+    tq = -M;
+    if (PARAMS) {
+      T dE_dL0 = gam * gam * (ksh * L0) - ext * ks;
+      o.gr0[0] = gdx + dE_dL0 * (bc.r0x / L0) + M * (bc.r0y / L0sq);
+      o.gr0[1] = gdy + dE_dL0 * (bc.r0y / L0) - M * (bc.r0x / L0sq);
+      o.gks = ext * ext * 0.5;
+      o.gksh = gam * gam * (0.5 * L0sq);
+    }
+  } else {
+    const double iL0 = 1.0 / L0;
+    T dotp = dUx * bc.r0x + dUy * bc.r0y;
+    T crs = dUy * bc.r0x - dUx * bc.r0y;
+    T ea = dotp * iL0;
+    T es = crs * iL0 - mean * L0;
+    T a = ea * ks, s = es * ksh;
+    gdx = a * (bc.r0x * iL0) - s * (bc.r0y * iL0);
+    gdy = a * (bc.r0y * iL0) + s * (bc.r0x * iL0);
+    tq = -(s * L0);
+    if (PARAMS) {
+      const double iL03 = iL0 * iL0 * iL0;
+      T dea0 = dUx * iL0 - dotp * (bc.r0x * iL03), dea1 = dUy * iL0 - dotp * (bc.r0y * iL03);
+      T des0 = dUy * iL0 - crs * (bc.r0x * iL03) - mean * (bc.r0x * iL0);
+      T des1 = -(dUx * iL0) - crs * (bc.r0y * iL03) - mean * (bc.r0y * iL0);
+      o.gr0[0] = a * dea0 + s * des0;
+      o.gr0[1] = a * dea1 + s * des1;
+      o.gks = ea * ea * 0.5;
+      o.gksh = es * es * 0.5;
+    }
+  }
+  T bend = dth * kr;
+  o.f1[0] = -gdx; o.f1[1] = -gdy;
+  o.f1[2] = tq * 0.5 - (gdx * t1x + gdy * t1y) - bend;
+  o.f2[0] = gdx; o.f2[1] = gdy;
+  o.f2[2] = tq * 0.5 + (gdx * t2x + gdy * t2y) + bend;
+  if (PARAMS) {
+    o.gkr = dth * dth * 0.5;
+    o.gr1[0] = -(c1m * gdx + b1.s * gdy);
+    o.gr1[1] = b1.s * gdx - c1m * gdy;
+    o.gr2[0] = c2m * gdx + b2.s * gdy;
+    o.gr2[1] = c2m * gdy - b2.s * gdx;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// drive / load signals
+// ------------------------------------------------------------------------------------------
+struct DriveEval {
+  double s[2], sdot[2], dsdp[2][DFX_MAX_DRIVE_PARAMS];
+};
+
+__device__ __forceinline__ void pulse_eval(double tau, double A, double f, bool windowed, bool want_grad, double& s,
+                                           double& ds_dtau, double& ds_dA, double& ds_df) {
+  const bool on = (tau > 0.0) && (!windowed || tau < 1.0 / f);
+  s = ds_dtau = ds_dA = ds_df = 0.0;
+  if (on) {
+    const double ph = 2.0 * kPi * f * tau;
+    double sn, cs;
+    sincos(ph, &sn, &cs);
+    const double shape = (1.0 - cs) * 0.5;
+    s = A * shape;
+    if (want_grad) {
+      ds_dA = shape;
+      ds_dtau = A * kPi * f * sn;
+      ds_df = A * kPi * tau * sn;
+    }
+  }
+}
+
+__device__ inline void drive_eval(int kind, double t, const double* p, bool want_grad, DriveEval& e) {
+  e.s[0] = e.s[1] = e.sdot[0] = e.sdot[1] = 0.0;
+#pragma unroll
+  for (int j = 0; j < DFX_MAX_DRIVE_PARAMS; ++j) e.dsdp[0][j] = e.dsdp[1][j] = 0.0;
+  switch (kind) {
+    case DFX_DRIVE_PULSE:
+    case DFX_DRIVE_HARMONIC: {
+      double s, dtau, dA, df;
+      pulse_eval(t - p[2], p[0], p[1], kind == DFX_DRIVE_PULSE, want_grad, s, dtau, dA, df);
+      e.s[0] = s; e.sdot[0] = dtau;
+      e.dsdp[0][0] = dA; e.dsdp[0][1] = df; e.dsdp[0][2] = -dtau;
+    } break;
+    case DFX_DRIVE_RAMP: {
+      if (t < 1.0 / p[1]) { e.s[0] = p[0] * t * p[1]; e.sdot[0] = p[0] * p[1]; e.dsdp[0][0] = t * p[1]; e.dsdp[0][1] = p[0] * t; }
+      else { e.s[0] = p[0]; e.dsdp[0][0] = 1.0; }
+    } break;
+    case DFX_DRIVE_STATIC_PULSE: {
+      const double A = p[0], f = p[1], cs = p[2], csr = p[3], delay = p[4];
+      double s, dtau, dA, df;
+      pulse_eval(t - cs / csr - delay, A, f, true, want_grad, s, dtau, dA, df);
+      e.s[0] = s; e.sdot[0] = dtau;
+      e.dsdp[0][0] = dA; e.dsdp[0][1] = df;
+      e.dsdp[0][2] = -dtau / csr; e.dsdp[0][3] = dtau * cs / (csr * csr); e.dsdp[0][4] = -dtau;
+      if (t < cs / csr) { e.s[1] = t * csr; e.sdot[1] = csr; e.dsdp[1][3] = t; }
+      else { e.s[1] = cs; e.dsdp[1][2] = 1.0; }
+    } break;
+    default: break;
+  }
+}
+
+__device__ inline void load_eval(int kind, double t, const double* c, double& s, double& sdot) {
+  s = sdot = 0.0;
+  if (kind == DFX_LOAD_RAMP) {
+    if (t < 1.0 / c[1]) { s = c[0] * t * c[1]; sdot = c[0] * c[1]; } else { s = c[0]; }
+  } else if (kind == DFX_LOAD_SECH2) {
+    const double a = c[0], sh = c[1];
+    const double x = t / sh - 3.0;
+    const double ch = cosh(x), th = tanh(-x);
+    const double pre = 2.0 * a / (sh * sh);
+    s = pre / (ch * ch) * th;
+    const double dch2 = -2.0 * sinh(x) / (ch * ch * ch);
+    const double dth = -(1.0 - th * th);
+    sdot = pre * (dch2 * th + dth / (ch * ch)) / sh;
+  }
+}
+
+// ------------------------------------------------------------------------------------------
+// CTA-wide sum (warp shuffles + one shared array), result broadcast to every thread
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ double warp_sum(double v) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+  return v;
+}
+
+// red must hold >= 33 doubles.  Contains two __syncthreads().
+__device__ __forceinline__ double block_sum(double v, double* red) {
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5, nw = (blockDim.x + 31) >> 5;
+  v = warp_sum(v);
+  if (lane == 0) red[warp] = v;
+  __syncthreads();
+  if (warp == 0) {
+    double t = lane < nw ? red[lane] : 0.0;
+    t = warp_sum(t);
+    if (lane == 0) red[32] = t;
+  }
+  __syncthreads();
+  return red[32];
+}
+
+}  // namespace dfx

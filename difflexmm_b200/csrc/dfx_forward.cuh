@@ -1,0 +1,356 @@
+// dfx_forward.cuh -- forward solve: one persistent CTA per design integrates the whole time
+// horizon (adaptive Dopri5 of jax.experimental.ode, reference call site dynamics.py:166) with the
+// RHS of dynamics.py:33-55 inlined.  State, stage derivatives, node force slots and parameters
+// live on chip (shared memory, spilled to a per-design global scratch only when the lattice is
+// too large); the only HBM traffic is parameters in, dense output `ys` out.
+//
+// Per RHS evaluation (two CTA barriers):
+//   A  per block-DOF : stage state u_s, v_s (constrained DOFs follow the drive), sin/cos(theta)
+//   B  per bond      : analytic ligament (+contact) gradient -> per-node force slots.  Every
+//                      polygon vertex belongs to at most one bond, so the bond->block scatter is a
+//                      conflict-free slot write (no atomics)
+//   C  per block-DOF : gather the block's node slots, add damping and load, divide by inertia
+#pragma once
+
+#include "dfx_device.cuh"
+
+namespace dfx {
+
+struct DevTopo {
+  int n_blocks, n_npb, n_bonds, n_nodes, n_dof, n_free, n_cons;
+  int bond_energy, contact, drive_kind, load_kind, n_drive_params, n_damped;
+  const int2* bond_nodes;   // [n_bonds] global node ids (na, nb)
+  const int2* bond_blocks;  // [n_bonds] block ids (na / npb, nb / npb)
+  const int* free_of_dof;   // [n_dof] natural numbering (3*block+dof) -> free index or -1
+  const int* cons_slot;     // [n_dof] -> index in the constrained list or -1
+  const int* damp_slot;     // [n_dof] -> index into the (n_damped,3) damping leaf or -1
+  const double* drive_vec0; // [n_cons]
+  const double* drive_vec1; // [n_cons]
+  const double* load_mul;   // [n_dof] load multiplier (0 = not loaded)
+  const int* free_dofs;     // [n_free] natural DOF id of every free DOF
+  double load_consts[DFX_MAX_LOAD_CONSTS];
+};
+
+// arrays of the forward kernel, in placement-priority order (doubles)
+enum { FA_US = 0, FA_VS, FA_FS, FA_U0, FA_V0, FA_KV, FA_INVM, FA_CD, FA_BONDC, FA_CNV, FA_ALPHA, FA_COUNT };
+
+struct Placement {
+  // off >= 0: offset (doubles) into dynamic shared memory;  off < 0: -(off+1) = offset into the
+  // per-design global scratch
+  long long off[16];
+};
+
+struct FwdArgs {
+  DevTopo topo;
+  DfxParams p;
+  Tableau tab;
+  Placement place;
+  const double* y0; long long y0_bstride;
+  const double* ts; long long ts_bstride; int n_t;
+  double rtol, atol;
+  int init_step_variant; long long max_steps;
+  double* ys; DfxStats* stats;
+  double* scratch; long long scratch_per_design;  // doubles
+};
+
+__device__ __forceinline__ double* placed(const Placement& pl, int i, double* smem, double* scratch) {
+  long long o = pl.off[i];
+  return o >= 0 ? smem + o : scratch + (-(o + 1));
+}
+
+template <class L>
+__device__ __forceinline__ const double* leaf_ptr(const L& l, int b) {
+  return l.ptr ? l.ptr + (long long)b * l.bstride : nullptr;
+}
+
+// shared by both kernels: per-design constants (bond constants, reference edge angles, 1/m,
+// damping coefficient per DOF in component-major layout e = dof*NB + block)
+__device__ inline void setup_design_constants(const DevTopo& T, const DfxParams& p, int design, double* bondc /*[4][nbonds]*/,
+                                              double* cnv /*[2][nnodes] or null*/, double* alpha /*[2][nnodes] or null*/,
+                                              double* invm, double* cd) {
+  const int NB = T.n_blocks, NN = T.n_nodes, npb = T.n_npb;
+  const double* g_cnv = leaf_ptr(p.centroid_node_vectors, design);
+  const double* g_ref = leaf_ptr(p.reference_vector, design);
+  const double* g_inertia = leaf_ptr(p.inertia, design);
+  const double* g_damp = leaf_ptr(p.damping, design);
+  for (int b = threadIdx.x; b < T.n_bonds; b += blockDim.x) {
+    const double rx = g_ref[2 * b], ry = g_ref[2 * b + 1];
+    bondc[b] = rx;
+    bondc[T.n_bonds + b] = ry;
+    bondc[2 * T.n_bonds + b] = sqrt(rx * rx + ry * ry);
+    bondc[3 * T.n_bonds + b] = atan2(ry, rx);
+  }
+  for (int n = threadIdx.x; n < NN; n += blockDim.x) {
+    const double rx = g_cnv[2 * n], ry = g_cnv[2 * n + 1];
+    if (cnv) { cnv[n] = rx; cnv[NN + n] = ry; }
+    if (alpha) {
+      const int blk = n / npb, l = n - blk * npb;
+      const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
+      alpha[n] = atan2(g_cnv[2 * nn + 1] - ry, g_cnv[2 * nn] - rx);       // next edge
+      alpha[NN + n] = atan2(g_cnv[2 * np + 1] - ry, g_cnv[2 * np] - rx);  // previous edge
+    }
+  }
+  for (int e = threadIdx.x; e < 3 * NB; e += blockDim.x) {
+    const int j = e / NB, blk = e - j * NB, dof = 3 * blk + j;
+    const int f = T.free_of_dof[dof];
+    invm[e] = f >= 0 ? 1.0 / g_inertia[f] : 0.0;
+    const int ds = T.damp_slot[dof];
+    cd[e] = (ds >= 0 && g_damp) ? (p.damping_per_dof ? g_damp[ds] : g_damp[0]) : 0.0;
+  }
+}
+
+__global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
+  extern __shared__ double smem[];
+  const DevTopo& T = a.topo;
+  const int design = blockIdx.x;
+  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb;
+  double* red = smem;  // 40 doubles reserved at the start of shared memory
+  double* scratch = a.scratch ? a.scratch + (long long)design * a.scratch_per_design : nullptr;
+  double* Us = placed(a.place, FA_US, smem, scratch);      // [5][NB]  x, y, theta, sin, cos
+  double* Vs = placed(a.place, FA_VS, smem, scratch);      // [3][NB]  stage velocity
+  double* Fs = placed(a.place, FA_FS, smem, scratch);      // [3][NN]  node force slots
+  double* u0 = placed(a.place, FA_U0, smem, scratch);      // [3][NB]
+  double* v0 = placed(a.place, FA_V0, smem, scratch);      // [3][NB]
+  double* kv = placed(a.place, FA_KV, smem, scratch);      // [7][3][NB]
+  double* invm = placed(a.place, FA_INVM, smem, scratch);  // [3][NB]
+  double* cd = placed(a.place, FA_CD, smem, scratch);      // [3][NB]
+  double* bondc = placed(a.place, FA_BONDC, smem, scratch);  // [4][NBONDS]
+  double* cnv = placed(a.place, FA_CNV, smem, scratch);    // [2][NN]
+  double* alpha = T.contact ? placed(a.place, FA_ALPHA, smem, scratch) : nullptr;  // [2][NN]
+
+  const double* g_ks = leaf_ptr(a.p.k_stretch, design);
+  const double* g_ksh = leaf_ptr(a.p.k_shear, design);
+  const double* g_kr = leaf_ptr(a.p.k_rot, design);
+  const double* g_contact = leaf_ptr(a.p.contact, design);
+  const double* g_drive = leaf_ptr(a.p.drive, design);
+  const double* ts = a.ts + (long long)design * a.ts_bstride;
+  const double* y0g = a.y0 + (long long)design * a.y0_bstride;
+  const int nf = T.n_free;
+  double* ys = a.ys + (long long)design * a.n_t * 2 * nf;
+  const double rtol = a.rtol, atol = a.atol;
+  const Tableau& tab = a.tab;
+
+  setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd);
+  for (int i = tid; i < 3 * NN; i += nthr) Fs[i] = 0.0;
+  for (int e = tid; e < ND; e += nthr) {
+    const int j = e / NB, blk = e - j * NB;
+    const int f = T.free_of_dof[3 * blk + j];
+    u0[e] = f >= 0 ? y0g[f] : 0.0;
+    v0[e] = f >= 0 ? y0g[nf + f] : 0.0;
+    if (f >= 0) { ys[f] = u0[e]; ys[nf + f] = v0[e]; }
+  }
+  double cmin = 0, ccut = 0, ckc = 0;
+  if (T.contact) { cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
+  __syncthreads();
+
+  // ---- RHS phases B and C (phase A is written by the caller into Us / Vs) ---------------------
+  auto rhs_BC = [&](double tstage, double* kout) {
+    __syncthreads();
+    for (int b = tid; b < NBONDS; b += nthr) {
+      const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
+      BlockState<double> s1, s2;
+      s1.x = Us[bl.x]; s1.y = Us[NB + bl.x]; s1.th = Us[2 * NB + bl.x]; s1.s = Us[3 * NB + bl.x]; s1.c = Us[4 * NB + bl.x];
+      s2.x = Us[bl.y]; s2.y = Us[NB + bl.y]; s2.th = Us[2 * NB + bl.y]; s2.s = Us[3 * NB + bl.y]; s2.c = Us[4 * NB + bl.y];
+      BondConst bc = {bondc[b], bondc[NBONDS + b], bondc[2 * NBONDS + b], bondc[3 * NBONDS + b]};
+      const double ks = g_ks[a.p.k_per_bond[0] ? b : 0], ksh = g_ksh[a.p.k_per_bond[1] ? b : 0], kr = g_kr[a.p.k_per_bond[2] ? b : 0];
+      BondOut<double> o;
+      bond_gradient<double, false>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
+      if (T.contact) {
+        // void angles depend on the two rotations only
+        const double psi1 = wrap_value(alpha[nd.x] - alpha[NN + nd.y] + s1.th - s2.th);
+        const double psi2 = wrap_value(alpha[nd.y] - alpha[NN + nd.x] + s2.th - s1.th);
+        double e1, e2, d0, d1, d2;
+        contact_term<double>(psi1, cmin, ccut, ckc, e1, d0, d1, d2);
+        contact_term<double>(psi2, cmin, ccut, ckc, e2, d0, d1, d2);
+        o.f1[2] += e1 - e2;
+        o.f2[2] += e2 - e1;
+      }
+      Fs[nd.x] = -o.f1[0]; Fs[NN + nd.x] = -o.f1[1]; Fs[2 * NN + nd.x] = -o.f1[2];
+      Fs[nd.y] = -o.f2[0]; Fs[NN + nd.y] = -o.f2[1]; Fs[2 * NN + nd.y] = -o.f2[2];
+    }
+    __syncthreads();
+    double ls = 0.0, lsd;
+    if (T.load_kind != DFX_LOAD_NONE) load_eval(T.load_kind, tstage, T.load_consts, ls, lsd);
+    for (int e = tid; e < ND; e += nthr) {
+      const int j = e / NB, blk = e - j * NB;
+      double F = 0.0;
+      const double* slot = Fs + (long long)j * NN + blk * npb;
+      for (int l = 0; l < npb; ++l) F += slot[l];
+      if (T.load_kind != DFX_LOAD_NONE) F += T.load_mul[3 * blk + j] * ls;
+      kout[e] = (F - cd[e] * Vs[e]) * invm[e];
+    }
+  };
+
+  // write stage displacement / velocity of DOF e, constrained DOFs from the drive signal
+  auto put_stage = [&](int e, double u, double v, double tstage) {
+    const int j = e / NB, blk = e - j * NB;
+    if (invm[e] == 0.0) {
+      v = 0.0;
+      const int c = T.cons_slot[3 * blk + j];
+      u = 0.0;
+      if (c >= 0 && T.drive_kind != DFX_DRIVE_ZERO) {
+        DriveEval de;
+        drive_eval(T.drive_kind, tstage, g_drive, false, de);
+        u = T.drive_vec0[c] * de.s[0] + T.drive_vec1[c] * de.s[1];
+      }
+    }
+    Us[e] = u;
+    Vs[e] = v;
+    if (j == 2) {
+      double sn, cs;
+      sincos(u, &sn, &cs);
+      Us[3 * NB + blk] = sn;
+      Us[4 * NB + blk] = cs;
+    }
+  };
+
+  long long n_steps = 0, n_acc = 0, n_rhs = 0;
+  int status = 0;
+  double t = ts[0];
+
+  // f0 = rhs(y0, t0)
+  for (int e = tid; e < ND; e += nthr) put_stage(e, u0[e], v0[e], t);
+  rhs_BC(t, kv);
+  n_rhs++;
+
+  // ---- initial_step_size(fun, t0, y0, order=4, rtol, atol, f0) ---------------------------------
+  double dt;
+  {
+    double sd0 = 0, sd1 = 0;
+    for (int e = tid; e < ND; e += nthr) {
+      if (invm[e] == 0.0) continue;
+      const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
+      const double a0 = u0[e] / su, a1 = v0[e] / sv, b0 = v0[e] / su, b1 = kv[e] / sv;
+      sd0 += a0 * a0 + a1 * a1;
+      sd1 += b0 * b0 + b1 * b1;
+    }
+    const double d0 = sqrt(block_sum(sd0, red));
+    const double d1 = sqrt(block_sum(sd1, red));
+    const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
+    for (int e = tid; e < ND; e += nthr) put_stage(e, u0[e] + h0 * v0[e], v0[e] + h0 * kv[e], t + h0);
+    rhs_BC(t + h0, kv + ND);
+    n_rhs++;
+    double sd2 = 0;
+    for (int e = tid; e < ND; e += nthr) {
+      if (invm[e] == 0.0) continue;
+      const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
+      const double b0 = (Vs[e] - v0[e]) / su, b1 = (kv[ND + e] - kv[e]) / sv;
+      sd2 += b0 * b0 + b1 * b1;
+    }
+    const double d2 = sqrt(block_sum(sd2, red)) / h0;
+    double h1;
+    if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
+    else h1 = pow(0.01 / (a.init_step_variant == 0 ? d1 + d2 : fmax(d1, d2)), 0.2);
+    dt = fmin(100.0 * h0, h1);
+  }
+
+  // ---- time loop ---------------------------------------------------------------------------------
+  const double inv_n = 1.0 / (2.0 * nf);
+  int it = 1;
+  while (it < a.n_t) {
+    const double target = ts[it];
+    long long istep = 0;
+    bool crossed = !(t < target);
+    while (!crossed) {
+      if (!(dt > 0.0)) { status |= DFX_STATUS_DT_UNDERFLOW; break; }
+      if (istep >= a.max_steps) { status |= DFX_STATUS_MAX_STEPS; break; }
+      // six stages; stage s produces kv[s+1]
+#pragma unroll 1
+      for (int s = 0; s < 6; ++s) {
+        const double ha = dt * tab.alpha[s], h2 = dt * dt, tstage = t + ha;
+        for (int e = tid; e < ND; e += nthr) {
+          double au = 0.0, av = 0.0;
+          for (int l = 0; l <= s; ++l) {
+            const double k = kv[l * ND + e];
+            au = fma(tab.a2[s][l], k, au);
+            av = fma(tab.beta[s][l], k, av);
+          }
+          put_stage(e, u0[e] + ha * v0[e] + h2 * au, v0[e] + dt * av, tstage);
+        }
+        rhs_BC(tstage, kv + (s + 1) * ND);
+      }
+      n_rhs += 6;
+      // error ratio: sqrt(mean((err / (atol + rtol*max(|y0|,|y1|)))^2))
+      double se = 0.0;
+      for (int e = tid; e < ND; e += nthr) {
+        if (invm[e] == 0.0) continue;
+        double eu = 0.0, ev = 0.0;
+#pragma unroll
+        for (int l = 0; l < 7; ++l) {
+          const double k = kv[l * ND + e];
+          eu = fma(tab.e2[l], k, eu);
+          ev = fma(tab.c_err[l], k, ev);
+        }
+        eu = dt * (tab.sum_err * v0[e] + dt * eu);
+        ev = dt * ev;
+        const double tu = atol + rtol * fmax(fabs(u0[e]), fabs(Us[e]));
+        const double tv = atol + rtol * fmax(fabs(v0[e]), fabs(Vs[e]));
+        const double ru = eu / tu, rv = ev / tv;
+        se += ru * ru + rv * rv;
+      }
+      const double ratio = sqrt(block_sum(se, red) * inv_n);
+      ++n_steps; ++istep;
+      if (!isfinite(ratio)) { status |= DFX_STATUS_NONFINITE; break; }
+      if (ratio <= 1.0) {
+        const double t_new = t + dt;
+        // dense output for every requested time inside (t, t_new]
+        while (it < a.n_t && !(t_new < ts[it])) {
+          const double x = (ts[it] - t) / (t_new - t);
+          double* out = ys + (long long)it * 2 * nf;
+          for (int e = tid; e < ND; e += nthr) {
+            if (invm[e] == 0.0) continue;
+            const int j = e / NB, blk = e - j * NB;
+            const int f = T.free_of_dof[3 * blk + j];
+            double mu = 0.0, mv = 0.0;
+#pragma unroll
+            for (int l = 0; l < 7; ++l) {
+              const double k = kv[l * ND + e];
+              mu = fma(tab.m2[l], k, mu);
+              mv = fma(tab.c_mid[l], k, mv);
+            }
+            {
+              const double y0_ = u0[e], y1_ = Us[e], d0_ = dt * v0[e], d1_ = dt * Vs[e];
+              const double ym = y0_ + dt * (tab.sum_mid * v0[e] + dt * mu);
+              const double ca = -2. * d0_ + 2. * d1_ - 8. * y0_ - 8. * y1_ + 16. * ym;
+              const double cb = 5. * d0_ - 3. * d1_ + 18. * y0_ + 14. * y1_ - 32. * ym;
+              const double cc = -4. * d0_ + d1_ - 11. * y0_ - 5. * y1_ + 16. * ym;
+              out[f] = (((ca * x + cb) * x + cc) * x + d0_) * x + y0_;
+            }
+            {
+              const double y0_ = v0[e], y1_ = Vs[e], d0_ = dt * kv[e], d1_ = dt * kv[6 * ND + e];
+              const double ym = y0_ + dt * mv;
+              const double ca = -2. * d0_ + 2. * d1_ - 8. * y0_ - 8. * y1_ + 16. * ym;
+              const double cb = 5. * d0_ - 3. * d1_ + 18. * y0_ + 14. * y1_ - 32. * ym;
+              const double cc = -4. * d0_ + d1_ - 11. * y0_ - 5. * y1_ + 16. * ym;
+              out[nf + f] = (((ca * x + cb) * x + cc) * x + d0_) * x + y0_;
+            }
+          }
+          ++it;
+          crossed = true;
+        }
+        for (int e = tid; e < ND; e += nthr) {
+          u0[e] = Us[e];
+          v0[e] = Vs[e];
+          kv[e] = kv[6 * ND + e];
+        }
+        t = t_new;
+        ++n_acc;
+      }
+      const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
+      const double factor = fmin(10.0, fmax(pow(ratio, -0.2) * 0.9, dfactor));
+      dt = (ratio == 0.0) ? dt * 10.0 : dt * factor;
+    }
+    if (!crossed) {  // integration stopped early: fill the remaining outputs with NaN
+      for (; it < a.n_t; ++it)
+        for (int f = tid; f < 2 * nf; f += nthr) ys[(long long)it * 2 * nf + f] = nan("");
+    }
+  }
+  if (tid == 0 && a.stats) {
+    DfxStats st;
+    st.steps = n_steps; st.accepted = n_acc; st.rhs_evals = n_rhs; st.status = status; st.reserved = 0; st.last_dt = dt;
+    a.stats[design] = st;
+  }
+}
+
+}  // namespace dfx

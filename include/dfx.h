@@ -1,0 +1,189 @@
+/* dfx.h -- C ABI of the B200-native DifFlexMM dynamic solver (libdfx.so).
+ *
+ * Drop-in boundary: these entry points replace the call
+ *     odeint(rhs, _state0, timepoints, control_params, _inertia, rtol, atol)
+ * at /root/reference/difflexmm/dynamics.py:166 and what jax.grad derives for it
+ * (jax.experimental.ode._odeint_rev, jax 0.4.8), i.e. reference functions a3-a12 of
+ * SURVEY.md section 8(a):
+ *   - dfx_forward  <- odeint forward solve              (dynamics.py:166, rhs at :33-55)
+ *   - dfx_adjoint  <- the custom_vjp backward of odeint (continuous adjoint, restarted
+ *                     per output interval; cotangents for y0, ts, every ControlParams
+ *                     leaf and the reduced inertia)
+ *   - dfx_expand_fields <- the history reconstruction    (dynamics.py:129-136,169-182)
+ *   - dfx_topology_create <- what setup_dynamic_solver closes over (dynamics.py:60-136):
+ *                     bond list, constrained DOF pairs and their drive signal, loaded
+ *                     DOFs and their load signal, damped blocks, energy vocabulary.
+ *
+ * Plain C: pointers + sizes, no C++/torch types.  All array arguments of
+ * dfx_forward / dfx_adjoint / dfx_expand_fields are DEVICE pointers (float64 unless
+ * noted); the DfxTopologyDesc passed to dfx_topology_create holds HOST pointers and is
+ * copied.  The caller owns every buffer.  Calls are stream-ordered and re-entrant; a
+ * topology handle is immutable and may be shared between threads and streams of the
+ * device it was created on.
+ *
+ * Layouts (row-major, batch index b outermost):
+ *   state vectors   [2*n_free]   = free displacements then free velocities, i.e. the
+ *                                  raveled (2, n_free) array the reference hands to odeint
+ *   ys, g           [B][n_t][2*n_free]
+ *   every parameter leaf has a batch stride in elements; stride 0 = shared by all designs
+ */
+#ifndef DFX_H
+#define DFX_H
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* ---- vocabulary ------------------------------------------ */
+enum { DFX_BOND_LIGAMENT = 0,     /* energy.py:158-176 ligament_energy            */
+       DFX_BOND_LINEARIZED = 1 }; /* energy.py:99-117  ligament_energy_linearized */
+
+/* constrained-DOF drive u_c(t) = vec0[c]*s0(t) + vec1[c]*s1(t); parameter order fixed */
+enum {
+  DFX_DRIVE_ZERO = 0,     /* dynamics.py:66 default `lambda t: 0`; 0 params                  */
+  DFX_DRIVE_PULSE = 1,    /* problems/quads_focusing.py:211-222; (amplitude, loading_rate,
+                             input_delay): A*(1-cos(2 pi f tau))/2 on 0<tau<1/f, tau=t-delay  */
+  DFX_DRIVE_HARMONIC = 2, /* problems/quads_spin.py:210-221; same params, on tau>0          */
+  DFX_DRIVE_RAMP = 3,     /* problems/hinge_characterization.py:134-139; (amplitude,
+                             loading_rate): A*(t<1/f ? t*f : 1)                              */
+  DFX_DRIVE_STATIC_PULSE = 4 /* problems/quads_kinetic_energy_static_tuning.py:176-196;
+                             (amplitude, loading_rate, compressive_strain,
+                             compressive_strain_rate, input_delay):
+                             s0 = pulse(t - cs/csr - delay; A, f)  [vec0 = dynamic vector]
+                             s1 = (t < cs/csr ? t*csr : cs)        [vec1 = static vector,
+                                                                    geometric scale folded in] */
+};
+#define DFX_MAX_DRIVE_PARAMS 5
+
+/* external load on loaded DOFs: load_vec[l] * s(t); constants only (the reference's
+ * loading closures capture their constants: tests/test_difflexmm.py:85-86,
+ * scripts/pulse_RS.py:49-50) */
+enum {
+  DFX_LOAD_NONE = 0,
+  DFX_LOAD_RAMP = 1, /* c0 * (t < 1/c1 ? t*c1 : 1)                                   */
+  DFX_LOAD_SECH2 = 2 /* 2*c0/c1^2 * cosh(t/c1-3)^-2 * tanh(3-t/c1)                   */
+};
+#define DFX_MAX_LOAD_CONSTS 4
+
+/* ---- static topology --------------------------------------------------------------- */
+typedef struct DfxTopologyDesc {
+  int32_t n_blocks;          /* rigid units                                            */
+  int32_t n_npb;             /* nodes (polygon vertices) per block                      */
+  int32_t n_bonds;
+  const int32_t* bond_nodes; /* [n_bonds][2] global node ids (block*n_npb + local)      */
+  int32_t n_constrained;
+  const int32_t* constrained_dofs; /* [n_constrained] global DOF ids block*3+dof, in the
+                                      order of constrained_block_DOF_pairs               */
+  int32_t bond_energy;       /* DFX_BOND_*                                              */
+  int32_t contact;           /* 1 = angle-based contact energy (energy.py:364-407)      */
+  int32_t drive_kind;        /* DFX_DRIVE_*                                             */
+  const double* drive_vec0;  /* [n_constrained] or NULL (= zeros)                       */
+  const double* drive_vec1;  /* [n_constrained] or NULL                                 */
+  int32_t load_kind;         /* DFX_LOAD_*                                              */
+  int32_t n_loaded;
+  const int32_t* loaded_dofs;/* [n_loaded] global DOF ids                               */
+  const double* load_vec;    /* [n_loaded] multiplier per loaded DOF, or NULL (= ones)  */
+  double load_consts[DFX_MAX_LOAD_CONSTS];
+  int32_t n_damped;          /* 0 = no damping term                                     */
+  const int32_t* damped_blocks; /* [n_damped] block ids (loading.py:88-89)              */
+} DfxTopologyDesc;
+
+typedef struct DfxTopology DfxTopology; /* opaque */
+
+/* ---- runtime parameters: the differentiable leaves of (control_params, _inertia) ---- */
+typedef struct DfxLeaf {
+  const double* ptr; /* device */
+  int64_t bstride;   /* elements between consecutive designs; 0 = shared               */
+} DfxLeaf;
+
+typedef struct DfxParams {
+  DfxLeaf centroid_node_vectors; /* [n_blocks*n_npb*2]                                  */
+  DfxLeaf reference_vector;      /* [n_bonds*2]                                         */
+  DfxLeaf k_stretch, k_shear, k_rot; /* [1] or [n_bonds], see k_per_bond               */
+  int32_t k_per_bond[3];         /* 0 = scalar leaf, 1 = (n_bonds,) leaf                */
+  DfxLeaf damping;               /* [1] or [n_damped*3]                                 */
+  int32_t damping_per_dof;       /* 0 = scalar leaf, 1 = (n_damped,3) leaf              */
+  DfxLeaf inertia;               /* [n_free]  (reduced to the free DOFs, dynamics.py:157-163) */
+  DfxLeaf contact;               /* [3] = (min_angle, cutoff_angle, k_contact); NULL if contact==0 */
+  DfxLeaf drive;                 /* [n_drive_params(kind)]                              */
+} DfxParams;
+
+/* cotangent outputs of dfx_adjoint, one slice per design (no sharing), same leaf shapes.
+ * A NULL pointer skips the store (the quadrature is still integrated: it is part of the
+ * error norm of the reference's augmented system). */
+typedef struct DfxParamGrads {
+  double* centroid_node_vectors; /* [B][n_blocks*n_npb*2] */
+  double* reference_vector;      /* [B][n_bonds*2]        */
+  double* k_stretch;             /* [B][1 or n_bonds]     */
+  double* k_shear;
+  double* k_rot;
+  double* damping;               /* [B][1 or n_damped*3]  */
+  double* inertia;               /* [B][n_free]           */
+  double* contact;               /* [B][3]                */
+  double* drive;                 /* [B][n_drive_params]   */
+} DfxParamGrads;
+
+typedef struct DfxOptions {
+  int32_t init_step_variant; /* 0: h1 = (0.01/(d1+d2))^(1/5)  (jax 0.4.8, the reference's pin)
+                                1: h1 = (0.01/max(d1,d2))^(1/5) (later jax releases)     */
+  int32_t threads;           /* CTA size override, 0 = choose                           */
+  int64_t max_steps;         /* attempted-step cap per odeint call, 0 = 1<<40 (jax: inf)*/
+} DfxOptions;
+
+enum { DFX_OK = 0, DFX_ERR_INVALID = 1, DFX_ERR_CUDA = 2, DFX_ERR_UNSUPPORTED = 3 };
+enum { DFX_STATUS_OK = 0, DFX_STATUS_MAX_STEPS = 1, DFX_STATUS_DT_UNDERFLOW = 2,
+       DFX_STATUS_NONFINITE = 4 };
+
+typedef struct DfxStats { /* one per design, device memory */
+  int64_t steps;     /* attempted RK steps            */
+  int64_t accepted;  /* accepted RK steps             */
+  int64_t rhs_evals; /* (augmented) RHS evaluations   */
+  int32_t status;    /* DFX_STATUS_* bit-or           */
+  int32_t reserved;
+  double last_dt;
+} DfxStats;
+
+/* ---- entry points ------------------------------------------------------------------ */
+int dfx_topology_create(const DfxTopologyDesc* desc, int device, DfxTopology** out);
+void dfx_topology_destroy(DfxTopology* topo);
+int dfx_topology_n_free(const DfxTopology* topo);
+int dfx_drive_n_params(int drive_kind);
+
+/* bytes of device scratch dfx_adjoint / dfx_forward need for `batch` designs */
+size_t dfx_forward_workspace_bytes(const DfxTopology* topo, int batch);
+size_t dfx_adjoint_workspace_bytes(const DfxTopology* topo, int batch);
+
+/* forward solve: ys[b][0] = y0[b]; ys[b][i] = state at ts[i].  stream = cudaStream_t. */
+int dfx_forward(const DfxTopology* topo, const DfxParams* params, int batch,
+                const double* y0, int64_t y0_bstride,
+                const double* ts, int64_t ts_bstride, int n_t,
+                double rtol, double atol, const DfxOptions* opt,
+                double* ys, DfxStats* stats,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* continuous adjoint.  aug_size = number of entries the reference's augmented state has,
+ * 2*(2 n_free) + 1 + sum(size of every leaf of (control_params, _inertia)); it is the
+ * denominator of the RMS error norm.  Pass 0 to count only the leaves listed in DfxParams. */
+int dfx_adjoint(const DfxTopology* topo, const DfxParams* params, int batch,
+                const double* ys, const double* ts, int64_t ts_bstride, int n_t,
+                const double* g, double rtol, double atol, int64_t aug_size,
+                const DfxOptions* opt,
+                double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
+                void* workspace, size_t workspace_bytes, void* stream);
+
+/* fields[b][i][0][blk][dof] = displacement, fields[b][i][1][blk][dof] = velocity of every
+ * block DOF (constrained DOFs follow the drive and its time derivative). */
+int dfx_expand_fields(const DfxTopology* topo, const DfxParams* params, int batch,
+                      const double* ys, const double* ts, int64_t ts_bstride, int n_t,
+                      double* fields, void* stream);
+
+const char* dfx_last_error(void);
+const char* dfx_version(void);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* DFX_H */

@@ -1,0 +1,109 @@
+"""GPU parity tests proper: libdfx (CUDA, through its C ABI) against the golden fixtures written by
+the literal restatement of the reference and against the C++ oracle on the same inputs.
+
+Tolerances are the north star's: trajectories rel-L2 <= 1e-6, parameter gradients rel-L2 <= 1e-5."""
+
+import numpy as np
+import pytest
+import torch
+
+from cases import golden_names, load_golden, rel_l2
+from difflexmm_b200 import _abi
+
+pytestmark = pytest.mark.gpu
+
+TRAJ_TOL = 1e-6
+GRAD_TOL = 1e-5
+
+
+def _solver(spec):
+    from difflexmm_b200 import _lib
+    return _lib, _lib.Topology(spec, torch.cuda.current_device())
+
+
+def _dev_params(c, batch=1):
+    leaves = {k: torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64, device="cuda") for k, v in c.leaves.items()}
+    return _abi.ParamSet(c.spec, batch, leaves, c.per_bond, c.damping_per_dof)
+
+
+def _significant(ref, key):
+    """leaves whose golden gradient is pure round-off (e.g. shear stiffness in a pure tensile test) are
+    compared absolutely"""
+    return np.abs(ref[key]).max() > 1e-9
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_forward_matches_golden(name):
+    c = load_golden(name)
+    lib, topo = _solver(c.spec)
+    ps = _dev_params(c)
+    y0 = torch.as_tensor(c.y0, device="cuda")
+    ts = torch.as_tensor(c.ts, device="cuda")
+    ys, stats = lib.forward(topo, ps, y0, ts, c.rtol, c.atol, _abi.DfxOptions(0, 0, 0))
+    st = stats.numpy()[0]
+    assert st["status"] == 0
+    assert rel_l2(ys[0].cpu().numpy(), c.ref["ys"]) <= TRAJ_TOL
+    assert abs(int(st["steps"]) - int(c.ref["fwd_steps"])) <= max(2, int(0.01 * c.ref["fwd_steps"]))
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_adjoint_matches_golden(name):
+    c = load_golden(name)
+    lib, topo = _solver(c.spec)
+    ps = _dev_params(c)
+    ys = torch.as_tensor(c.ref["ys"][None], device="cuda")
+    ts = torch.as_tensor(c.ts, device="cuda")
+    g = torch.as_tensor(c.g[None], device="cuda")
+    y0_bar, ts_bar, grads, stats = lib.adjoint(topo, ps, ys, ts, g, c.rtol, c.atol, c.aug_size, _abi.DfxOptions(0, 0, 0))
+    st = stats.numpy()[0]
+    assert st["status"] == 0
+    assert abs(int(st["steps"]) - int(c.ref["bwd_steps"])) <= max(2, int(0.01 * c.ref["bwd_steps"]))
+    assert rel_l2(y0_bar[0].cpu().numpy(), c.ref["y0_bar"]) <= GRAD_TOL
+    assert rel_l2(ts_bar[0].cpu().numpy(), c.ref["ts_bar"]) <= GRAD_TOL
+    for k, v in grads.items():
+        key = "grad_" + k
+        if key not in c.ref:
+            continue
+        got = v[0].cpu().numpy()
+        if _significant(c.ref, key):
+            assert rel_l2(got, c.ref[key]) <= GRAD_TOL, k
+        else:
+            assert np.abs(got - c.ref[key]).max() <= 1e-9, k
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_cuda_matches_cpp_oracle_batched(name):
+    """a batch of 3 perturbed designs: CUDA vs the C++ oracle on identical inputs"""
+    from oracle import Oracle
+    c = load_golden(name)
+    rng = np.random.default_rng(0)
+    B = 3
+    leaves = dict(c.leaves)
+    cnv = np.stack([leaves["centroid_node_vectors"] * (1 + 0.01 * rng.standard_normal(leaves["centroid_node_vectors"].shape))
+                    for _ in range(B)])
+    leaves["centroid_node_vectors"] = cnv
+    orc = Oracle(c.spec)
+    ps_h = orc.params(B, leaves, c.per_bond, c.damping_per_dof)
+    ys_h, st_h = orc.forward(ps_h, c.y0, c.ts, c.rtol, c.atol)
+    g = np.cos(ys_h) + 0.3
+    y0b_h, tsb_h, gr_h, sb_h = orc.adjoint(ps_h, ys_h, c.ts, g, c.rtol, c.atol)
+    lib, topo = _solver(c.spec)
+    dl = {k: torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64, device="cuda") for k, v in leaves.items()}
+    ps_d = _abi.ParamSet(c.spec, B, dl, c.per_bond, c.damping_per_dof)
+    ys_d, st_d = lib.forward(topo, ps_d, torch.as_tensor(c.y0, device="cuda"), torch.as_tensor(c.ts, device="cuda"),
+                             c.rtol, c.atol, _abi.DfxOptions(0, 0, 0))
+    assert (st_d.numpy()["status"] == 0).all()
+    for b in range(B):
+        assert rel_l2(ys_d[b].cpu().numpy(), ys_h[b]) <= TRAJ_TOL
+    y0b_d, tsb_d, gr_d, sb_d = lib.adjoint(topo, ps_d, torch.as_tensor(ys_h, device="cuda"), torch.as_tensor(c.ts, device="cuda"),
+                                           torch.as_tensor(g, device="cuda"), c.rtol, c.atol, 0, _abi.DfxOptions(0, 0, 0))
+    assert (sb_d.numpy()["status"] == 0).all()
+    for b in range(B):
+        assert rel_l2(y0b_d[b].cpu().numpy(), y0b_h[b]) <= GRAD_TOL
+        for k in gr_h:
+            ref = gr_h[k][b]
+            got = gr_d[k][b].cpu().numpy()
+            if np.abs(ref).max() > 1e-9:
+                assert rel_l2(got, ref) <= GRAD_TOL, (k, b)
+            else:
+                assert np.abs(got - ref).max() <= 1e-9, (k, b)

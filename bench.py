@@ -1,0 +1,322 @@
+#!/usr/bin/env python
+"""bench.py -- forward+adjoint design evaluations per second (BASELINE.json metric).
+
+Workload (config.workload): cfg3 of BASELINE.json, the quads_focusing random-initial-guess ensemble
+(24x16 quads, contact, pulse drive, n_t=200, rtol 1e-8 / atol 1e-4; designs = initial design +
+U(-1,1)*0.15*spacing, one numpy PRNG stream per design).  One "step" = one forward solve + one
+adjoint solve (objective: target kinetic energy) of every design of the rank's batch.  Each rank
+holds `--designs` designs (default 1024, the whole ensemble of the north star on one GPU); ranks
+are independent (no data-path collective), so N GPUs process N*designs per step: weak scaling.
+
+  value      designs/s with all inputs resident in HBM (forward kernel + objective cotangent + adjoint kernel)
+  e2e        the same through the public API (DynamicSolver.odeint + torch.autograd) with the per-design leaves
+             copied host->device from pinned memory and objective values + gradients read back, every step
+  roofline   adjoint kernel: algorithmic FP64 flops (convention W, with the step counts
+             the kernel reports) / CUDA-event duration, against the FP64-FMA peak measured in this run
+  cpu_baseline  the C++ CPU oracle (a port of the reference algorithm, NOT the reference) on the host cores
+
+`--impl reference` times the CPU implementation of the path (oracle port: JAX is not installable in
+this image) on the same config.
+"""
+
+import argparse
+import json
+import os
+import subprocess
+import sys
+import threading
+import time
+
+import numpy as np
+
+ROOT = os.path.dirname(os.path.abspath(__file__))
+sys.path.insert(0, ROOT)
+
+METRIC = "forward+adjoint design evaluations per second"
+UNIT = "designs/s"
+
+
+def flops_model(spec, aug_size, n_t, fwd_steps, bwd_steps):
+    """SURVEY section 8(d), convention W.  Returns (forward flops, adjoint flops) for the given totals of
+    attempted steps (summed over designs; per-design terms scale with the number of designs in them)."""
+    f_rhs = 144 * spec.n_bonds + 41 * spec.n_blocks + 3 * spec.n_free
+    N = 2 * spec.n_free
+
+    def fwd(steps, designs):
+        return steps * (6 * f_rhs + 65 * N) + designs * 50 * N * n_t
+
+    def bwd(steps, designs):
+        return steps * (24 * f_rhs + 65 * aug_size) + designs * (n_t - 1) * (8 * f_rhs + 60 * aug_size)
+    return fwd, bwd
+
+
+class ClockSampler:
+    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+
+    def __init__(self, index):
+        self.rows, self._stop, self.index = [], threading.Event(), index
+        self._t = threading.Thread(target=self._run, daemon=True)
+
+    def _run(self):
+        q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
+             "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
+        while not self._stop.is_set():
+            try:
+                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                     capture_output=True, text=True, timeout=5).stdout.strip()
+                if out:
+                    self.rows.append([x.strip() for x in out.split(",")])
+            except Exception:
+                pass
+            self._stop.wait(0.2)
+
+    def __enter__(self):
+        self._t.start()
+        return self
+
+    def __exit__(self, *a):
+        self._stop.set()
+        self._t.join(timeout=5)
+
+    def summary(self):
+        sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
+        mx = [float(r[1]) for r in self.rows if len(r) > 1 and r[1].replace(".", "").isdigit()]
+        reasons = set()
+        for r in self.rows:
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                if v.lower().startswith("active"):
+                    reasons.add(name)
+        return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
+                "reasons": sorted(reasons), "samples": len(self.rows)}
+
+
+def build_problem(n_designs, seed0):
+    import torch
+    from difflexmm_b200.problems import QuadsFocusing
+    prob = QuadsFocusing()
+    spec, drive = prob.lower()
+    hs, vs = prob.random_ensemble(n_designs, noise=0.15, seed0=seed0)
+    leaves, pb, dpd, aug, y0, ts = prob.boundary_inputs((hs, vs), batch=n_designs, device="cpu")
+    return prob, spec, drive, leaves, pb, dpd, aug, y0, ts
+
+
+def target_free_index(prob, spec):
+    """free-DOF indices of the 3 DOFs of every target block (all free in this configuration)."""
+    free_of = -np.ones(3 * spec.n_blocks, dtype=np.int64)
+    free_of[spec.free_dofs] = np.arange(spec.n_free)
+    idx = free_of[(prob.target_blocks()[:, None] * 3 + np.arange(3)[None]).reshape(-1)]
+    assert (idx >= 0).all()
+    return idx
+
+
+def run_cpu(args, rank_out=True):
+    """CPU implementation of the path (C++ oracle port of the reference algorithm), all host cores."""
+    from oracle import Oracle
+    cores = os.cpu_count() or 1
+    n = max(cores, 1)
+    prob, spec, drive, leaves, pb, dpd, aug, y0, ts = build_problem(n, seed0=0)
+    orc = Oracle(spec)
+    lv = {k: v.numpy() for k, v in leaves.items()}
+    ps = orc.params(n, lv, pb, dpd)
+    nf = spec.n_free
+    tidx = target_free_index(prob, spec)
+
+    def step():
+        ys, _ = orc.forward(ps, y0.numpy(), ts.numpy(), prob.rtol, prob.atol, n_threads=cores)
+        g = np.zeros_like(ys)
+        g[:, :, nf + tidx] = ys[:, :, nf + tidx] * lv["inertia"][:, None, tidx]
+        orc.adjoint(ps, ys, ts.numpy(), g, prob.rtol, prob.atol, aug, n_threads=cores)
+    return step, n, cores
+
+
+def main():
+    ap = argparse.ArgumentParser()
+    ap.add_argument("--gpus", type=int, default=1)
+    ap.add_argument("--steps", type=int, default=3)
+    ap.add_argument("--warmup", type=int, default=3)
+    ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--designs", type=int, default=1024, help="designs per GPU per step")
+    ap.add_argument("--no-cpu-baseline", action="store_true")
+    ap.add_argument("--no-e2e", action="store_true")
+    args = ap.parse_args()
+    rank = int(os.environ.get("RANK", "0"))
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+
+    config = {"workload": "quads_focusing 24x16 random-initial-guess ensemble (cfg3): forward + adjoint per design, "
+                          "n_t=200, rtol=1e-8, atol=1e-4, contact on, noise 0.15*spacing",
+              "designs_per_gpu": args.designs, "parallelism": f"designs sharded over {world} rank(s), no collective",
+              "l2": "inputs larger than L2 (ys + cotangent = 7 MB per design)"}
+
+    if args.impl == "reference":
+        if rank != 0:
+            return
+        step, n, cores = run_cpu(args)
+        for _ in range(min(args.warmup, 1)):  # the CPU path has no warm-up effects worth 3 x 15 s
+            step()
+        t0 = time.perf_counter()
+        for _ in range(args.steps):
+            step()
+        dt = (time.perf_counter() - t0) / args.steps
+        val = n / dt
+        sample = f"{n} designs of the same ensemble per step, one per host thread"
+        print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
+                          "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
+                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
+                          "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+
+    import torch
+    import torch.distributed as dist
+    from difflexmm_b200 import _abi
+    from difflexmm_b200.dynamics import DynamicSolver
+
+    torch.cuda.set_device(local_rank)
+    dev = torch.device("cuda", local_rank)
+    if world > 1:
+        dist.init_process_group("nccl", device_id=dev)
+    B = args.designs
+    prob, spec, drive, leaves_h, pb, dpd, aug, y0_h, ts_h = build_problem(B, seed0=rank * B)
+    solver = DynamicSolver(spec, drive, prob.rtol, prob.atol, dev)
+    lib = solver._lib
+    nf = spec.n_free
+    n_t = len(ts_h)
+    tidx = torch.as_tensor(target_free_index(prob, spec), device=dev)
+
+    leaves_pinned = {k: v.contiguous().pin_memory() for k, v in leaves_h.items()}
+    leaves_d = {k: v.to(dev) for k, v in leaves_pinned.items()}
+    y0, ts = y0_h.to(dev), ts_h.to(dev)
+    ps = _abi.ParamSet(spec, B, leaves_d, pb, dpd)
+
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+    kernel_ms = {"forward": [], "adjoint": []}
+    last = {}
+
+    def step(timed):
+        if timed:
+            ev[0].record()
+        ys, st_f = lib.forward(solver.handle, ps, y0, ts, prob.rtol, prob.atol, solver.options)
+        if timed:
+            ev[1].record()
+        g = torch.zeros_like(ys)
+        g[:, :, nf + tidx] = ys[:, :, nf + tidx] * leaves_d["inertia"][:, None, tidx]
+        if timed:
+            ev[2].record()
+        y0_bar, ts_bar, grads, st_b = lib.adjoint(solver.handle, ps, ys, ts, g, prob.rtol, prob.atol, aug, solver.options)
+        if timed:
+            ev[3].record()
+        last.update(ys=ys, grads=grads, st_f=st_f, st_b=st_b)
+
+    def barrier():
+        if world > 1:
+            dist.barrier()
+        torch.cuda.synchronize()
+
+    for _ in range(args.warmup):
+        step(False)
+    barrier()
+    with ClockSampler(local_rank) as clocks:
+        start, stop = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        start.record()
+        for _ in range(args.steps):
+            step(True)
+            torch.cuda.synchronize()
+            kernel_ms["forward"].append(ev[0].elapsed_time(ev[1]))
+            kernel_ms["adjoint"].append(ev[2].elapsed_time(ev[3]))
+        stop.record()
+        barrier()
+        ms_total = start.elapsed_time(stop)
+    t = torch.tensor([ms_total], dtype=torch.float64, device=dev)
+    if world > 1:
+        dist.all_reduce(t, op=dist.ReduceOp.MAX)
+    ms_per_step = t.item() / args.steps
+    value = world * B / (ms_per_step * 1e-3)
+
+    st_f, st_b = last["st_f"].numpy(), last["st_b"].numpy()
+    bad = int((st_f["status"] != 0).sum() + (st_b["status"] != 0).sum())
+    fwd_fl, bwd_fl = flops_model(spec, aug, n_t, 0, 0)
+    flops_adj = bwd_fl(int(st_b["steps"].sum()), B)
+    flops_fwd = fwd_fl(int(st_f["steps"].sum()), B)
+    adj_ms = float(np.mean(kernel_ms["adjoint"]))
+    fwd_ms = float(np.mean(kernel_ms["forward"]))
+
+    # ---- e2e through the public API with host buffers ----------------------------------------------------
+    e2e = None
+    if not args.no_e2e:
+        host_names = ["centroid_node_vectors", "inertia"]  # the per-design leaves; the rest is shared by the ensemble
+        h2d = sum(leaves_pinned[k].numel() * 8 for k in host_names)
+        out_pinned = {k: torch.empty_like(leaves_pinned[k]).pin_memory() for k in host_names}
+        obj_pinned = torch.empty(B, dtype=torch.float64).pin_memory()
+        d2h = sum(v.numel() * 8 for v in out_pinned.values()) + obj_pinned.numel() * 8
+
+        def e2e_step():
+            lv = dict(leaves_d)
+            for k in host_names:
+                lv[k] = leaves_pinned[k].to(dev, non_blocking=True).requires_grad_(True)
+            ys = solver.odeint(y0, ts, lv, B, pb, dpd, aug)
+            v = ys[:, :, nf + tidx]
+            obj = (lv["inertia"][:, None, tidx] * v ** 2 / 2).sum(dim=(1, 2))
+            obj.sum().backward()
+            for k in host_names:
+                out_pinned[k].copy_(lv[k].grad, non_blocking=True)
+            obj_pinned.copy_(obj.detach(), non_blocking=True)
+            torch.cuda.synchronize()
+
+        for _ in range(max(1, min(args.warmup, 1))):
+            e2e_step()
+        barrier()
+        t0 = time.perf_counter()
+        n_e2e = max(1, min(args.steps, 3))
+        for _ in range(n_e2e):
+            e2e_step()
+        barrier()
+        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(te, op=dist.ReduceOp.MAX)
+        e2e = {"value": world * B / te.item(), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+
+    if rank != 0:
+        if world > 1:
+            dist.destroy_process_group()
+        return
+
+    # ---- roofline denominator: FP64 FMA peak measured here (MEASURED_PEAKS.json has no FP64 entry) -------
+    peak, peak_src = None, "nominal 148 SMs x 64 DFMA/clk x 2 x sm_max_mhz"
+    try:
+        import ctypes as C
+        lib.lib.dfx_fp64_peak.restype = C.c_double
+        peak = float(lib.lib.dfx_fp64_peak(C.c_void_p(torch.cuda.current_stream().cuda_stream)))
+        peak_src = "measured in this run: register-resident DFMA chains, all SMs (dfx_fp64_peak)"
+    except Exception:
+        pass
+    cl = clocks.summary()
+    if not peak:
+        peak = 148 * 64 * 2 * (cl["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
+    achieved = flops_adj / (adj_ms * 1e-3) / 1e12
+    roofline = {"kernel": "adjoint_kernel", "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "note": "HBM and tensor rooflines do not bind this path (10.7 MB and 10 Gflop per design, no dense contraction)",
+                "forward_kernel": {"achieved": flops_fwd / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms}, "adjoint_ms": adj_ms,
+                "steps_fwd_mean": float(st_f["steps"].mean()), "steps_bwd_mean": float(st_b["steps"].mean())}
+
+    cpu_baseline = None
+    if not args.no_cpu_baseline and world == 1:
+        cstep, n, cores = run_cpu(args)
+        t0 = time.perf_counter()
+        cstep()
+        dtc = time.perf_counter() - t0
+        cpu_baseline = {"value": n / dtc, "unit": UNIT, "cores": cores, "kind": "port",
+                        "sample": f"{n} designs of the same ensemble, one per host thread, C++ oracle (not the JAX reference)"}
+
+    out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "data": "synthetic", "config": config, "clocks": cl, "e2e": e2e, "gpu_launches": 2 * args.steps,
+           "roofline": roofline, "cpu_baseline": cpu_baseline, "failed_designs": bad}
+    print(json.dumps(out))
+    if world > 1:
+        dist.destroy_process_group()
+
+
+if __name__ == "__main__":
+    main()

@@ -398,3 +398,50 @@ extern "C" int dfx_expand_fields(const DfxTopology* t, const DfxParams* params, 
   if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "expand_fields launch failed: %s", cudaGetErrorString(e));
   return DFX_OK;
 }
+
+// ---- FP64 FMA peak micro-benchmark: the roofline denominator of this path (MEASURED_PEAKS.json holds
+// HBM and bf16 only).  Register-resident chains of dependent DFMAs, 8 independent chains per thread.
+namespace {
+__global__ void __launch_bounds__(256) fp64_peak_kernel(double* out, int iters, double a, double b) {
+  double x0 = threadIdx.x * 1e-3, x1 = x0 + 1, x2 = x0 + 2, x3 = x0 + 3, x4 = x0 + 4, x5 = x0 + 5, x6 = x0 + 6, x7 = x0 + 7;
+#pragma unroll 1
+  for (int i = 0; i < iters; ++i) {
+#pragma unroll
+    for (int u = 0; u < 8; ++u) {
+      x0 = fma(x0, a, b); x1 = fma(x1, a, b); x2 = fma(x2, a, b); x3 = fma(x3, a, b);
+      x4 = fma(x4, a, b); x5 = fma(x5, a, b); x6 = fma(x6, a, b); x7 = fma(x7, a, b);
+    }
+  }
+  out[blockIdx.x * blockDim.x + threadIdx.x] = x0 + x1 + x2 + x3 + x4 + x5 + x6 + x7;
+}
+}  // namespace
+
+// returns the measured FP64 throughput in TFLOP/s (2 flops per FMA), or a negative value on error
+extern "C" double dfx_fp64_peak(void* stream_) {
+  cudaStream_t stream = (cudaStream_t)stream_;
+  int dev = 0, sms = 0;
+  if (cudaGetDevice(&dev) != cudaSuccess) return -1.0;
+  cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+  const int threads = 256, blocks = sms * 8, iters = 4096;
+  double* out = nullptr;
+  if (cudaMalloc((void**)&out, sizeof(double) * threads * blocks) != cudaSuccess) return -1.0;
+  cudaEvent_t e0, e1;
+  cudaEventCreate(&e0);
+  cudaEventCreate(&e1);
+  double best = -1.0;
+  for (int rep = 0; rep < 4; ++rep) {
+    cudaEventRecord(e0, stream);
+    fp64_peak_kernel<<<blocks, threads, 0, stream>>>(out, iters, 0.999999, 1e-9);
+    cudaEventRecord(e1, stream);
+    if (cudaEventSynchronize(e1) != cudaSuccess) break;
+    float ms = 0;
+    cudaEventElapsedTime(&ms, e0, e1);
+    const double flops = 2.0 * 64.0 * iters * (double)threads * blocks;
+    const double tf = flops / (ms * 1e-3) / 1e12;
+    if (rep > 0 && tf > best) best = tf;
+  }
+  cudaEventDestroy(e0);
+  cudaEventDestroy(e1);
+  cudaFree(out);
+  return best;
+}

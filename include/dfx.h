@@ -180,6 +180,9 @@ int dfx_expand_fields(const DfxTopology* topo, const DfxParams* params, int batc
                       const double* ys, const double* ts, int64_t ts_bstride, int n_t,
                       double* fields, void* stream);
 
+/* measurement helper: FP64 FMA throughput of the current device in TFLOP/s (roofline denominator) */
+double dfx_fp64_peak(void* stream);
+
 const char* dfx_last_error(void);
 const char* dfx_version(void);
 

@@ -36,7 +36,8 @@ def lib():
 
 
 def _f64(a):
-    return np.ascontiguousarray(np.asarray(a, dtype=np.float64))
+    a = np.asarray(a, dtype=np.float64)
+    return a if a.flags.c_contiguous else np.array(a, order="C")  # keeps 0-d leaves 0-d
 
 
 class Oracle:

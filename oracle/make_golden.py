@@ -216,7 +216,7 @@ def static_pulse_case(name, n1, n2, *, n_t, rtol, atol):
     cs, csr, f = 0.01, 25.0, 30.
     t_static = cs / csr
     delay = 0.1 / f
-    ts = np.concatenate([[0.], np.linspace(t_static + delay, t_static + delay + 0.5 / f, n_t)])
+    ts = np.concatenate([[0.], np.linspace(t_static + delay, t_static + delay + 0.2 / f, n_t)])
     run_case(name, n_blocks=geo.n_blocks, n_npb=4, bonds=bonds(), cons=cons, bond_energy=0, use_contact=True,
              drive_kind=_abi.DFX_DRIVE_STATIC_PULSE, drive_vec0=dyn, drive_vec1=sta,
              drive_params=dict(amplitude=7.5, loading_rate=f, compressive_strain=cs, compressive_strain_rate=csr,
@@ -255,7 +255,9 @@ CASES = {
     "quads_5x4_tight": lambda: quad_case("quads_5x4_tight", 5, 4, contact_window=(-15 * math.pi / 180, -10 * math.pi / 180),
                                          noise=0.2, n_t=4, t_end=0.006, rtol=1e-9, atol=1e-9, seed=3, g_mode="generic"),
     "kagome_3x2_perbond": lambda: kagome_case("kagome_3x2_perbond", 3, 2, n_t=4, t_end=0.008, rtol=1e-8, atol=1e-4),
-    "static_pulse_4x4": lambda: static_pulse_case("static_pulse_4x4", 4, 4, n_t=4, rtol=1e-8, atol=1e-4),
+    # tight tolerance: with top and bottom rows clamped this small lattice is stiff and, at atol=1e-4, borderline
+    # accept/reject decisions make the trajectory sensitive to round-off at the 1e-6 level
+    "static_pulse_4x4": lambda: static_pulse_case("static_pulse_4x4", 4, 4, n_t=3, rtol=1e-9, atol=1e-8),
     "tensile_linearized": lambda: tensile_case("tensile_linearized", 2, 1, n_t=4, t_end=60.),
     "tensile_ligament": lambda: tensile_case("tensile_ligament", 2, 0, n_t=4, t_end=60.),
 }

@@ -22,7 +22,7 @@ def _solver(spec):
 
 
 def _dev_params(c, batch=1):
-    leaves = {k: torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64, device="cuda") for k, v in c.leaves.items()}
+    leaves = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64, device="cuda").contiguous() for k, v in c.leaves.items()}
     return _abi.ParamSet(c.spec, batch, leaves, c.per_bond, c.damping_per_dof)
 
 
@@ -88,7 +88,7 @@ def test_cuda_matches_cpp_oracle_batched(name):
     g = np.cos(ys_h) + 0.3
     y0b_h, tsb_h, gr_h, sb_h = orc.adjoint(ps_h, ys_h, c.ts, g, c.rtol, c.atol)
     lib, topo = _solver(c.spec)
-    dl = {k: torch.as_tensor(np.ascontiguousarray(v), dtype=torch.float64, device="cuda") for k, v in leaves.items()}
+    dl = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64, device="cuda").contiguous() for k, v in leaves.items()}
     ps_d = _abi.ParamSet(c.spec, B, dl, c.per_bond, c.damping_per_dof)
     ys_d, st_d = lib.forward(topo, ps_d, torch.as_tensor(c.y0, device="cuda"), torch.as_tensor(c.ts, device="cuda"),
                              c.rtol, c.atol, _abi.DfxOptions(0, 0, 0))
@@ -107,3 +107,37 @@ def test_cuda_matches_cpp_oracle_batched(name):
                 assert rel_l2(got, ref) <= GRAD_TOL, (k, b)
             else:
                 assert np.abs(got - ref).max() <= 1e-9, (k, b)
+
+
+@pytest.mark.parametrize("problem", ["quads_focusing", "kagome_focusing"])
+def test_full_size_config_matches_cpp_oracle(problem):
+    """cfg1 / cfg2 of BASELINE.json at their default lattices: CUDA vs C++ oracle (trajectory, step counts,
+    gradients of the target kinetic energy w.r.t. every parameter leaf)."""
+    from oracle import Oracle
+    from difflexmm_b200.problems import KagomeFocusing, QuadsFocusing
+    P = QuadsFocusing() if problem == "quads_focusing" else KagomeFocusing()
+    spec, drive = P.lower()
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(P.initial_design())
+    lv = {k: v.numpy() for k, v in leaves.items()}
+    orc = Oracle(spec)
+    ph = orc.params(1, lv, pb, dpd)
+    ys_h, st_h = orc.forward(ph, y0.numpy(), ts.numpy(), P.rtol, P.atol)
+    nf = spec.n_free
+    g = np.zeros_like(ys_h)
+    g[:, :, nf:] = ys_h[:, :, nf:] * lv["inertia"]
+    y0b_h, tsb_h, gr_h, sb_h = orc.adjoint(ph, ys_h, ts.numpy(), g, P.rtol, P.atol, aug)
+    lib, topo = _solver(spec)
+    dl = {k: v.to("cuda").contiguous() for k, v in leaves.items()}
+    ps = _abi.ParamSet(spec, 1, dl, pb, dpd)
+    opt = _abi.DfxOptions(0, 0, 0)
+    ys_d, st_d = lib.forward(topo, ps, y0.cuda(), ts.cuda(), P.rtol, P.atol, opt)
+    assert st_d.numpy()["status"][0] == 0
+    assert rel_l2(ys_d[0].cpu().numpy(), ys_h[0]) <= TRAJ_TOL
+    assert abs(int(st_d.numpy()["steps"][0]) - int(st_h["steps"][0])) <= 0.01 * st_h["steps"][0]
+    y0b_d, tsb_d, gr_d, sb_d = lib.adjoint(topo, ps, torch.as_tensor(ys_h, device="cuda"), ts.cuda(),
+                                           torch.as_tensor(g, device="cuda"), P.rtol, P.atol, aug, opt)
+    assert sb_d.numpy()["status"][0] == 0
+    assert abs(int(sb_d.numpy()["steps"][0]) - int(sb_h["steps"][0])) <= 0.01 * sb_h["steps"][0]
+    for k in gr_h:
+        assert rel_l2(gr_d[k][0].cpu().numpy(), gr_h[k][0]) <= GRAD_TOL, k
+    assert rel_l2(tsb_d[0].cpu().numpy(), tsb_h[0]) <= GRAD_TOL

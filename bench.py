@@ -90,10 +90,16 @@ class ClockSampler:
                 "reasons": sorted(reasons), "samples": len(self.rows)}
 
 
+HORIZON_SCALE = 1.0  # < 1 only for profiling runs (ncu replays every launch dozens of times)
+
+
 def build_problem(n_designs, seed0):
     import torch
     from difflexmm_b200.problems import QuadsFocusing
     prob = QuadsFocusing()
+    if HORIZON_SCALE != 1.0:
+        prob.simulation_time *= HORIZON_SCALE
+        prob.n_timepoints = max(2, int(round(prob.n_timepoints * HORIZON_SCALE)))
     spec, drive = prob.lower()
     hs, vs = prob.random_ensemble(n_designs, noise=0.15, seed0=seed0)
     leaves, pb, dpd, aug, y0, ts = prob.boundary_inputs((hs, vs), batch=n_designs, device="cpu")
@@ -138,7 +144,11 @@ def main():
     ap.add_argument("--designs", type=int, default=1024, help="designs per GPU per step")
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--horizon-scale", type=float, default=1.0,
+                    help="profiling only: shorten the simulated time and n_timepoints by this factor (invalid as a bench value)")
     args = ap.parse_args()
+    global HORIZON_SCALE
+    HORIZON_SCALE = args.horizon_scale
     rank = int(os.environ.get("RANK", "0"))
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
@@ -147,6 +157,8 @@ def main():
                           "n_t=200, rtol=1e-8, atol=1e-4, contact on, noise 0.15*spacing",
               "designs_per_gpu": args.designs, "parallelism": f"designs sharded over {world} rank(s), no collective",
               "l2": "inputs larger than L2 (ys + cotangent = 7 MB per design)"}
+    if args.horizon_scale != 1.0:
+        config["PROFILING_ONLY_horizon_scale"] = args.horizon_scale
 
     if args.impl == "reference":
         if rank != 0:

@@ -40,6 +40,7 @@ enum {
 
 struct PlacementA { long long off[AA_COUNT]; };
 
+constexpr int SCW = 16;    // per-warp partial slots per scalar leaf (CTAs have at most 512 threads = 16 warps)
 constexpr int NSCAL = 13;  // 0 t0_bar | 1-3 k_stretch,k_shear,k_rot | 4 damping | 5-7 contact | 8-12 drive
 constexpr int SC_T0 = 0, SC_KS = 1, SC_KSH = 2, SC_KR = 3, SC_DAMP = 4, SC_CONTACT = 5, SC_DRIVE = 8;
 
@@ -113,9 +114,10 @@ struct ScalCtx {
   double *wk1, *wk7, *wsol, *werr, *wmid;  // [NSCAL][32]
 };
 __device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, int which, double partial) {
-  const double v = warp_sum(partial);
+  // most warps contribute nothing to the sparse scalars (contact, drive, t0): skip their shuffles
+  const double v = __any_sync(0xffffffffu, partial != 0.0) ? warp_sum(partial) : 0.0;
   if ((threadIdx.x & 31) != 0) return;
-  const int idx = which * 32 + (threadIdx.x >> 5);
+  const int idx = which * SCW + (threadIdx.x >> 5);
   switch (c.mode) {
     case 0: s.wk1[idx] = v; break;
     case 7: s.wk7[idx] = v; break;
@@ -166,8 +168,8 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
   double* Sq0 = SC;
   double* Sqnew = SC + NSCAL;
   ScalCtx sc;
-  sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * 32; sc.wsol = sc.wk7 + NSCAL * 32;
-  sc.werr = sc.wsol + NSCAL * 32; sc.wmid = sc.werr + NSCAL * 32;
+  sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * SCW; sc.wsol = sc.wk7 + NSCAL * SCW;
+  sc.werr = sc.wsol + NSCAL * SCW; sc.wmid = sc.werr + NSCAL * SCW;
 
   const double* g_ks = leaf_ptr(a.p.k_stretch, design);
   const double* g_ksh = leaf_ptr(a.p.k_shear, design);
@@ -186,7 +188,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
   for (int i = tid; i < 3 * NN; i += nthr) { Fs[i] = 0.0; Hs[i] = 0.0; }
   for (int i = tid; i < 2 * NN; i += nthr) { Gs[i] = 0.0; if (Ga) Ga[i] = 0.0; }
   for (int i = tid; i < NQ; i += nthr) { qc.q0[i] = 0.0; qc.k1[i] = 0.0; qc.k7[i] = 0.0; qc.qnew[i] = 0.0; qc.asol[i] = 0.0; qc.aerr[i] = 0.0; qc.amid[i] = 0.0; }
-  for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * 32; i += nthr) SC[i] = 0.0;
+  for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * SCW; i += nthr) SC[i] = 0.0;
   double cmin = 0, ccut = 0, ckc = 0;
   if (T.contact) { cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
   // y_bar = g[-1]
@@ -350,7 +352,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
   // total of a scalar leaf's per-warp partials
   auto wtotal = [&](const double* wa, int which) {
     double s = 0.0;
-    for (int w = 0; w < nwarp; ++w) s += wa[which * 32 + w];
+    for (int w = 0; w < nwarp; ++w) s += wa[which * SCW + w];
     return s;
   };
 
@@ -530,7 +532,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
             u0[e] = Us[e]; v0[e] = Vs[e]; lu0[e] = Lus[e]; lv0[e] = Lvs[e];
             kv[e] = kv[6 * ND + e]; klu[e] = klu[6 * ND + e]; klv[e] = klv[6 * ND + e];
           }
-          if (tid < NSCAL) for (int w = 0; w < nwarp; ++w) sc.wk1[tid * 32 + w] = sc.wk7[tid * 32 + w];
+          if (tid < NSCAL) for (int w = 0; w < nwarp; ++w) sc.wk1[tid * SCW + w] = sc.wk7[tid * SCW + w];
           double* tmp = qc.k1; qc.k1 = qc.k7; qc.k7 = tmp;
         }
         if (tid < NSCAL) Sq0[tid] = Sqnew[tid];

@@ -6,7 +6,10 @@
 #include <new>
 #include <vector>
 
-#include "dfx_adjoint.cuh"
+#include <cstdlib>
+#include <type_traits>
+
+#include "dfx_adjoint2.cuh"
 
 using namespace dfx;
 
@@ -45,6 +48,7 @@ cudaError_t upload(const std::vector<T>& h, T** d) {
 struct DfxTopology {
   int device;
   DevTopo dev;
+  const int* node_bond;  // [n_nodes] bond*2+side or -1 (fast adjoint kernel)
   std::vector<void*> allocs;
   int sm_count;
 };
@@ -103,7 +107,7 @@ void adjoint_sizes(const DevTopo& T, const QuadLayout& q, long long (&sz)[AA_COU
   const long long NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds;
   sz[AA_US] = 5 * NB; sz[AA_WS] = 3 * NB; sz[AA_VS] = 3 * NB; sz[AA_LUS] = 3 * NB; sz[AA_LVS] = 3 * NB;
   sz[AA_FS] = 3 * NN; sz[AA_HS] = 3 * NN; sz[AA_GS] = 2 * NN; sz[AA_GA] = T.contact ? 2 * NN : 0;
-  sz[AA_SC] = 2 * NSCAL + 5 * NSCAL * 32;
+  sz[AA_SC] = 2 * NSCAL + 5 * NSCAL * SCW;
   sz[AA_INVM] = 3 * NB; sz[AA_CD] = 3 * NB;
   sz[AA_U0] = 3 * NB; sz[AA_V0] = 3 * NB; sz[AA_LU0] = 3 * NB; sz[AA_LV0] = 3 * NB;
   sz[AA_KV] = 21 * NB; sz[AA_KLU] = 21 * NB; sz[AA_KLV] = 21 * NB;
@@ -128,6 +132,35 @@ int pick_threads(const DevTopo& T, int requested) {
   if (t < 32) t = 32;
   if (t > 512) t = 512;
   return t;
+}
+
+// launch plan of the fast adjoint kernel (dfx_adjoint2.cuh); ok=false -> use the generic kernel
+struct FastPlan { bool ok; int threads, nt, ns, cols_per_warp; size_t smem; long long scratch; };
+
+FastPlan plan_fast_adjoint(const DevTopo& T) {
+  FastPlan f = {};
+  const char* mode = getenv("DFX_ADJOINT_KERNEL");  // "generic" | "notmem" | unset (fast + TMEM)
+  if (mode && !strcmp(mode, "generic")) return f;
+  int t = T.n_blocks > (T.n_bonds + 1) / 2 ? T.n_blocks : (T.n_bonds + 1) / 2;
+  t = t <= 384 ? 384 : 512;  // the CTA size is a compile-time constant of the kernel (addresses become immediates)
+  if (T.n_npb > 4 || T.n_blocks > t || T.n_bonds > 2 * t) return f;
+  const int nwarp = t / 32, groups = (nwarp + 3) / 4;
+  f.cols_per_warp = (512 / groups) & ~1;
+  f.nt = f.cols_per_warp >= 168 ? 84 : (f.cols_per_warp >= 128 ? 64 : 0);
+  if (mode && !strcmp(mode, "notmem")) f.nt = 0;
+  const size_t fixed = (size_t)(40 + 8LL * T.n_blocks + 14LL * T.n_bonds + (2 * NSCAL + 5 * NSCAL * SCW) + 32) * 8 +
+                       (size_t)((T.n_nodes + 1) & ~1) * 4;
+  const size_t cap = kSmemBytes - 1024;
+  if (fixed + 8 * (size_t)t > cap) return f;
+  int ns = (int)((cap - fixed) / (8 * (size_t)t));
+  if (ns > S_NCONST - f.nt) ns = S_NCONST - f.nt;
+  f.ns = ns;
+  f.smem = fixed + (size_t)ns * t * 8;
+  const int n_over = S_NCONST - f.nt - ns > 0 ? S_NCONST - f.nt - ns : 0;  // constants that spill to global
+  f.scratch = (long long)(n_over + (NQA + 1) * NE) * t + 32;
+  f.threads = t;
+  f.ok = true;
+  return f;
 }
 
 int check_params(const DevTopo& T, const DfxParams* p) {
@@ -183,6 +216,7 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
       load_mul[dof] = d->load_vec ? d->load_vec[l] : 1.0;
     }
   std::vector<int2> bn(d->n_bonds), bb(d->n_bonds);
+  std::vector<int> node_bond(n_nodes, -1);
   for (int b = 0; b < d->n_bonds; ++b) {
     const int na = d->bond_nodes[2 * b], nb = d->bond_nodes[2 * b + 1];
     if (na < 0 || na >= n_nodes || nb < 0 || nb >= n_nodes) return fail(DFX_ERR_INVALID, "bond %d refers to a node out of range", b);
@@ -192,6 +226,8 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
                   "requires at most one bond per vertex, as in every geometry class of the reference", b);
     bn[b] = make_int2(na, nb);
     bb[b] = make_int2(na / d->n_npb, nb / d->n_npb);
+    node_bond[na] = 2 * b;
+    node_bond[nb] = 2 * b + 1;
   }
   int cur = 0;
   CUDA_TRY(cudaGetDevice(&cur));
@@ -206,7 +242,7 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   D.bond_energy = d->bond_energy; D.contact = d->contact ? 1 : 0; D.drive_kind = d->drive_kind;
   D.load_kind = d->load_kind; D.n_drive_params = n_drive_params_of(d->drive_kind); D.n_damped = d->n_damped;
   for (int i = 0; i < DFX_MAX_LOAD_CONSTS; ++i) D.load_consts[i] = d->load_consts[i];
-  int2 *dbn, *dbb; int *dfo, *dcs, *dds, *dfd; double *dv0, *dv1, *dlm;
+  int2 *dbn, *dbb; int *dfo, *dcs, *dds, *dfd, *dnb; double *dv0, *dv1, *dlm;
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(bn, &dbn);
   if (e == cudaSuccess) e = upload(bb, &dbb);
@@ -217,13 +253,20 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   if (e == cudaSuccess) e = upload(v0, &dv0);
   if (e == cudaSuccess) e = upload(v1, &dv1);
   if (e == cudaSuccess) e = upload(load_mul, &dlm);
+  if (e == cudaSuccess) e = upload(node_bond, &dnb);
   if (e != cudaSuccess) { delete t; cudaSetDevice(cur); return fail(DFX_ERR_CUDA, "topology upload failed: %s", cudaGetErrorString(e)); }
   D.bond_nodes = dbn; D.bond_blocks = dbb; D.free_of_dof = dfo; D.cons_slot = dcs; D.damp_slot = dds; D.free_dofs = dfd;
   D.drive_vec0 = dv0; D.drive_vec1 = dv1; D.load_mul = dlm;
-  t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm};
+  t->node_bond = dnb;
+  t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm, dnb};
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   cudaFuncSetAttribute(adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaFuncSetAttribute(adjoint2_kernel<84, 32, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
+  cudaFuncSetAttribute(adjoint2_kernel<84, -1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
+  cudaFuncSetAttribute(adjoint2_kernel<64, -1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
+  cudaFuncSetAttribute(adjoint2_kernel<0, -1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
+  cudaFuncSetAttribute(adjoint2_kernel<0, -1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaSetDevice(cur);
   *out = t;
   return DFX_OK;
@@ -260,6 +303,10 @@ size_t dfx_adjoint_workspace_bytes(const DfxTopology* t, int batch) {
   size_t smem;
   adjoint_sizes(t->dev, q, sz);
   plan(sz, off, &smem, &g);
+  FastPlan f = plan_fast_adjoint(t->dev);
+  // worst case of the two kernels (the fast one assumes S_TOTAL slots with no TMEM)
+  long long fast = f.ok ? (long long)(S_NCONST - f.ns + (NQA + 1) * NE) * f.threads + 32 : 0;
+  if (fast > g) g = fast;
   return (size_t)g * sizeof(double) * (size_t)batch;
 }
 
@@ -339,6 +386,8 @@ int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const 
   a.y0_bar = y0_bar; a.ts_bar = ts_bar;
   if (grads) a.grads = *grads;
   a.stats = stats;
+  const FastPlan fp = plan_fast_adjoint(T);
+  if (fp.ok) g = fp.scratch;
   a.scratch_per_design = g;
   bool own_ws = false;
   if (g > 0) {
@@ -351,8 +400,22 @@ int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const 
       own_ws = true;
     }
   }
-  const int threads = pick_threads(T, opt ? opt->threads : 0);
-  adjoint_kernel<<<batch, threads, smem, stream>>>(a);
+  if (fp.ok) {
+    Adj2Args A2;
+    A2.a = a;
+    A2.node_bond = t->node_bond;
+    A2.tp_scratch_per_design = fp.scratch;
+    A2.ns_slots = fp.ns;
+    A2.tmem_cols_per_warp = fp.cols_per_warp;
+    if (fp.nt == 84 && fp.ns == 32) adjoint2_kernel<84, 32, 384><<<batch, 384, fp.smem, stream>>>(A2);
+    else if (fp.nt == 84) adjoint2_kernel<84, -1, 384><<<batch, 384, fp.smem, stream>>>(A2);
+    else if (fp.nt == 64) adjoint2_kernel<64, -1, 512><<<batch, 512, fp.smem, stream>>>(A2);
+    else if (fp.threads == 384) adjoint2_kernel<0, -1, 384><<<batch, 384, fp.smem, stream>>>(A2);
+    else adjoint2_kernel<0, -1, 512><<<batch, 512, fp.smem, stream>>>(A2);
+  } else {
+    const int threads = pick_threads(T, opt ? opt->threads : 0);
+    adjoint_kernel<<<batch, threads, smem, stream>>>(a);
+  }
   cudaError_t e = cudaGetLastError();
   if (own_ws) cudaFreeAsync(a.scratch, stream);
   if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "adjoint_kernel launch failed: %s", cudaGetErrorString(e));

@@ -208,18 +208,8 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
     for (int b = tid; b < NBONDS; b += nthr) {
       const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
       BlockState<Dual> s1, s2;
-      s1.x = Dual(Us[bl.x], Ws[bl.x]); s1.y = Dual(Us[NB + bl.x], Ws[NB + bl.x]);
-      s1.th = Dual(Us[2 * NB + bl.x], Ws[2 * NB + bl.x]);
-      {
-        const double sn = Us[3 * NB + bl.x], cs = Us[4 * NB + bl.x];
-        s1.s = Dual(sn, cs * s1.th.d); s1.c = Dual(cs, -sn * s1.th.d);
-      }
-      s2.x = Dual(Us[bl.y], Ws[bl.y]); s2.y = Dual(Us[NB + bl.y], Ws[NB + bl.y]);
-      s2.th = Dual(Us[2 * NB + bl.y], Ws[2 * NB + bl.y]);
-      {
-        const double sn = Us[3 * NB + bl.y], cs = Us[4 * NB + bl.y];
-        s2.s = Dual(sn, cs * s2.th.d); s2.c = Dual(cs, -sn * s2.th.d);
-      }
+      make_block(Us[bl.x], Us[NB + bl.x], Us[2 * NB + bl.x], Us[3 * NB + bl.x], Us[4 * NB + bl.x], Ws[bl.x], Ws[NB + bl.x], Ws[2 * NB + bl.x], s1);
+      make_block(Us[bl.y], Us[NB + bl.y], Us[2 * NB + bl.y], Us[3 * NB + bl.y], Us[4 * NB + bl.y], Ws[bl.y], Ws[NB + bl.y], Ws[2 * NB + bl.y], s2);
       BondConst bc = {bondc[b], bondc[NBONDS + b], bondc[2 * NBONDS + b], bondc[3 * NBONDS + b]};
       const double ks = g_ks[ks_pb ? b : 0], ksh = g_ksh[ksh_pb ? b : 0], kr = g_kr[kr_pb ? b : 0];
       BondOut<Dual> o;

@@ -27,7 +27,7 @@ constexpr int S_U0 = 63, S_V0 = 66, S_LU0 = 69, S_LV0 = 72;   // state at the st
 constexpr int S_TV = 75, S_TLU = 78, S_TW = 81;               // stage v, lambda_u, w parked across the bond phase
 constexpr int S_INVM = 84, S_CD = 87;                         // 1/m and damping coefficient of the 3 DOFs
 constexpr int S_BOND = 90;                                    // per bond (2 per thread) constants
-constexpr int BC_R0X = 0, BC_R0Y = 1, BC_L0 = 2, BC_PHI0 = 3, BC_R1X = 4, BC_R1Y = 5, BC_R2X = 6, BC_R2Y = 7,
+constexpr int BC_R0X = 0, BC_R0Y = 1, BC_L0 = 2, BC_IL0 = 3, BC_R1X = 4, BC_R1Y = 5, BC_R2X = 6, BC_R2Y = 7,
               BC_DA1 = 8, BC_DA2 = 9, BC_N = 10;
 constexpr int S_KPBC = S_BOND + 2 * BC_N;                     // 110: per-bond stiffness values [2 bonds][3] (per-bond leaves only)
 constexpr int S_NCONST = S_KPBC + 6;                          // 116 slots in the TMEM / shared / global tiers
@@ -108,14 +108,33 @@ struct TP {
   __device__ __forceinline__ void fence_st() const { if (NT > 0) tmem_st_wait(); }
 };
 
-// scalar-leaf update kept out of line: it is called ~13 times per evaluation and is not on the critical path
-__device__ __noinline__ void scal_update_nl(int mode, double cs, double ce, double cm, double cs0, double ce0, double cm0,
-                                            double* wbase, int which, double partial) {
-  QuadCtx c;
-  c.mode = mode; c.cs = cs; c.ce = ce; c.cm = cm; c.cs0 = cs0; c.ce0 = ce0; c.cm0 = cm0;
-  ScalCtx s;
-  s.wk1 = wbase; s.wk7 = s.wk1 + NSCAL * SCW; s.wsol = s.wk7 + NSCAL * SCW; s.werr = s.wsol + NSCAL * SCW; s.wmid = s.werr + NSCAL * SCW;
-  scal_update(c, s, which, partial);
+// scalar-leaf update kept out of line (not on the critical path): up to three consecutive scalar leaves per call,
+// their warp reductions interleaved
+__device__ __noinline__ void scal_update3_nl(int mode, double cs, double ce, double cm, double cs0, double ce0, double cm0,
+                                             double* wbase, int which, int n, double p0, double p1, double p2) {
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+    p0 += __shfl_xor_sync(0xffffffffu, p0, o);
+    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
+    p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+  }
+  if ((threadIdx.x & 31) != 0) return;
+  double* wk1 = wbase; double* wk7 = wk1 + NSCAL * SCW; double* wsol = wk7 + NSCAL * SCW;
+  double* werr = wsol + NSCAL * SCW; double* wmid = werr + NSCAL * SCW;
+  for (int k = 0; k < n; ++k) {
+    const double v = k == 0 ? p0 : (k == 1 ? p1 : p2);
+    const int idx = (which + k) * SCW + (threadIdx.x >> 5);
+    switch (mode) {
+      case 0: wk1[idx] = v; break;
+      case 7: wk7[idx] = v; break;
+      case 2: {
+        const double k1 = wk1[idx];
+        wsol[idx] = cs0 * k1 + cs * v; werr[idx] = ce0 * k1 + ce * v; wmid[idx] = cm0 * k1 + cm * v;
+      } break;
+      case 6: werr[idx] += ce * v; wmid[idx] += cm * v; wk7[idx] = v; break;
+      default: wsol[idx] += cs * v; werr[idx] += ce * v; wmid[idx] += cm * v; break;
+    }
+  }
 }
 
 struct Adj2Args {
@@ -137,13 +156,15 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int nthr = TT, nwarp = TT / 32;
   const int NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;
+  // array strides of the shared stage / slot arrays: compile-time in the specialised variant (addresses become immediates)
+  const int NBS = NS >= 0 ? TT : NB, NDS = NS >= 0 ? 2 * TT : NBONDS;
 
   // ---- carve shared memory: red[40] | Us[5][NB] | Ws[3][NB] | SL[14][NBONDS] | SC | drv[32] | nodeb[NN] | tp[ns][T]
   double* red = smem;
   double* Us = red + 40;
-  double* Ws = Us + 5 * NB;
-  double* SL = Ws + 3 * NB;  // per bond: gdx gdy T1 T2 | hx hy H1 H2 | g1x g1y g2x g2y | a1 a2
-  double* SC = SL + 14 * NBONDS;
+  double* Ws = Us + 5 * NBS;
+  double* SL = Ws + 3 * NBS;  // per bond: gdx gdy T1 T2 | hx hy H1 H2 | g1x g1y g2x g2y | a1 a2
+  double* SC = SL + 14 * NDS;
   double* drv = SC + (2 * NSCAL + 5 * NSCAL * SCW);
   int* nodeb = (int*)(drv + 32);
   double* tp_s = (double*)(nodeb + ((NN + 1) & ~1));
@@ -217,11 +238,17 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     dslot[j] = T.damp_slot[dof];
   }
   const bool has_cons = cslot[0] >= 0 || cslot[1] >= 0 || cslot[2] >= 0;
+  bool has_load = false;
+  if (T.load_kind != DFX_LOAD_NONE && has_blk)
+    for (int j = 0; j < 3; ++j) has_load |= T.load_mul[3 * blk + j] != 0.0;
+  const bool warp_t0 = __any_sync(0xffffffffu, has_cons || has_load);
+  bool warp_contact = false;
+  const int2 bb0 = T.bond_blocks[bnd[0]], bb1 = T.bond_blocks[bnd[1]];
 
   // ---- constants into the thread-private store -------------------------------------------------------------
   for (int i = tid; i < NN; i += nthr) nodeb[i] = A.node_bond[i];
   for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * SCW; i += nthr) SC[i] = 0.0;
-  for (int i = tid; i < 14 * NBONDS; i += nthr) SL[i] = 0.0;
+  for (int i = tid; i < 14 * NDS; i += nthr) SL[i] = 0.0;
   for (int i = tid; i < 32; i += nthr) drv[i] = 0.0;
   if (tid == 0) { drv[30] = nan(""); drv[31] = nan(""); }
 #pragma unroll
@@ -240,7 +267,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     const int2 nd = T.bond_nodes[b];
     const double rx = g_ref[2 * b], ry = g_ref[2 * b + 1];
     tp.st(s0 + BC_R0X, rx); tp.st(s0 + BC_R0Y, ry);
-    tp.st(s0 + BC_L0, sqrt(rx * rx + ry * ry)); tp.st(s0 + BC_PHI0, atan2(ry, rx));
+    tp.st(s0 + BC_L0, sqrt(rx * rx + ry * ry)); tp.st(s0 + BC_IL0, 1.0 / sqrt(rx * rx + ry * ry));
     tp.st(s0 + BC_R1X, g_cnv[2 * nd.x]); tp.st(s0 + BC_R1Y, g_cnv[2 * nd.x + 1]);
     tp.st(s0 + BC_R2X, g_cnv[2 * nd.y]); tp.st(s0 + BC_R2Y, g_cnv[2 * nd.y + 1]);
     double da1 = 0.0, da2 = 0.0;
@@ -270,7 +297,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
   sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * SCW; sc.wsol = sc.wk7 + NSCAL * SCW;
   sc.werr = sc.wsol + NSCAL * SCW; sc.wmid = sc.werr + NSCAL * SCW;
 
-#define SCAL(which, partial) scal_update_nl(qc.mode, qc.cs, qc.ce, qc.cm, qc.cs0, qc.ce0, qc.cm0, sc.wk1, which, partial)
+#define SCAL3(which, n, p0, p1, p2) scal_update3_nl(qc.mode, qc.cs, qc.ce, qc.cm, qc.cs0, qc.ce0, qc.cm0, sc.wk1, which, n, p0, p1, p2)
   QuadCtx qc;  // pointer fields unused here
   qc.atol = atol; qc.rtol = rtol; qc.crossing = false; qc.x = 0; qc.h = 0; qc.mode = 0;
   qc.cs = qc.ce = qc.cm = qc.cs0 = qc.ce0 = qc.cm0 = 0;
@@ -283,29 +310,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     const int mode = qc.mode;
     const int a_q0 = QA_Q0 + par, a_qn = QA_Q0 + 1 - par, a_k1 = QA_K1 + par, a_k7 = QA_K1 + 1 - par;
     if (mode >= 2 && mode <= 5) {
-      // sol = (first ? c_sol[0]*k1 : sol) + c_sol[j]*val, same for err (and the midpoint sum on crossing steps)
-      const bool first = mode == 2;
-      const int a_s = first ? a_k1 : QA_SOL, a_e = first ? a_k1 : QA_ERR, a_m = first ? a_k1 : a_k7;
-      const double fs = first ? qc.cs0 : 1.0, fe = first ? qc.ce0 : 1.0, fm = first ? qc.cm0 : 1.0;
-#pragma unroll
-      for (int c0 = 0; c0 < NE; c0 += 8) {
-        if (c0 < ne_used) {
-          double s_in[8], e_in[8];
-#pragma unroll
-          for (int k = 0; k < 8; ++k) { s_in[k] = Q(a_s, c0 + k); e_in[k] = Q(a_e, c0 + k); }
-#pragma unroll
-          for (int k = 0; k < 8; ++k) {
-            Q(QA_SOL, c0 + k) = fma(qc.cs, qv[c0 + k], fs * s_in[k]);
-            Q(QA_ERR, c0 + k) = fma(qc.ce, qv[c0 + k], fe * e_in[k]);
-          }
-          if (qc.crossing) {
-#pragma unroll
-            for (int k = 0; k < 8; ++k) s_in[k] = Q(a_m, c0 + k);
-#pragma unroll
-            for (int k = 0; k < 8; ++k) Q(a_k7, c0 + k) = fma(qc.cm, qv[c0 + k], fm * s_in[k]);
-          }
-        }
-      }
+      // handled by the prefetch / commit path of aug_BC
     } else if (mode == 6) {
       if (!qc.crossing) {
 #pragma unroll
@@ -352,6 +357,22 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     return acc;
   };
 
+  // Accumulating stages (RK stages 2..5 of a step): the running solution / error sums of a group of entries are
+  // fetched early (before the bond arithmetic or the CTA barrier) and committed once the integrands are known, so
+  // the L2 latency of the thread-private quadratures overlaps with computation.
+  struct AccCoef { int a_s, a_e, a_m, a_k7; double fs, fe, fm; bool on; };
+  auto acc_coef = [&]() {
+    AccCoef c;
+    const int mode = qc.mode;
+    c.on = mode >= 2 && mode <= 5;
+    const bool first = mode == 2;
+    const int a_k1 = QA_K1 + par;
+    c.a_k7 = QA_K1 + 1 - par;
+    c.a_s = first ? a_k1 : QA_SOL; c.a_e = first ? a_k1 : QA_ERR; c.a_m = first ? a_k1 : c.a_k7;
+    c.fs = first ? qc.cs0 : 1.0; c.fe = first ? qc.ce0 : 1.0; c.fm = first ? qc.cm0 : 1.0;
+    return c;
+  };
+
   // ---- one augmented RHS evaluation: phases B and C.  The stage v, lambda_u and w of this thread's unit
   // are parked in the thread-private store by publish(); derivative stage `kidx` is written there too.
   // `time_next`: real time of the next evaluation when it is already known (drive channels are prepared for it).
@@ -363,6 +384,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     __syncthreads();
     // ============ phase B: bonds ============
     double p_ks = 0, p_ksh = 0, p_kr = 0, p_c0 = 0, p_c1 = 0, p_c2 = 0;
+    const AccCoef ac = acc_coef();
+    constexpr int NEB = NE - E_REF;  // bond-owned entries: reference vector (+ per-bond stiffnesses)
     if (tid == nthr - 1 && T.drive_kind != DFX_DRIVE_ZERO) {  // drive channels: now (with derivatives) and next
       DriveEval de;
       drive_eval(T.drive_kind, time, g_drive, true, de);
@@ -375,18 +398,15 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
 #pragma unroll 1
     for (int i = 0; i < 2; ++i) {
       const int b = bnd[i];
-      const int2 bl = T.bond_blocks[b];
-      const int b1 = bl.x, b2 = bl.y;
+      const int b1 = i == 0 ? bb0.x : bb1.x, b2 = i == 0 ? bb0.y : bb1.y;
       double c[BC_N];
       tp.template ldn<BC_N>(S_BOND + i * BC_N, 1, c);
       double ks = ks_u, ksh = ksh_u, kr = kr_u;
       if (any_pb) { ks = tp.ldc(S_KPBC + 3 * i); ksh = tp.ldc(S_KPBC + 3 * i + 1); kr = tp.ldc(S_KPBC + 3 * i + 2); }
       BlockState<Dual> s1, s2;
-      s1.x = Dual(Us[b1], Ws[b1]); s1.y = Dual(Us[NB + b1], Ws[NB + b1]); s1.th = Dual(Us[2 * NB + b1], Ws[2 * NB + b1]);
-      { const double sn = Us[3 * NB + b1], cs = Us[4 * NB + b1]; s1.s = Dual(sn, cs * s1.th.d); s1.c = Dual(cs, -sn * s1.th.d); }
-      s2.x = Dual(Us[b2], Ws[b2]); s2.y = Dual(Us[NB + b2], Ws[NB + b2]); s2.th = Dual(Us[2 * NB + b2], Ws[2 * NB + b2]);
-      { const double sn = Us[3 * NB + b2], cs = Us[4 * NB + b2]; s2.s = Dual(sn, cs * s2.th.d); s2.c = Dual(cs, -sn * s2.th.d); }
-      BondConst bc = {c[BC_R0X], c[BC_R0Y], c[BC_L0], c[BC_PHI0]};
+      make_block(Us[b1], Us[NBS + b1], Us[2 * NBS + b1], Us[3 * NBS + b1], Us[4 * NBS + b1], Ws[b1], Ws[NBS + b1], Ws[2 * NBS + b1], s1);
+      make_block(Us[b2], Us[NBS + b2], Us[2 * NBS + b2], Us[3 * NBS + b2], Us[4 * NBS + b2], Ws[b2], Ws[NBS + b2], Ws[2 * NBS + b2], s2);
+      BondConst bc = {c[BC_R0X], c[BC_R0Y], c[BC_L0], c[BC_IL0]};
       BondOut<Dual> o;
       bond_gradient<Dual, true>(T.bond_energy, s1, s2, c[BC_R1X], c[BC_R1Y], c[BC_R2X], c[BC_R2Y], bc, ks, ksh, kr, o);
       double a1 = 0.0, a2 = 0.0;
@@ -406,23 +426,38 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
       }
       if (has_bnd[i]) {
         // forces on the two ends are equal and opposite: store (gdx, gdy) once, the two torques separately
-        SL[b] = o.f2[0].v; SL[NBONDS + b] = o.f2[1].v; SL[2 * NBONDS + b] = -o.f1[2].v; SL[3 * NBONDS + b] = -o.f2[2].v;
-        SL[4 * NBONDS + b] = o.f2[0].d; SL[5 * NBONDS + b] = o.f2[1].d; SL[6 * NBONDS + b] = o.f1[2].d; SL[7 * NBONDS + b] = o.f2[2].d;
-        SL[8 * NBONDS + b] = -o.gr1[0].d; SL[9 * NBONDS + b] = -o.gr1[1].d;
-        SL[10 * NBONDS + b] = -o.gr2[0].d; SL[11 * NBONDS + b] = -o.gr2[1].d;
-        if (contact) { SL[12 * NBONDS + b] = a1; SL[13 * NBONDS + b] = a2; }
+        SL[b] = o.f2[0].v; SL[NDS + b] = o.f2[1].v; SL[2 * NDS + b] = -o.f1[2].v; SL[3 * NDS + b] = -o.f2[2].v;
+        SL[4 * NDS + b] = o.f2[0].d; SL[5 * NDS + b] = o.f2[1].d; SL[6 * NDS + b] = o.f1[2].d; SL[7 * NDS + b] = o.f2[2].d;
+        SL[8 * NDS + b] = -o.gr1[0].d; SL[9 * NDS + b] = -o.gr1[1].d;
+        SL[10 * NDS + b] = -o.gr2[0].d; SL[11 * NDS + b] = -o.gr2[1].d;
+        if (contact) { SL[12 * NDS + b] = a1; SL[13 * NDS + b] = a2; }
         // d(w.F)/dp = -(dual part of dE/dp)
-        qv[E_REF + 2 * i] = -o.gr0[0].d; qv[E_REF + 2 * i + 1] = -o.gr0[1].d;
-        if (ks_pb) qv[E_KPB + 3 * i] = -o.gks.d; else p_ks -= o.gks.d;
-        if (ksh_pb) qv[E_KPB + 3 * i + 1] = -o.gksh.d; else p_ksh -= o.gksh.d;
-        if (kr_pb) qv[E_KPB + 3 * i + 2] = -o.gkr.d; else p_kr -= o.gkr.d;
+        // (static indices keep qv in registers although the bond loop is not unrolled)
+        if (i == 0) { qv[E_REF] = -o.gr0[0].d; qv[E_REF + 1] = -o.gr0[1].d; }
+        else { qv[E_REF + 2] = -o.gr0[0].d; qv[E_REF + 3] = -o.gr0[1].d; }
+        if (ks_pb) { if (i == 0) qv[E_KPB] = -o.gks.d; else qv[E_KPB + 3] = -o.gks.d; } else p_ks -= o.gks.d;
+        if (ksh_pb) { if (i == 0) qv[E_KPB + 1] = -o.gksh.d; else qv[E_KPB + 4] = -o.gksh.d; } else p_ksh -= o.gksh.d;
+        if (kr_pb) { if (i == 0) qv[E_KPB + 2] = -o.gkr.d; else qv[E_KPB + 5] = -o.gkr.d; } else p_kr -= o.gkr.d;
+      }
+    }
+    if (ac.on && want_q) {
+      // bond-owned entries: all loads first, then the updates
+      double bs_in[NEB], be_in[NEB];
+#pragma unroll
+      for (int k = 0; k < NEB; ++k) if (E_REF + k < ne_used) { bs_in[k] = Q(ac.a_s, E_REF + k); be_in[k] = Q(ac.a_e, E_REF + k); }
+#pragma unroll
+      for (int k = 0; k < NEB; ++k) if (E_REF + k < ne_used) {
+        Q(QA_SOL, E_REF + k) = fma(qc.cs, qv[E_REF + k], ac.fs * bs_in[k]);
+        Q(QA_ERR, E_REF + k) = fma(qc.ce, qv[E_REF + k], ac.fe * be_in[k]);
       }
     }
     if (want_q) {
-      if (!ks_pb) SCAL(SC_KS, p_ks);
-      if (!ksh_pb) SCAL(SC_KSH, p_ksh);
-      if (!kr_pb) SCAL(SC_KR, p_kr);
-      if (contact) { SCAL(SC_CONTACT, p_c0); SCAL(SC_CONTACT + 1, p_c1); SCAL(SC_CONTACT + 2, p_c2); }
+      if (!ks_pb || !ksh_pb || !kr_pb) SCAL3(SC_KS, 3, ks_pb ? 0.0 : p_ks, ksh_pb ? 0.0 : p_ksh, kr_pb ? 0.0 : p_kr);
+      if (contact) {
+        // a warp takes part in the contact scalars from the first time one of its bonds touches (sticky)
+        warp_contact = warp_contact || __any_sync(0xffffffffu, p_c0 != 0.0 || p_c1 != 0.0 || p_c2 != 0.0);
+        if (warp_contact) SCAL3(SC_CONTACT, 3, p_c0, p_c1, p_c2);
+      }
     }
     __syncthreads();
     // ============ phase C: this thread's unit ============
@@ -435,12 +470,12 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
           const int b = nb_ >> 1;
           const bool second = nb_ & 1;
           const double sg = second ? -1.0 : 1.0;
-          F[0] += sg * SL[b]; F[1] += sg * SL[NBONDS + b]; F[2] += SL[(second ? 3 : 2) * NBONDS + b];
-          HW[0] -= sg * SL[4 * NBONDS + b]; HW[1] -= sg * SL[5 * NBONDS + b]; HW[2] += SL[(second ? 7 : 6) * NBONDS + b];
-          qv[E_CNV + l] = SL[(second ? 10 : 8) * NBONDS + b]; qv[E_CNV + 4 + l] = SL[(second ? 11 : 9) * NBONDS + b];
+          F[0] += sg * SL[b]; F[1] += sg * SL[NDS + b]; F[2] += SL[(second ? 3 : 2) * NDS + b];
+          HW[0] -= sg * SL[4 * NDS + b]; HW[1] -= sg * SL[5 * NDS + b]; HW[2] += SL[(second ? 7 : 6) * NDS + b];
+          qv[E_CNV + l] = SL[(second ? 10 : 8) * NDS + b]; qv[E_CNV + 4 + l] = SL[(second ? 11 : 9) * NDS + b];
           if (contact) {
             // dS/dalpha = -(dual part of dE/dalpha): a1next:+e1, a1prev:-e2, a2next:+e2, a2prev:-e1
-            const double e1d = SL[12 * NBONDS + b], e2d = SL[13 * NBONDS + b];
+            const double e1d = SL[12 * NDS + b], e2d = SL[13 * NDS + b];
             An[l] = second ? -e2d : -e1d;
             Ap[l] = second ? e1d : e2d;
           }
@@ -495,29 +530,52 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
         if (any_contact) {
           // contact chain of the centroid_node_vectors cotangent: edge l -> l+1 is node l's "next" edge and,
           // reversed, node (l+1)'s "previous" edge; both angles have the same derivative w.r.t. the end points
-#pragma unroll 1
-          for (int l = 0; l < npb; ++l) {
-            const int ln = (l + 1 == npb) ? 0 : l + 1;
-            const int n = blk * npb + l, m = blk * npb + ln;
-            const double ex = g_cnv[2 * m] - g_cnv[2 * n], ey = g_cnv[2 * m + 1] - g_cnv[2 * n + 1];
-            const double inv = 1.0 / (ex * ex + ey * ey);
-            const double wx = -(An[l] + Ap[ln]) * ey * inv, wy = (An[l] + Ap[ln]) * ex * inv;
 #pragma unroll
-            for (int k = 0; k < 4; ++k) {
-              if (k == ln) { qv[E_CNV + k] += wx; qv[E_CNV + 4 + k] += wy; }
-              if (k == l) { qv[E_CNV + k] -= wx; qv[E_CNV + 4 + k] -= wy; }
+          for (int l = 0; l < 4; ++l) {
+            if (l < npb) {
+              const bool last = l + 1 == npb;
+              const int ln = last ? 0 : l + 1;
+              const int n = blk * npb + l, m = blk * npb + ln;
+              const double ex = g_cnv[2 * m] - g_cnv[2 * n], ey = g_cnv[2 * m + 1] - g_cnv[2 * n + 1];
+              const double inv = 1.0 / (ex * ex + ey * ey);
+              const double ap_n = last ? Ap[0] : Ap[l + 1 < 4 ? l + 1 : 0];
+              const double wx = -(An[l] + ap_n) * ey * inv, wy = (An[l] + ap_n) * ex * inv;
+#pragma unroll
+              for (int k = 0; k < 4; ++k) {
+                if (k == ln) { qv[E_CNV + k] += wx; qv[E_CNV + 4 + k] += wy; }
+                if (k == l) { qv[E_CNV + k] -= wx; qv[E_CNV + 4 + k] -= wy; }
+              }
             }
           }
         }
       }
-      probe = quad_apply(qv);
-      SCAL(SC_T0, p_t0);
-      if (has_damp && !damp_pd) SCAL(SC_DAMP, p_damp);
-      if (ndp > 0) SCAL(SC_DRIVE, p_dr0);
-      if (ndp > 1) SCAL(SC_DRIVE + 1, p_dr1);
-      if (ndp > 2) SCAL(SC_DRIVE + 2, p_dr2);
-      if (ndp > 3) SCAL(SC_DRIVE + 3, p_dr3);
-      if (ndp > 4) SCAL(SC_DRIVE + 4, p_dr4);
+      if (ac.on) {
+        // unit-owned entries in two groups: all loads of a group are in flight before the first dependent use
+#pragma unroll
+        for (int c0 = 0; c0 < E_REF; c0 += 7) {
+          double s_in[7], e_in[7];
+#pragma unroll
+          for (int k = 0; k < 7; ++k) { s_in[k] = Q(ac.a_s, c0 + k); e_in[k] = Q(ac.a_e, c0 + k); }
+#pragma unroll
+          for (int k = 0; k < 7; ++k) {
+            Q(QA_SOL, c0 + k) = fma(qc.cs, qv[c0 + k], ac.fs * s_in[k]);
+            Q(QA_ERR, c0 + k) = fma(qc.ce, qv[c0 + k], ac.fe * e_in[k]);
+          }
+        }
+        if (qc.crossing) {  // midpoint sums: one step in ~25, not prefetched
+#pragma unroll
+          for (int k = 0; k < NE; ++k) if (k < ne_used) Q(ac.a_k7, k) = fma(qc.cm, qv[k], ac.fm * Q(ac.a_m, k));
+        }
+      } else {
+        probe = quad_apply(qv);
+      }
+      // t0_bar and the drive parameters only receive contributions from constrained or loaded DOFs
+      if (warp_t0) {
+        SCAL3(SC_T0, 1, p_t0, 0.0, 0.0);
+        if (ndp > 0) SCAL3(SC_DRIVE, ndp < 3 ? ndp : 3, p_dr0, p_dr1, p_dr2);
+        if (ndp > 3) SCAL3(SC_DRIVE + 3, ndp - 3, p_dr3, p_dr4, 0.0);
+      }
+      if (has_damp && !damp_pd) SCAL3(SC_DAMP, 1, p_damp, 0.0, 0.0);
     }
     tp.fence_st();
     return probe;
@@ -548,8 +606,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     if (has_blk) {
       double sn, cs;
       sincos(u[2], &sn, &cs);
-      Us[blk] = u[0]; Us[NB + blk] = u[1]; Us[2 * NB + blk] = u[2]; Us[3 * NB + blk] = sn; Us[4 * NB + blk] = cs;
-      Ws[blk] = w[0]; Ws[NB + blk] = w[1]; Ws[2 * NB + blk] = w[2];
+      Us[blk] = u[0]; Us[NBS + blk] = u[1]; Us[2 * NBS + blk] = u[2]; Us[3 * NBS + blk] = sn; Us[4 * NBS + blk] = cs;
+      Ws[blk] = w[0]; Ws[NBS + blk] = w[1]; Ws[2 * NBS + blk] = w[2];
     }
     tp.fence_st();
   };

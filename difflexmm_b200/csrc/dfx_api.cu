@@ -148,12 +148,20 @@ FastPlan plan_fast_adjoint(const DevTopo& T) {
   f.cols_per_warp = (512 / groups) & ~1;
   f.nt = f.cols_per_warp >= 168 ? 84 : (f.cols_per_warp >= 128 ? 64 : 0);
   if (mode && !strcmp(mode, "notmem")) f.nt = 0;
-  const size_t fixed = (size_t)(40 + 8LL * T.n_blocks + 14LL * T.n_bonds + (2 * NSCAL + 5 * NSCAL * SCW) + 32) * 8 +
-                       (size_t)((T.n_nodes + 1) & ~1) * 4;
   const size_t cap = kSmemBytes - 1024;
+  auto fixed_bytes = [&](long long nbs, long long nds) {
+    return (size_t)(40 + 8 * nbs + 14 * nds + (2 * NSCAL + 5 * NSCAL * SCW) + 32) * 8 + (size_t)((T.n_nodes + 1) & ~1) * 4;
+  };
+  size_t fixed = fixed_bytes(T.n_blocks, T.n_bonds);
   if (fixed + 8 * (size_t)t > cap) return f;
   int ns = (int)((cap - fixed) / (8 * (size_t)t));
   if (ns > S_NCONST - f.nt) ns = S_NCONST - f.nt;
+  if (f.nt == 84 && t == 384) {
+    // specialised variant: all constants in shared memory (32 slots) and compile-time array strides (T, 2T)
+    const size_t fixed_s = fixed_bytes(t, 2 * t);
+    if (fixed_s + 32 * 8 * (size_t)t <= cap) { fixed = fixed_s; ns = 32; }
+    else if (ns == 32) ns = 31;  // cannot use the specialised variant: keep the run-time one
+  }
   f.ns = ns;
   f.smem = fixed + (size_t)ns * t * 8;
   const int n_over = S_NCONST - f.nt - ns > 0 ? S_NCONST - f.nt - ns : 0;  // constants that spill to global
@@ -507,4 +515,23 @@ extern "C" double dfx_fp64_peak(void* stream_) {
   cudaEventDestroy(e1);
   cudaFree(out);
   return best;
+}
+
+// ---- self-test of the device math primitives (tests/test_gpu_parity.py::test_device_math) ------------
+namespace {
+__global__ void math_selftest_kernel(const double* x, const double* y, double* o_rsqrt, double* o_angle, double* o_rcp, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= n) return;
+  o_rsqrt[i] = rsqrt_pos(x[i]);
+  o_rcp[i] = rcp_pos(x[i]);
+  const double r = rsqrt_pos(x[i] * x[i] + y[i] * y[i]);
+  o_angle[i] = angle_of_unit(y[i] * r, x[i] * r);
+}
+}  // namespace
+
+extern "C" int dfx_math_selftest(const double* x, const double* y, double* o_rsqrt, double* o_angle, double* o_rcp, int n, void* stream_) {
+  math_selftest_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(x, y, o_rsqrt, o_angle, o_rcp, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "math_selftest launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
 }

@@ -101,6 +101,15 @@ __device__ __forceinline__ double val(Dual a) { return a.v; }
 __device__ __forceinline__ double dot_part(double) { return 0.0; }
 __device__ __forceinline__ double dot_part(Dual a) { return a.d; }
 
+// L = sqrt(L2), 1/L2 from r = 1/sqrt(value of L2)
+__device__ __forceinline__ double len_from(double L2, double r) { return L2 * r; }
+__device__ __forceinline__ Dual len_from(Dual L2, double r) { return Dual(L2.v * r, 0.5 * L2.d * r); }
+__device__ __forceinline__ double inv_from(double, double r) { return r * r; }
+__device__ __forceinline__ Dual inv_from(Dual L2, double r) { const double i = r * r; return Dual(i, -L2.d * i * i); }
+template <class T> __device__ __forceinline__ T make_T(double v, double d);
+template <> __device__ __forceinline__ double make_T<double>(double v, double) { return v; }
+template <> __device__ __forceinline__ Dual make_T<Dual>(double v, double d) { return Dual(v, d); }
+
 // reciprocal and reciprocal square root helpers
 __device__ __forceinline__ double recipT(double a) { return 1.0 / a; }
 __device__ __forceinline__ Dual recipT(Dual a) {
@@ -119,9 +128,9 @@ __device__ __forceinline__ Dual atan2T(Dual y, Dual x, Dual inv_r2) {
 }
 // jnp.mod(a + pi, 2 pi) - pi on the value; derivative 1
 __device__ __forceinline__ double wrap_value(double a) {
-  const double two_pi = 2.0 * kPi;
+  const double two_pi = 2.0 * kPi, inv_two_pi = 1.0 / two_pi;
   double m = a + kPi;
-  m = m - two_pi * floor(m / two_pi);
+  m = fma(-two_pi, floor(m * inv_two_pi), m);
   return m - kPi;
 }
 __device__ __forceinline__ double wrapT(double a) { return wrap_value(a); }
@@ -131,13 +140,62 @@ __device__ __forceinline__ Dual wrapT(Dual a) { return Dual(wrap_value(a.v), a.d
 // per-bond gradient
 // ------------------------------------------------------------------------------------------
 template <class T>
-struct BlockState {  // one rigid unit at the current stage: displacement, rotation, sin/cos
+struct BlockState {  // one rigid unit at the current stage: displacement, rotation, sin/cos(theta)
   T x, y, th, s, c;
 };
+__device__ __forceinline__ void make_block(double x, double y, double th, double sv, double cv, BlockState<double>& b) {
+  b.x = x; b.y = y; b.th = th; b.s = sv; b.c = cv;
+}
 
-struct BondConst {  // per design and bond, precomputed once per launch
-  double r0x, r0y, L0, phi0;
+__device__ __forceinline__ void make_block(double x, double y, double th, double sv, double cv, double wx, double wy, double wth,
+                                           BlockState<Dual>& b) {
+  b.x = Dual(x, wx); b.y = Dual(y, wy); b.th = Dual(th, wth);
+  b.s = Dual(sv, cv * wth); b.c = Dual(cv, -sv * wth);
+}
+
+struct BondConst {  // per design and bond, precomputed once per launch: reference vector, its length and 1/length
+  double r0x, r0y, L0, iL0;
 };
+
+// atan(t) for |t| <= tan(pi/8): t * P(t^2), interpolated at Chebyshev nodes, max error 6e-17
+__device__ __forceinline__ double atan_small(double t) {
+  const double u = t * t;
+  double p = -0.01750805688110568;
+  p = fma(p, u, 0.03769427981208796);
+  p = fma(p, u, -0.0502446052811003);
+  p = fma(p, u, 0.05844521903264865);
+  p = fma(p, u, -0.06662628649373917);
+  p = fma(p, u, 0.07692016940630392);
+  p = fma(p, u, -0.0909089521235964);
+  p = fma(p, u, 0.11111110689133682);
+  p = fma(p, u, -0.14285714278117734);
+  p = fma(p, u, 0.19999999999929152);
+  p = fma(p, u, -0.33333333333333076);
+  p = fma(p, u, 1.0);
+  return t * p;
+}
+// angle in (-pi, pi] of the unit vector (cg, sg); the usual case |angle| <= pi/4 is branch free
+__device__ __forceinline__ double angle_of_unit(double sg, double cg) {
+  if (cg >= 0.70710678118654757) {
+    const double d = 1.0 + cg;
+    double r;
+    asm("rcp.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(d));
+    r = fma(fma(-d, r, 1.0), r, r);
+    r = fma(fma(-d, r, 1.0), r, r);
+    return 2.0 * atan_small(sg * r);  // tan(angle/2) = sin/(1+cos)
+  }
+  return atan2(sg, cg);
+}
+// 1/sqrt(x) for positive normal x: hardware approximation + two Newton steps
+__device__ __forceinline__ double rsqrt_pos(double x) {
+  double r;
+  asm("rsqrt.approx.ftz.f64 %0, %1;" : "=d"(r) : "d"(x));
+  double e = fma(-x * r, r, 1.0);
+  r = fma(fma(0.375, e, 0.5) * e, r, r);
+  e = fma(-x * r, r, 1.0);
+  r = fma(0.5 * e, r, r);
+  return r;
+}
 
 template <class T>
 struct BondOut {
@@ -189,9 +247,19 @@ __device__ __forceinline__ void bond_gradient(int energy_kind, const BlockState<
   if (energy_kind == DFX_BOND_LIGAMENT) {
     T dx = dUx + bc.r0x, dy = dUy + bc.r0y;
     T L2 = dx * dx + dy * dy;
-    T iL2 = recipT(L2);
-    T L = sqrtT(L2);
-    T gam = wrapT(atan2T(dy, dx, iL2) - bc.phi0 - mean);
+    const double rinv = rsqrt_pos(val(L2));
+    T iL2 = inv_from(L2, rinv);
+    T L = len_from(L2, rinv);
+    // shear angle (reference energy.py:139-153): wrap(atan2(current) - atan2(R(mean) r0)) = wrap((phi - phi0) - mean).
+    // phi - phi0 is the angle of the unit bond direction rotated by the constant -phi0 of the bond: no atan2
+    // range reduction in the usual case, and the mean rotation enters as a plain number exactly as in the reference.
+    double gv;
+    {
+      const double cp = bc.r0x * bc.iL0, sp = bc.r0y * bc.iL0;
+      const double ex = val(dx) * rinv, ey = val(dy) * rinv;
+      gv = wrap_value(angle_of_unit(cp * ey - sp * ex, cp * ex + sp * ey) - val(mean));
+    }
+    T gam = make_T<T>(gv, (val(dx) * dot_part(dy) - val(dy) * dot_part(dx)) * val(iL2) - dot_part(mean));
     T ext = L - L0;
     T A = ext * ks * L * iL2;  // ks (L-L0)/L
     T M = gam * (ksh * L0sq);  // dE/dgamma

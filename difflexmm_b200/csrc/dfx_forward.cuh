@@ -78,7 +78,7 @@ __device__ inline void setup_design_constants(const DevTopo& T, const DfxParams&
     bondc[b] = rx;
     bondc[T.n_bonds + b] = ry;
     bondc[2 * T.n_bonds + b] = sqrt(rx * rx + ry * ry);
-    bondc[3 * T.n_bonds + b] = atan2(ry, rx);
+    bondc[3 * T.n_bonds + b] = 1.0 / bondc[2 * T.n_bonds + b];
   }
   for (int n = threadIdx.x; n < NN; n += blockDim.x) {
     const double rx = g_cnv[2 * n], ry = g_cnv[2 * n + 1];
@@ -150,8 +150,8 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
     for (int b = tid; b < NBONDS; b += nthr) {
       const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
       BlockState<double> s1, s2;
-      s1.x = Us[bl.x]; s1.y = Us[NB + bl.x]; s1.th = Us[2 * NB + bl.x]; s1.s = Us[3 * NB + bl.x]; s1.c = Us[4 * NB + bl.x];
-      s2.x = Us[bl.y]; s2.y = Us[NB + bl.y]; s2.th = Us[2 * NB + bl.y]; s2.s = Us[3 * NB + bl.y]; s2.c = Us[4 * NB + bl.y];
+      make_block(Us[bl.x], Us[NB + bl.x], Us[2 * NB + bl.x], Us[3 * NB + bl.x], Us[4 * NB + bl.x], s1);
+      make_block(Us[bl.y], Us[NB + bl.y], Us[2 * NB + bl.y], Us[3 * NB + bl.y], Us[4 * NB + bl.y], s2);
       BondConst bc = {bondc[b], bondc[NBONDS + b], bondc[2 * NBONDS + b], bondc[3 * NBONDS + b]};
       const double ks = g_ks[a.p.k_per_bond[0] ? b : 0], ksh = g_ksh[a.p.k_per_bond[1] ? b : 0], kr = g_kr[a.p.k_per_bond[2] ? b : 0];
       BondOut<double> o;

@@ -183,6 +183,9 @@ int dfx_expand_fields(const DfxTopology* topo, const DfxParams* params, int batc
 /* measurement helper: FP64 FMA throughput of the current device in TFLOP/s (roofline denominator) */
 double dfx_fp64_peak(void* stream);
 
+/* test helper: evaluates the device math primitives (1/sqrt(x), angle of the unit vector along (x,y), 1/x) */
+int dfx_math_selftest(const double* x, const double* y, double* out_rsqrt, double* out_angle, double* out_rcp, int n, void* stream);
+
 const char* dfx_last_error(void);
 const char* dfx_version(void);
 

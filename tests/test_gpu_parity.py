@@ -172,3 +172,29 @@ def test_full_size_config_matches_cpp_oracle(problem):
     if problem == "quads_focusing":  # the well-conditioned configuration meets the north-star tolerances outright
         assert traj_floor < TRAJ_TOL
         assert rel_l2(tsb_d[0].cpu().numpy(), tsb_h[0]) <= GRAD_TOL
+
+
+def test_device_math():
+    """the hand-rolled device primitives of the bond kernel (reciprocal square root, reciprocal, polynomial
+    angle-of-unit-vector) against numpy, to a few ulp"""
+    import ctypes as C
+    from difflexmm_b200 import _lib
+    rng = np.random.default_rng(0)
+    n = 1 << 16
+    x = np.concatenate([rng.uniform(1e-3, 1e3, n // 2), 10.0 ** rng.uniform(-12, 12, n // 2)])
+    ang = rng.uniform(-np.pi, np.pi, n)
+    rad = 10.0 ** rng.uniform(-3, 3, n)
+    vx, vy = rad * np.cos(ang), rad * np.sin(ang)
+    d = lambda a: torch.as_tensor(a, device="cuda")
+    xs, ys_ = d(x), d(vy)
+    xa = d(vx)
+    o1, o2, o3 = torch.empty_like(xs), torch.empty_like(xs), torch.empty_like(xs)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert _lib.lib.dfx_math_selftest(C.c_void_p(xs.data_ptr()), C.c_void_p(ys_.data_ptr()), C.c_void_p(o1.data_ptr()),
+                                      C.c_void_p(o2.data_ptr()), C.c_void_p(o3.data_ptr()), n, stream) == 0
+    assert np.max(np.abs(o1.cpu().numpy() * np.sqrt(x) - 1)) < 1e-15
+    assert np.max(np.abs(o3.cpu().numpy() * x - 1)) < 1e-15
+    o4 = torch.empty_like(xs)
+    assert _lib.lib.dfx_math_selftest(C.c_void_p(xa.data_ptr()), C.c_void_p(ys_.data_ptr()), C.c_void_p(o1.data_ptr()),
+                                      C.c_void_p(o4.data_ptr()), C.c_void_p(o3.data_ptr()), n, stream) == 0
+    assert np.max(np.abs(o4.cpu().numpy() - np.arctan2(vy, vx))) < 2e-15

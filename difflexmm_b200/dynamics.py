@@ -260,7 +260,8 @@ class DynamicSolver:
     def expand_fields(self, ys, ts, control_params):
         """(B, n_t, 2, n_blocks, 3) from the free-DOF solution (reference `dynamics.py:129-136,
         169-182`, without the dense Jacobian): free DOFs are copied; constrained DOFs follow the
-        drive signal and its time derivative.  Differentiable torch (cheap, outside the time loop)."""
+        drive signal (displacement) and its time derivative (velocity).  Differentiable torch: it is
+        cheap post-processing outside the time loop (libdfx offers the same as `dfx_expand_fields`)."""
         spec, dev = self.spec, self.device
         B, n_t = ys.shape[0], ys.shape[1]
         nf, nd = spec.n_free, spec.n_blocks * 3
@@ -269,37 +270,40 @@ class DynamicSolver:
         out = out.index_copy(3, free, ys.reshape(B, n_t, 2, nf))
         if len(spec.constrained_dofs) and spec.n_drive_params:
             cons = torch.as_tensor(spec.constrained_dofs.astype(np.int64), device=dev)
-            params = {n: _as_t(control_params.constraint_params[n], dev) for n in self.drive.param_names}
-            params = {n: (p.reshape(-1, 1) if p.dim() == 1 else p) for n, p in params.items()}
-            with torch.enable_grad():
-                tt = ts.detach().clone().requires_grad_(True)
-                tb = tt if tt.dim() == 2 else tt[None].expand(B, n_t)
-                u_c = self.drive(tb, **params)  # (B, n_t, n_c)
-                (du_dt,) = torch.autograd.grad(u_c.sum(), tt, create_graph=u_c.requires_grad)
-            du_dt_b = du_dt if du_dt.dim() == 2 else du_dt[None].expand(B, n_t)
-            s0, s1 = self.drive.channels(tb, **params)
-            # velocity = d u_c / dt per channel (autograd above gives only the vec-weighted sum)
-            v_c = self._drive_rate(tb, params)
+            u_c, v_c = drive_values(self.drive, ts if ts.dim() == 2 else ts[None].expand(B, n_t),
+                                    control_params.constraint_params, dev)
             out = out.index_copy(3, cons, torch.stack([u_c.expand(B, n_t, -1), v_c.expand(B, n_t, -1)], dim=2))
         return out.reshape(B, n_t, 2, spec.n_blocks, 3)
 
-    def _drive_rate(self, tb, params):
-        """time derivative of the drive of every constrained DOF, (B, n_t, n_c)."""
-        with torch.enable_grad():
-            t = tb.detach().clone().requires_grad_(True)
-            s0, s1 = self.drive.channels(t, **params)
-            need_graph = any(isinstance(p, torch.Tensor) and p.requires_grad for p in params.values())
-            d0 = torch.autograd.grad(s0.sum(), t, create_graph=need_graph, allow_unused=True)[0]
-            d1 = torch.autograd.grad(s1.sum(), t, create_graph=need_graph, allow_unused=True)[0]
-        out = 0.
-        dev = tb.device
-        if self.drive.vec0 is not None and d0 is not None:
-            out = out + d0[..., None] * torch.as_tensor(self.drive.vec0, device=dev)
-        if self.drive.vec1 is not None and d1 is not None:
-            out = out + d1[..., None] * torch.as_tensor(self.drive.vec1, device=dev)
-        if not isinstance(out, torch.Tensor):
-            out = torch.zeros((*tb.shape, len(self.spec.constrained_dofs)), dtype=_F64, device=dev)
-        return out
+
+def drive_values(drive: DriveSignal, tb, constraint_params, device):
+    """displacement and velocity of every constrained DOF at times `tb` (B, n_t): (u_c, du_c/dt), each
+    (B, n_t, n_constrained).  The time derivative is taken per channel with autograd on the `where`-selected
+    branch, which is what `jacobian(kinematics, argnums=1)` yields in the reference (`dynamics.py:130-134`)."""
+    params = {n: _as_t(constraint_params[n], device) for n in drive.param_names}
+    params = {n: (p.reshape(-1, 1) if p.dim() == 1 else p) for n, p in params.items()}
+    need_graph = any(p.requires_grad for p in params.values())
+    with torch.enable_grad():
+        t = tb.detach().clone().requires_grad_(True)
+        s0, s1 = drive.channels(t, **params)
+        rates = []
+        for sk in (s0, s1):
+            if sk.requires_grad:
+                rates.append(torch.autograd.grad(sk.sum(), t, create_graph=need_graph, allow_unused=True)[0])
+            else:
+                rates.append(None)
+    s0, s1 = drive.channels(tb, **params)
+    n_c = len(drive.vec0) if drive.vec0 is not None else len(drive.vec1)
+    u = torch.zeros((*tb.shape, n_c), dtype=_F64, device=device)
+    v = torch.zeros((*tb.shape, n_c), dtype=_F64, device=device)
+    for vec, sk, rk in ((drive.vec0, s0, rates[0]), (drive.vec1, s1, rates[1])):
+        if vec is None:
+            continue
+        vt = torch.as_tensor(vec, device=device)
+        u = u + sk[..., None] * vt
+        if rk is not None:
+            v = v + rk[..., None] * vt
+    return u, v
 
 
 def setup_dynamic_solver(

@@ -1,0 +1,56 @@
+"""The C-ABI library loads on a CPU-only box and exports every entry point that include/dfx.h declares
+(no compute calls here: those need a GPU)."""
+
+import ctypes as C
+import os
+import re
+
+import pytest
+
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+
+
+def _declared_functions():
+    src = open(os.path.join(ROOT, "include", "dfx.h")).read()
+    src = re.sub(r"/\*.*?\*/", "", src, flags=re.S)
+    return sorted(set(re.findall(r"\b(dfx_[a-z0-9_]+)\s*\(", src)))
+
+
+def test_header_declares_the_boundary():
+    names = _declared_functions()
+    for required in ("dfx_topology_create", "dfx_topology_destroy", "dfx_forward", "dfx_adjoint", "dfx_expand_fields",
+                     "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_last_error"):
+        assert required in names
+
+
+def test_library_exports_every_declared_symbol():
+    from difflexmm_b200 import _lib  # raises if libdfx.so is missing: there is no fallback
+    for name in _declared_functions():
+        assert hasattr(_lib.lib, name), f"libdfx.so does not export {name}"
+    assert b"sm_100a" in _lib.lib.dfx_version()
+    assert [_lib.lib.dfx_drive_n_params(k) for k in range(5)] == [0, 3, 3, 2, 5]
+
+
+def test_ctypes_struct_layout_matches_header_sizes():
+    from difflexmm_b200 import _abi
+    assert C.sizeof(_abi.DfxStats) == 40
+    assert C.sizeof(_abi.DfxLeaf) == 16
+    assert C.sizeof(_abi.DfxOptions) == 16
+    assert C.sizeof(_abi.DfxParamGrads) == 9 * 8
+    # DfxParams: 5 leaves, int[3] (+pad), leaf, int (+pad), 3 leaves
+    assert C.sizeof(_abi.DfxParams) == 5 * 16 + 16 + 16 + 8 + 3 * 16
+
+
+def test_topology_create_reports_errors_instead_of_crashing():
+    import numpy as np
+    import torch
+    from difflexmm_b200 import _abi, _lib
+    spec = _abi.TopologySpec(2, 4, [[0, 6]], [])
+    if not torch.cuda.is_available():
+        with pytest.raises(RuntimeError, match="dfx_topology_create failed"):
+            _lib.Topology(spec, 0)
+    # a vertex shared by two bonds is rejected by the slot-based assembly, with a message
+    desc = _abi.TopologySpec(2, 4, [[0, 6], [0, 7]], []).to_desc()
+    h = C.c_void_p()
+    rc = _lib.lib.dfx_topology_create(C.byref(desc), 0, C.byref(h))
+    assert rc != 0 and b"more than one bond" in _lib.lib.dfx_last_error()

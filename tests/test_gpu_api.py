@@ -1,0 +1,93 @@
+"""The reference-facing API on the GPU: setup_dynamic_solver / solve_dynamics / ControlParams, differentiation through
+the solver with torch.autograd (the analogue of jax.grad through odeint), batches of designs."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from cases import rel_l2
+
+pytestmark = pytest.mark.gpu
+
+
+def _problem(**kw):
+    from difflexmm_b200.problems import QuadsFocusing
+    args = dict(n1_blocks=8, n2_blocks=7, simulation_time=0.012, n_timepoints=9, target_shift=(1, 1))
+    args.update(kw)
+    return QuadsFocusing(**args)
+
+
+def test_setup_dynamic_solver_matches_oracle_fields():
+    """same call sequence as the reference's ForwardProblem.setup / forward (problems/quads_focusing.py:239-310)"""
+    from difflexmm_b200.dynamics import setup_dynamic_solver
+    from difflexmm_b200.energy import build_contact_energy, build_strain_energy, combine_block_energies, ligament_energy
+    from difflexmm_b200.geometry import QuadGeometry
+    from oracle import Oracle
+    P = _problem()
+    spec, drive = P.lower()
+    geo = QuadGeometry(P.n1_blocks, P.n2_blocks, spacing=P.spacing, bond_length=P.bond_length)
+    block_centroids, centroid_node_vectors, bond_connectivity, reference_bond_vectors = geo.get_parametrization()
+    bonds = bond_connectivity()
+    energy = combine_block_energies(build_strain_energy(bonds, ligament_energy), build_contact_energy(bonds))
+    solve_dynamics = setup_dynamic_solver(geo, energy, constrained_block_DOF_pairs=P.constrained_block_DOF_pairs,
+                                          constrained_DOFs_fn=drive, damped_blocks=np.arange(geo.n_blocks),
+                                          rtol=P.rtol, atol=P.atol)
+    design = P.initial_design()
+    cp = P.control_params(design, "cuda")
+    fields = solve_dynamics(torch.zeros(2, geo.n_blocks, 3, dtype=torch.float64), P.timepoints(), cp)
+    assert fields.shape == (P.n_timepoints, 2, geo.n_blocks, 3)
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(design)
+    orc = Oracle(spec)
+    ps = orc.params(1, {k: v.numpy() for k, v in leaves.items()}, pb, dpd)
+    ys, _ = orc.forward(ps, y0.numpy(), ts.numpy(), P.rtol, P.atol)
+    ref = orc.expand_fields(ps, ys, ts.numpy())[0]
+    assert rel_l2(fields.cpu().numpy(), ref) <= 1e-6
+
+
+def test_design_gradient_through_the_solver_matches_finite_differences():
+    """value_and_grad(target kinetic energy)(design) -- the hot call of the reference's optimisation loop
+    (problems/quads_focusing.py:565-569) -- against central differences of the forward solve"""
+    P = _problem(rtol=1e-10, atol=1e-10)
+    P.setup()
+    hs, vs = P.initial_design()
+    hs = hs.clone().requires_grad_(True)
+    vs = vs.clone().requires_grad_(True)
+    J = P.target_kinetic_energy((hs, vs))
+    J.backward()
+    assert torch.isfinite(hs.grad).all() and torch.isfinite(vs.grad).all()
+    rng = np.random.default_rng(0)
+    d_hs, d_vs = torch.from_numpy(rng.standard_normal(hs.shape)), torch.from_numpy(rng.standard_normal(vs.shape))
+    eps = 1e-5
+    with torch.no_grad():
+        Jp = P.target_kinetic_energy((hs + eps * d_hs, vs + eps * d_vs))
+        Jm = P.target_kinetic_energy((hs - eps * d_hs, vs - eps * d_vs))
+    fd = ((Jp - Jm) / (2 * eps)).item()
+    an = ((hs.grad * d_hs).sum() + (vs.grad * d_vs).sum()).item()
+    assert abs(fd - an) <= 1e-5 * max(abs(fd), abs(an))
+
+
+def test_batch_of_designs_equals_one_by_one():
+    P = _problem()
+    P.setup()
+    hs, vs = P.random_ensemble(4, noise=0.05)
+    Jb = P.target_kinetic_energy((hs, vs), batch=4)
+    J1 = torch.stack([P.target_kinetic_energy((hs[i], vs[i])) for i in range(4)])
+    assert torch.allclose(Jb, J1, rtol=1e-12)
+    st = P.solver.last_forward_stats.numpy()
+    assert (st["status"] == 0).all() and (st["steps"] > 0).all()
+
+
+def test_expand_fields_kernel_matches_torch_postprocessing():
+    from difflexmm_b200 import _abi
+    P = _problem()
+    s = P.setup()
+    design = P.initial_design()
+    cp = P.control_params(design, "cuda")
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(design, device="cuda")
+    ps = _abi.ParamSet(P.spec, 1, {k: v.contiguous() for k, v in leaves.items()}, pb, dpd)
+    ys, _ = s.lib_forward(ps, y0, ts)
+    a = s._lib.expand_fields(s.handle, ps, ys, ts)
+    b = s.expand_fields(ys, ts, cp)
+    assert torch.allclose(a, b, rtol=1e-13, atol=1e-13)

@@ -1,0 +1,148 @@
+"""Host-side mirror of the reference interface: geometry, DOF bookkeeping, lowering of
+setup_dynamic_solver's arguments and of ControlParams (no GPU needed)."""
+
+import math
+
+import numpy as np
+import pytest
+import torch
+
+from difflexmm_b200 import _abi
+from difflexmm_b200.dynamics import lower_params, lower_topology
+from difflexmm_b200.energy import (build_contact_energy, build_strain_energy, combine_block_energies, ligament_energy,
+                                   ligament_energy_linearized)
+from difflexmm_b200.geometry import (DOFsInfo, KagomeGeometry, QuadGeometry, RotatedSquareGeometry, compute_inertia,
+                                     polygon_area, polygon_centroid, polygon_polar_moment)
+from difflexmm_b200.loading import pulse_drive, ramp_load
+from difflexmm_b200.problems import KagomeFocusing, QuadsFocusing, QuadsStaticTuning
+
+
+def test_polygon_properties_of_a_rectangle():
+    v = torch.tensor([[[0., 0.], [2., 0.], [2., 1.], [0., 1.]]], dtype=torch.float64)
+    assert torch.allclose(polygon_area(v), torch.tensor([2.], dtype=torch.float64))
+    assert torch.allclose(polygon_centroid(v), torch.tensor([[1., 0.5]], dtype=torch.float64))
+    # polar moment of a b x h rectangle about its centroid: b h (b^2 + h^2) / 12
+    assert torch.allclose(polygon_polar_moment(v), torch.tensor([2 * (4 + 1) / 12.], dtype=torch.float64))
+    I = compute_inertia(v, 3.0)
+    assert torch.allclose(I, torch.tensor([[6., 6., 2.5]], dtype=torch.float64))
+
+
+def test_dofs_info_order():
+    free, cons, all_ids = DOFsInfo(3, np.array([[2, 1], [0, 0]]))
+    assert cons.tolist() == [7, 0]                       # pair order (reference geometry.py:174)
+    assert free.tolist() == [1, 2, 3, 4, 5, 6, 8]        # ascending
+    assert all_ids.tolist() == list(range(9))
+    free, cons, _ = DOFsInfo(2, np.array([]))
+    assert len(cons) == 0 and free.tolist() == list(range(6))
+
+
+def test_quad_geometry_counts_and_rotated_square_design():
+    g = QuadGeometry(24, 16, spacing=15., bond_length=2.25)
+    bc, cnv, bonds, ref = g.get_parametrization()
+    assert g.n_blocks == 384 and bonds().shape == (728, 2) and ref().shape == (728, 2)
+    hs, vs = g.get_design_from_rotated_square(25 * math.pi / 180)
+    assert hs.shape == (25, 16, 2) and vs.shape == (24, 17, 2)
+    c = cnv(hs, vs)
+    assert c.shape == (384, 4, 2)
+    # centroid_node_vectors are measured from the centroid
+    assert torch.allclose(polygon_centroid(c), torch.zeros(384, 2, dtype=torch.float64), atol=1e-12)
+    # every node belongs to at most one bond
+    assert len(np.unique(bonds())) == bonds().size
+    # the quad design "from rotated square(angle)" is the rotated-square lattice of the opposite angle: node 0 of
+    # block (n1, n2) takes horizontal_shift[n1 + 1, n2], whose parity is flipped (reference geometry.py:866-873, 936-941)
+    rs = RotatedSquareGeometry(12, 8, spacing=15., bond_length=2.25)
+    rs.compute_geometry()
+    c_rs = rs.centroid_node_vectors(-25 * math.pi / 180)
+    assert torch.allclose(c_rs, c, atol=1e-12)
+
+
+def test_kagome_geometry_counts():
+    g = KagomeGeometry(20, 12, 20. * np.array([[1., 0.], [math.cos(math.pi / 3), math.sin(math.pi / 3)]]), 2.25)
+    bc, cnv, bonds, ref = g.get_parametrization()
+    assert g.n_blocks == 480 and g.n_npb == 3
+    assert bonds().shape == (240 + 220 + 228, 2)
+    assert len(np.unique(bonds())) == bonds().size
+    c = cnv()
+    assert c.shape == (480, 3, 2)
+    assert torch.allclose(polygon_centroid(c), torch.zeros(480, 2, dtype=torch.float64), atol=1e-12)
+    # bond reference vectors close the gap between the two bonded nodes of the regular lattice
+    nodes = (c + bc()[:, None, :]).reshape(-1, 2)
+    b = bonds()
+    assert torch.allclose(nodes[b[:, 1]] - nodes[b[:, 0]], ref(), atol=1e-12)
+
+
+@pytest.mark.parametrize("P,sizes", [
+    (QuadsFocusing, dict(n_blocks=384, n_bonds=728, n_cons=42, n_free=1110, aug=12009)),
+    (KagomeFocusing, dict(n_blocks=480, n_bonds=688, n_cons=48, n_free=1392, aug=None)),
+    (QuadsStaticTuning, dict(n_blocks=432, n_bonds=822, n_cons=150, n_free=1146, aug=None)),
+])
+def test_reference_configurations_lower_to_the_survey_sizes(P, sizes):
+    p = P()
+    spec, drive = p.lower()
+    assert spec.n_blocks == sizes["n_blocks"] and spec.n_bonds == sizes["n_bonds"]
+    assert len(spec.constrained_dofs) == sizes["n_cons"] and spec.n_free == sizes["n_free"]
+    leaves, pb, dpd, aug, y0, ts = p.boundary_inputs(p.initial_design())
+    assert leaves["inertia"].shape == (spec.n_free,) and dpd and pb == ()
+    assert leaves["drive"].shape == (spec.n_drive_params,)
+    if sizes["aug"]:
+        assert aug == sizes["aug"]
+    # what libdfx counts by itself when aug_size = 0 lacks block_centroids and density
+    ps = _abi.ParamSet(spec, 1, {k: v.numpy() for k, v in leaves.items()}, pb, dpd)
+    assert aug == ps.aug_size_of_listed_leaves() + 2 * spec.n_blocks + 1
+
+
+def test_batched_lowering_keeps_per_design_counts():
+    p = QuadsFocusing(n1_blocks=8, n2_blocks=7)
+    spec, drive = p.lower()
+    hs, vs = p.random_ensemble(3, noise=0.05)
+    l1, _, _, aug1, _, _ = p.boundary_inputs((hs[0], vs[0]))
+    lb, pb, dpd, augb, _, _ = p.boundary_inputs((hs, vs), batch=3)
+    assert augb == aug1
+    assert lb["centroid_node_vectors"].shape == (3,) + l1["centroid_node_vectors"].shape
+    assert lb["inertia"].shape == (3, spec.n_free)
+    assert torch.allclose(lb["inertia"][0], l1["inertia"])
+    assert lb["damping"].shape == l1["damping"].shape  # shared leaf stays shared
+    ps = _abi.ParamSet(spec, 3, {k: v.numpy() for k, v in lb.items()}, pb, dpd)
+    assert ps.batched["centroid_node_vectors"] and not ps.batched["reference_vector"]
+
+
+def test_gradients_flow_from_the_design_to_the_leaves():
+    p = QuadsFocusing(n1_blocks=8, n2_blocks=7)
+    p.lower()
+    hs, vs = p.initial_design()
+    hs = hs.clone().requires_grad_(True)
+    leaves, *_ = p.boundary_inputs((hs, vs))
+    (leaves["inertia"].sum() + leaves["centroid_node_vectors"].pow(2).sum()).backward()
+    assert hs.grad is not None and torch.isfinite(hs.grad).all() and hs.grad.abs().sum() > 0
+
+
+def test_vocabulary_is_closed_and_loud():
+    g = QuadGeometry(4, 3, spacing=15., bond_length=2.25)
+    g.compute_geometry()
+    bonds = g.bond_connectivity()
+    energy = combine_block_energies(build_strain_energy(bonds, ligament_energy), build_contact_energy(bonds))
+    with pytest.raises(TypeError):
+        lower_topology(g, lambda u, cp: 0.0)                                  # arbitrary Python energy
+    with pytest.raises(TypeError):
+        lower_topology(g, energy, constrained_block_DOF_pairs=[[0, 0]], constrained_DOFs_fn=lambda t: 0.0)
+    with pytest.raises(TypeError):
+        build_strain_energy(bonds, lambda *a, **k: 0.0)
+    with pytest.raises(NotImplementedError):
+        build_contact_energy(bonds, angle_based=False)
+    with pytest.raises(ValueError):
+        lower_topology(g, energy, constrained_block_DOF_pairs=[[0, 0], [0, 0]], constrained_DOFs_fn=pulse_drive([1, 0]))
+    spec, drive = lower_topology(g, build_strain_energy(bonds, ligament_energy_linearized), [[11, 0]], ramp_load(0.2, 1e-3),
+                                 [[0, 0], [0, 1]], pulse_drive([1., 0.]), np.arange(g.n_blocks))
+    assert spec.bond_energy == _abi.DFX_BOND_LINEARIZED and not spec.contact
+    assert spec.load_kind == _abi.DFX_LOAD_RAMP and spec.loaded_dofs.tolist() == [33]
+    assert spec.drive_kind == _abi.DFX_DRIVE_PULSE and spec.n_drive_params == 3
+
+
+def test_solver_refuses_to_run_without_cuda():
+    if torch.cuda.is_available():
+        pytest.skip("CUDA present")
+    from difflexmm_b200.dynamics import setup_dynamic_solver
+    g = QuadGeometry(4, 3, spacing=15., bond_length=2.25)
+    g.compute_geometry()
+    with pytest.raises(RuntimeError):
+        setup_dynamic_solver(g, build_strain_energy(g.bond_connectivity(), ligament_energy), device="cpu")

@@ -1,0 +1,148 @@
+"""CPU tests of the oracle (test infrastructure): it must reproduce
+  * the golden vectors written by the literal torch-autograd restatement of the reference
+    (oracle/ref_literal.py via oracle/make_golden.py),
+  * the reference's own tests for this path (tests/test_difflexmm.py:35-146 tensile known answer,
+    :149-176 frame invariance of the ligament energy),
+  * finite differences (force = -dE/du; adjoint gradient = d objective / d parameter).
+PARITY STATUS: unpinned against a real JAX run (jax is not installable in this image)."""
+
+import math
+
+import numpy as np
+import pytest
+
+from cases import golden_names, load_golden, rel_l2
+from difflexmm_b200 import _abi
+from oracle import Oracle
+
+
+@pytest.mark.parametrize("name", golden_names())
+def test_oracle_matches_literal_golden(name):
+    c = load_golden(name)
+    orc = Oracle(c.spec)
+    ps = orc.params(1, c.leaves, c.per_bond, c.damping_per_dof)
+    ys, st = orc.forward(ps, c.y0, c.ts, c.rtol, c.atol)
+    assert st["status"][0] == 0
+    assert int(st["steps"][0]) == int(c.ref["fwd_steps"]) and int(st["accepted"][0]) == int(c.ref["fwd_accepted"])
+    assert rel_l2(ys[0], c.ref["ys"]) < 1e-9
+    y0b, tsb, gr, sb = orc.adjoint(ps, c.ref["ys"][None], c.ts, c.g[None], c.rtol, c.atol, aug_size=c.aug_size)
+    assert sb["status"][0] == 0
+    assert abs(int(sb["steps"][0]) - int(c.ref["bwd_steps"])) <= 3
+    assert rel_l2(y0b[0], c.ref["y0_bar"]) < 1e-7
+    assert rel_l2(tsb[0], c.ref["ts_bar"]) < 1e-6
+    for k, v in gr.items():
+        key = "grad_" + k
+        if key in c.ref and np.abs(c.ref[key]).max() > 1e-9:
+            assert rel_l2(v[0], c.ref[key]) < 1e-7, k
+
+
+def _rotated_square_chain(n1_cells):
+    from difflexmm_b200.geometry import RotatedSquareGeometry
+    geo = RotatedSquareGeometry(n1_cells=n1_cells, n2_cells=1, spacing=1.0)
+    bc, cnvf, bonds, refv = geo.get_parametrization()
+    return geo, cnvf(0.).numpy(), bonds(), refv().numpy()
+
+
+@pytest.mark.parametrize("n1_cells", [5, 10, 20])
+@pytest.mark.parametrize("bond_energy", [_abi.DFX_BOND_LINEARIZED, _abi.DFX_BOND_LIGAMENT])
+def test_reference_tensile_known_answer(n1_cells, bond_energy):
+    """reference tests/test_difflexmm.py:35-146: a chain of rotated squares clamped on the left and pulled by a
+    ramped end load reaches the applied strain (rel 1e-4), both ligament energies, default 1e-8 tolerances."""
+    geo, cnv, bonds, ref = _rotated_square_chain(n1_cells)
+    k_stretch, mass = 1.0, 1.0
+    Jrot = 1.815 ** -2 / 4 * mass * geo.spacing ** 2
+    inertia = np.tile([mass, mass, Jrot], (geo.n_blocks, 1))
+    damping = 0.05 * np.tile([(k_stretch * mass) ** 0.5, (k_stretch * mass) ** 0.5,
+                              (k_stretch * mass) ** 0.5 * geo.spacing ** 2 / 4], (geo.n_blocks, 1))
+    cons = np.array([0 * 3 + 0, geo.n1_blocks * 3 + 0])
+    loaded = np.array([(geo.n1_blocks - 1) * 3, (geo.n_blocks - 1) * 3])
+    rate = 0.001 * (k_stretch / mass) ** 0.5
+    for strain in (0.2, 0.4, 0.6):
+        final_load = strain * geo.spacing * k_stretch
+        spec = _abi.TopologySpec(geo.n_blocks, 4, bonds, cons, bond_energy=bond_energy, load_kind=_abi.DFX_LOAD_RAMP,
+                                 loaded_dofs=loaded, load_consts=(final_load, rate), damped_blocks=np.arange(geo.n_blocks))
+        orc = Oracle(spec)
+        leaves = dict(centroid_node_vectors=cnv, reference_vector=ref, k_stretch=k_stretch, k_shear=1.851e-2 * k_stretch,
+                      k_rot=1.534e-4 / 4 * k_stretch * geo.spacing ** 2, damping=damping,
+                      inertia=inertia.reshape(-1)[spec.free_dofs])
+        ps = orc.params(1, leaves, damping_per_dof=True)
+        ts = np.linspace(0, 3 / rate, 100)
+        ys, st = orc.forward(ps, np.zeros(2 * spec.n_free), ts, 1e-8, 1e-8)
+        assert st["status"][0] == 0
+        fields = orc.expand_fields(ps, ys, ts)
+        got = fields[0, -1, 0, geo.n1_blocks - 1, 0] / (geo.spacing * (geo.n1_blocks - 1))
+        assert abs((got - strain) / strain) < 1e-4
+
+
+def test_reference_frame_invariance_of_ligament_energy():
+    """reference tests/test_difflexmm.py:149-176: two bonds between three nodes carried by one rigid rotation have
+    zero strain energy (< 1e-30) for rotations in [-pi, pi]."""
+    nodes = np.array([[[0., 0.], [1., 0.], [1., 1.]]])  # one rigid unit with three nodes
+    spec = _abi.TopologySpec(1, 3, [[0, 1], [1, 2]], [])
+    orc = Oracle(spec)
+    leaves = dict(centroid_node_vectors=nodes, reference_vector=np.array([[1., 0.], [0., 1.]]), k_stretch=1., k_shear=1.,
+                  k_rot=1., inertia=np.ones(3))
+    ps = orc.params(1, leaves)
+    for t in np.linspace(-math.pi, math.pi, 50):
+        assert orc.energy(ps, np.array([0., 0., t])) < 1e-30
+
+
+def _small_quads(contact_window):
+    from difflexmm_b200.problems import QuadsFocusing
+    P = QuadsFocusing(n1_blocks=8, n2_blocks=7, min_angle=contact_window[0], cutoff_angle=contact_window[1],
+                      simulation_time=0.01, n_timepoints=6)
+    spec, drive = P.lower()
+    hs, vs = P.random_ensemble(1, noise=0.05, seed0=7)
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs((hs[0], vs[0]))
+    return P, spec, {k: v.numpy() for k, v in leaves.items()}, pb, dpd, aug, y0.numpy(), ts.numpy()
+
+
+@pytest.mark.parametrize("window", [(-15 * math.pi / 180, -10 * math.pi / 180), (20 * math.pi / 180, 60 * math.pi / 180)],
+                         ids=["contact_inactive", "contact_active"])
+def test_force_is_minus_energy_gradient(window):
+    """finite differences of the energy (written from the energy definitions) against the analytic force in the RHS"""
+    P, spec, lv, pb, dpd, aug, y0, ts = _small_quads(window)
+    orc = Oracle(spec)
+    ps = orc.params(1, lv, pb, dpd)
+    rng = np.random.default_rng(0)
+    nf = spec.n_free
+    u = 0.3 * rng.standard_normal(nf)
+    t = 0.0  # drive at rest: constrained DOFs are zero
+    f = orc.rhs(ps, np.concatenate([u, np.zeros(nf)]), t)[nf:] * lv["inertia"]
+
+    def E(uu):
+        U = np.zeros(3 * spec.n_blocks)
+        U[spec.free_dofs] = uu
+        return orc.energy(ps, U)
+    idx = rng.choice(nf, 25, replace=False)
+    fd = np.array([-(E(u + 1e-6 * np.eye(nf)[i]) - E(u - 1e-6 * np.eye(nf)[i])) / 2e-6 for i in idx])
+    assert rel_l2(f[idx], fd) < 1e-7
+
+
+def test_adjoint_gradient_matches_finite_differences():
+    """d(objective)/d(parameter) from the adjoint against central differences of the forward solve, tight tolerance"""
+    P, spec, lv, pb, dpd, aug, y0, ts = _small_quads((-15 * math.pi / 180, -10 * math.pi / 180))
+    orc = Oracle(spec)
+    nf = spec.n_free
+    w = np.linspace(0.5, 1.5, len(ts) * 2 * nf).reshape(len(ts), 2 * nf)
+    rtol = atol = 1e-11
+
+    def objective(lvx):
+        ys, st = orc.forward(orc.params(1, lvx, pb, dpd), y0, ts, rtol, atol)
+        return float((w * np.sin(ys[0])).sum()), ys
+    J, ys = objective(lv)
+    g = (w * np.cos(ys[0]))[None]
+    y0b, tsb, gr, sb = orc.adjoint(orc.params(1, lv, pb, dpd), ys, ts, g, rtol, atol)
+    rng = np.random.default_rng(1)
+    for name, eps in (("centroid_node_vectors", 1e-6), ("reference_vector", 1e-6), ("k_shear", 1e-6), ("inertia", 1e-12),
+                      ("damping", 1e-9), ("drive", 2e-7)):
+        base = np.asarray(lv[name], dtype=np.float64)
+        d = rng.standard_normal(base.shape)
+        if name == "drive":  # (amplitude, rate, delay) span four decades: perturb each relative to its size
+            d = d * base
+        lp, lm = dict(lv), dict(lv)
+        lp[name], lm[name] = base + eps * d, base - eps * d
+        fd = (objective(lp)[0] - objective(lm)[0]) / (2 * eps)
+        an = float((gr[name][0] * d).sum())
+        tol = 2e-4 if name == "drive" else 2e-5  # the pulse delay has a large second derivative: FD truncation
+        assert abs(fd - an) <= tol * max(abs(fd), abs(an)), name

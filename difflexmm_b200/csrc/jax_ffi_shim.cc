@@ -1,0 +1,119 @@
+// jax_ffi_shim.cc -- XLA FFI handlers that expose libdfx's C ABI (include/dfx.h) to JAX as custom calls.
+//
+// NOT compiled in this image: it needs the XLA FFI headers shipped with a modern jaxlib
+// (`jax.ffi.include_dir()`, jax >= 0.4.31) and neither jax nor its headers are installed here.
+// It is kept in-tree, next to the kernels it binds, so that a maintainer with a JAX install can build it:
+//
+//   g++ -O2 -fPIC -shared -std=c++17 -I$(python -c "import jax; print(jax.ffi.include_dir())") \
+//       -I include -o libdfx_jax.so difflexmm_b200/csrc/jax_ffi_shim.cc -L difflexmm_b200 -ldfx
+//
+// and register it from Python:
+//
+//   jax.ffi.register_ffi_target("dfx_forward", jax.ffi.pycapsule(lib.DfxForward), platform="CUDA")
+//   jax.ffi.register_ffi_target("dfx_adjoint", jax.ffi.pycapsule(lib.DfxAdjoint), platform="CUDA")
+//
+// The two handlers replace the `odeint(rhs, _state0, timepoints, control_params, _inertia, rtol, atol)` call at
+// /root/reference/difflexmm/dynamics.py:166 and the backward of its custom_vjp.  Buffers are XLA-owned device
+// memory; the topology handle (created once per setup_dynamic_solver call) travels as an int64 attribute.
+
+#include <cstdint>
+
+#include "xla/ffi/api/ffi.h"
+
+#include "dfx.h"
+
+namespace ffi = xla::ffi;
+
+namespace {
+
+DfxLeaf Leaf(const ffi::Buffer<ffi::F64>& b, int64_t batch) {
+  DfxLeaf l;
+  l.ptr = b.typed_data();
+  // a leaf whose leading dimension equals the batch carries one slice per design, otherwise it is shared
+  l.bstride = (b.dimensions().size() > 0 && b.dimensions()[0] == batch) ? (int64_t)(b.element_count() / batch) : 0;
+  return l;
+}
+
+ffi::Error ForwardImpl(cudaStream_t stream, int64_t topo, int64_t k_per_bond_mask, int64_t damping_per_dof, double rtol,
+                       double atol, int64_t init_step_variant, ffi::Buffer<ffi::F64> y0, ffi::Buffer<ffi::F64> ts,
+                       ffi::Buffer<ffi::F64> cnv, ffi::Buffer<ffi::F64> ref, ffi::Buffer<ffi::F64> ks,
+                       ffi::Buffer<ffi::F64> ksh, ffi::Buffer<ffi::F64> kr, ffi::Buffer<ffi::F64> damping,
+                       ffi::Buffer<ffi::F64> inertia, ffi::Buffer<ffi::F64> contact, ffi::Buffer<ffi::F64> drive,
+                       ffi::ResultBuffer<ffi::F64> ys, ffi::ResultBuffer<ffi::U8> stats) {
+  const int64_t batch = ys->dimensions()[0], n_t = ys->dimensions()[1];
+  DfxParams p = {};
+  p.centroid_node_vectors = Leaf(cnv, batch); p.reference_vector = Leaf(ref, batch);
+  p.k_stretch = Leaf(ks, batch); p.k_shear = Leaf(ksh, batch); p.k_rot = Leaf(kr, batch);
+  for (int i = 0; i < 3; ++i) p.k_per_bond[i] = (k_per_bond_mask >> i) & 1;
+  p.damping = Leaf(damping, batch); p.damping_per_dof = (int32_t)damping_per_dof;
+  p.inertia = Leaf(inertia, batch); p.contact = Leaf(contact, batch); p.drive = Leaf(drive, batch);
+  DfxOptions opt = {(int32_t)init_step_variant, 0, 0};
+  const int64_t N = y0.dimensions().back();
+  int rc = dfx_forward(reinterpret_cast<const DfxTopology*>(topo), &p, (int)batch, y0.typed_data(),
+                       y0.dimensions().size() == 2 ? N : 0, ts.typed_data(), ts.dimensions().size() == 2 ? n_t : 0,
+                       (int)n_t, rtol, atol, &opt, ys->typed_data(), reinterpret_cast<DfxStats*>(stats->typed_data()),
+                       /*workspace=*/nullptr, 0, stream);
+  if (rc != DFX_OK) return ffi::Error(ffi::ErrorCode::kInternal, dfx_last_error());
+  return ffi::Error::Success();
+}
+
+ffi::Error AdjointImpl(cudaStream_t stream, int64_t topo, int64_t k_per_bond_mask, int64_t damping_per_dof, double rtol,
+                       double atol, int64_t aug_size, int64_t init_step_variant, ffi::Buffer<ffi::F64> ys,
+                       ffi::Buffer<ffi::F64> ts, ffi::Buffer<ffi::F64> g, ffi::Buffer<ffi::F64> cnv,
+                       ffi::Buffer<ffi::F64> ref, ffi::Buffer<ffi::F64> ks, ffi::Buffer<ffi::F64> ksh,
+                       ffi::Buffer<ffi::F64> kr, ffi::Buffer<ffi::F64> damping, ffi::Buffer<ffi::F64> inertia,
+                       ffi::Buffer<ffi::F64> contact, ffi::Buffer<ffi::F64> drive, ffi::ResultBuffer<ffi::F64> y0_bar,
+                       ffi::ResultBuffer<ffi::F64> ts_bar, ffi::ResultBuffer<ffi::F64> cnv_bar,
+                       ffi::ResultBuffer<ffi::F64> ref_bar, ffi::ResultBuffer<ffi::F64> ks_bar,
+                       ffi::ResultBuffer<ffi::F64> ksh_bar, ffi::ResultBuffer<ffi::F64> kr_bar,
+                       ffi::ResultBuffer<ffi::F64> damping_bar, ffi::ResultBuffer<ffi::F64> inertia_bar,
+                       ffi::ResultBuffer<ffi::F64> contact_bar, ffi::ResultBuffer<ffi::F64> drive_bar,
+                       ffi::ResultBuffer<ffi::U8> stats) {
+  const int64_t batch = ys.dimensions()[0], n_t = ys.dimensions()[1];
+  DfxParams p = {};
+  p.centroid_node_vectors = Leaf(cnv, batch); p.reference_vector = Leaf(ref, batch);
+  p.k_stretch = Leaf(ks, batch); p.k_shear = Leaf(ksh, batch); p.k_rot = Leaf(kr, batch);
+  for (int i = 0; i < 3; ++i) p.k_per_bond[i] = (k_per_bond_mask >> i) & 1;
+  p.damping = Leaf(damping, batch); p.damping_per_dof = (int32_t)damping_per_dof;
+  p.inertia = Leaf(inertia, batch); p.contact = Leaf(contact, batch); p.drive = Leaf(drive, batch);
+  DfxParamGrads gr = {cnv_bar->typed_data(), ref_bar->typed_data(), ks_bar->typed_data(), ksh_bar->typed_data(),
+                      kr_bar->typed_data(), damping_bar->typed_data(), inertia_bar->typed_data(),
+                      contact_bar->typed_data(), drive_bar->typed_data()};
+  DfxOptions opt = {(int32_t)init_step_variant, 0, 0};
+  int rc = dfx_adjoint(reinterpret_cast<const DfxTopology*>(topo), &p, (int)batch, ys.typed_data(), ts.typed_data(),
+                       ts.dimensions().size() == 2 ? n_t : 0, (int)n_t, g.typed_data(), rtol, atol, aug_size, &opt,
+                       y0_bar->typed_data(), ts_bar->typed_data(), &gr, reinterpret_cast<DfxStats*>(stats->typed_data()),
+                       /*workspace=*/nullptr, 0, stream);
+  if (rc != DFX_OK) return ffi::Error(ffi::ErrorCode::kInternal, dfx_last_error());
+  return ffi::Error::Success();
+}
+
+}  // namespace
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(
+    DfxForward, ForwardImpl,
+    ffi::Ffi::Bind()
+        .Ctx<ffi::PlatformStream<cudaStream_t>>()
+        .Attr<int64_t>("topology").Attr<int64_t>("k_per_bond_mask").Attr<int64_t>("damping_per_dof")
+        .Attr<double>("rtol").Attr<double>("atol").Attr<int64_t>("init_step_variant")
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()                                  // y0, ts
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()     // cnv, ref, ks
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()     // ksh, kr, damping
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()     // inertia, contact, drive
+        .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::U8>>());                                 // ys, stats
+
+XLA_FFI_DEFINE_HANDLER_SYMBOL(
+    DfxAdjoint, AdjointImpl,
+    ffi::Ffi::Bind()
+        .Ctx<ffi::PlatformStream<cudaStream_t>>()
+        .Attr<int64_t>("topology").Attr<int64_t>("k_per_bond_mask").Attr<int64_t>("damping_per_dof")
+        .Attr<double>("rtol").Attr<double>("atol").Attr<int64_t>("aug_size").Attr<int64_t>("init_step_variant")
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()     // ys, ts, g
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()     // cnv, ref, ks
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()     // ksh, kr, damping
+        .Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>().Arg<ffi::Buffer<ffi::F64>>()     // inertia, contact, drive
+        .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>()                                  // y0_bar, ts_bar
+        .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>()     // cnv_bar, ref_bar, ks_bar
+        .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>()     // ksh_bar, kr_bar, damping_bar
+        .Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>().Ret<ffi::Buffer<ffi::F64>>()     // inertia_bar, contact_bar, drive_bar
+        .Ret<ffi::Buffer<ffi::U8>>());                                                              // stats

@@ -395,7 +395,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
       drive_eval(T.drive_kind, time_next, g_drive, false, de);
       drv[28] = de.s[0]; drv[29] = de.s[1]; drv[30] = time_next;
     }
-#pragma unroll 1
+#pragma unroll
     for (int i = 0; i < 2; ++i) {
       const int b = bnd[i];
       const int b1 = i == 0 ? bb0.x : bb1.x, b2 = i == 0 ? bb0.y : bb1.y;

@@ -9,7 +9,7 @@
 #include <cstdlib>
 #include <type_traits>
 
-#include "dfx_adjoint2.cuh"
+#include "dfx_forward2.cuh"
 
 using namespace dfx;
 
@@ -171,6 +171,35 @@ FastPlan plan_fast_adjoint(const DevTopo& T) {
   return f;
 }
 
+// launch plan of the fast forward kernel (dfx_forward2.cuh)
+struct FastFwdPlan { bool ok; int threads, nt, ns, cols_per_warp, cols_alloc, ctas; size_t smem; long long scratch; };
+
+FastFwdPlan plan_fast_forward(const DevTopo& T) {
+  FastFwdPlan f = {};
+  const char* mode = getenv("DFX_FORWARD_KERNEL");  // "generic" | "notmem" | unset (fast + TMEM)
+  if (mode && !strcmp(mode, "generic")) return f;
+  int t = T.n_blocks > (T.n_bonds + 1) / 2 ? T.n_blocks : (T.n_bonds + 1) / 2;
+  t = t <= 384 ? 384 : 512;
+  if (T.n_npb > 4 || T.n_blocks > t || T.n_bonds > 2 * t) return f;
+  f.threads = t;
+  f.ctas = t == 384 ? 2 : 1;
+  f.nt = 42;
+  f.cols_per_warp = 2 * f.nt;
+  f.cols_alloc = t == 384 ? 256 : 512;  // 3 (resp. 4) warps share a lane quarter
+  if (mode && !strcmp(mode, "notmem")) { f.nt = 0; f.cols_alloc = 0; }
+  const size_t fixed = (size_t)(40 + 5LL * t + 8LL * t + 4) * 8 + (size_t)((T.n_nodes + 1) & ~1) * 4;
+  const size_t cap = kSmemBytes / f.ctas - 1024;
+  if (fixed + 8 * (size_t)t > cap) return f;
+  int ns = (int)((cap - fixed) / (8 * (size_t)t));
+  if (ns > F_NSLOT - f.nt) ns = F_NSLOT - f.nt;
+  f.ns = ns;
+  f.smem = fixed + (size_t)ns * t * 8;
+  const int n_over = F_NSLOT - f.nt - ns > 0 ? F_NSLOT - f.nt - ns : 0;
+  f.scratch = (long long)n_over * t + 32;
+  f.ok = true;
+  return f;
+}
+
 int check_params(const DevTopo& T, const DfxParams* p) {
   if (!p) return fail(DFX_ERR_INVALID, "params is NULL");
   if (!p->centroid_node_vectors.ptr || !p->reference_vector.ptr || !p->k_stretch.ptr || !p->k_shear.ptr || !p->k_rot.ptr ||
@@ -269,6 +298,12 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm, dnb};
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaFuncSetAttribute(forward2_kernel<42, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes / 2 - 1024);
+  cudaFuncSetAttribute(forward2_kernel<0, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes / 2 - 1024);
+  cudaFuncSetAttribute(forward2_kernel<42, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
+  cudaFuncSetAttribute(forward2_kernel<0, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
+  cudaFuncSetAttribute(forward2_kernel<42, 384, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(forward2_kernel<0, 384, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   cudaFuncSetAttribute(adjoint2_kernel<84, 32, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(adjoint2_kernel<84, -1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
@@ -296,6 +331,9 @@ size_t dfx_forward_workspace_bytes(const DfxTopology* t, int batch) {
   size_t smem;
   forward_sizes(t->dev, sz);
   plan(sz, off, &smem, &g);
+  FastFwdPlan f = plan_fast_forward(t->dev);
+  const long long fast = f.ok ? (long long)F_NSLOT * f.threads + 32 : 0;
+  if (fast > g) g = fast;
   return (size_t)g * sizeof(double) * (size_t)batch;
 }
 
@@ -337,6 +375,8 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
   a.init_step_variant = opt ? opt->init_step_variant : 0;
   a.max_steps = (opt && opt->max_steps > 0) ? opt->max_steps : (1LL << 40);
   a.ys = ys; a.stats = stats;
+  const FastFwdPlan fp = plan_fast_forward(t->dev);
+  if (fp.ok) g = fp.scratch;
   a.scratch_per_design = g;
   bool own_ws = false;
   if (g > 0) {
@@ -349,8 +389,22 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
       own_ws = true;
     }
   }
-  const int threads = pick_threads(t->dev, opt ? opt->threads : 0);
-  forward_kernel<<<batch, threads, smem, stream>>>(a);
+  if (fp.ok) {
+    Fwd2Args A2;
+    A2.a = a;
+    A2.node_bond = t->node_bond;
+    A2.tp_scratch_per_design = fp.scratch;
+    A2.ns_slots = fp.ns;
+    A2.tmem_cols_per_warp = fp.cols_per_warp;
+    A2.tmem_cols_alloc = fp.cols_alloc;
+    if (fp.threads == 384 && fp.nt == 42) forward2_kernel<42, 384, 2><<<batch, 384, fp.smem, stream>>>(A2);
+    else if (fp.threads == 384) forward2_kernel<0, 384, 2><<<batch, 384, fp.smem, stream>>>(A2);
+    else if (fp.nt == 42) forward2_kernel<42, 512, 1><<<batch, 512, fp.smem, stream>>>(A2);
+    else forward2_kernel<0, 512, 1><<<batch, 512, fp.smem, stream>>>(A2);
+  } else {
+    const int threads = pick_threads(t->dev, opt ? opt->threads : 0);
+    forward_kernel<<<batch, threads, smem, stream>>>(a);
+  }
   cudaError_t e = cudaGetLastError();
   if (own_ws) cudaFreeAsync(a.scratch, stream);
   if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "forward_kernel launch failed: %s", cudaGetErrorString(e));

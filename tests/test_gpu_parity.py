@@ -32,8 +32,19 @@ def _significant(ref, key):
     return np.abs(ref[key]).max() > 1e-9
 
 
+@pytest.fixture(params=["fast_tmem", "notmem", "generic"])
+def forward_kernel_mode(request, monkeypatch):
+    """the three forward code paths of libdfx (fast kernel with TMEM-resident stage history, fast kernel without
+    TMEM, generic kernel for any lattice size)"""
+    if request.param == "fast_tmem":
+        monkeypatch.delenv("DFX_FORWARD_KERNEL", raising=False)
+    else:
+        monkeypatch.setenv("DFX_FORWARD_KERNEL", request.param)
+    return request.param
+
+
 @pytest.mark.parametrize("name", golden_names())
-def test_forward_matches_golden(name):
+def test_forward_matches_golden(name, forward_kernel_mode):
     c = load_golden(name)
     lib, topo = _solver(c.spec)
     ps = _dev_params(c)

@@ -40,20 +40,23 @@ def multitask_value_and_grad(task_value_and_grad: Callable, design: Sequence[tor
                              weights: Sequence[float]):
     """weights @ [objective(design, task) for task in tasks] and its gradient w.r.t. the shared design.
 
-    `task_value_and_grad(design, task) -> (value, [grad per design tensor])` evaluates one task (one forward
-    + adjoint solve).  Tasks are sharded over the ranks; the weighted partial sums are packed into one flat
-    f64 buffer and all-reduced once."""
+    `task_value_and_grad(design, task, weight) -> (weight*value, [grad of weight*value per design tensor])`
+    evaluates one task (one forward + adjoint solve).  The weight goes INTO the differentiated function, as in the
+    reference where the cotangent entering each task's odeint backward is `weight_i * d objective_i / d ys`: the
+    adjoint solve is adaptive with an absolute tolerance, so scaling its cotangent afterwards is not the same
+    computation (the step sequence differs; results agree only to the integration tolerance).
+    Tasks are sharded over the ranks; the partial sums are packed into one flat f64 buffer and all-reduced once."""
     rank, nranks = world()
     b, e = shard_range(len(tasks), rank, nranks)
     dev = design[0].device
     sizes = [d.numel() for d in design]
     buf = torch.zeros(1 + sum(sizes), dtype=torch.float64, device=dev)
     for i in range(b, e):
-        v, gs = task_value_and_grad(design, tasks[i])
-        buf[0] += weights[i] * v
+        v, gs = task_value_and_grad(design, tasks[i], weights[i])
+        buf[0] += v
         off = 1
         for g, n in zip(gs, sizes):
-            buf[off:off + n] += weights[i] * g.reshape(-1).to(torch.float64)
+            buf[off:off + n] += g.reshape(-1).to(torch.float64)
             off += n
     allreduce_sum_(buf)
     grads, off = [], 1

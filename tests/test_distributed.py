@@ -21,12 +21,12 @@ def test_shard_range_partitions_everything():
             assert max(sizes) - min(sizes) <= 1
 
 
-def _task_value_and_grad(design, task):
+def _task_value_and_grad(design, task, weight=1.0):
     # stand-in for one forward + adjoint solve: a smooth function of the shared design and the task's parameters
     hs, vs = design
     amp, rate = task
     v = amp * (hs ** 2).sum() + rate * torch.sin(vs).sum()
-    return v, [2 * amp * hs, rate * torch.cos(vs)]
+    return weight * v, [weight * 2 * amp * hs, weight * rate * torch.cos(vs)]
 
 
 def _worker(rank, world, port, out):

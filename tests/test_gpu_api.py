@@ -91,3 +91,73 @@ def test_expand_fields_kernel_matches_torch_postprocessing():
     a = s._lib.expand_fields(s.handle, ps, ys, ts)
     b = s.expand_fields(ys, ts, cp)
     assert torch.allclose(a, b, rtol=1e-13, atol=1e-13)
+
+
+def test_lattice_beyond_the_fast_kernels_uses_the_generic_path():
+    """26 x 22 quads (572 units > 512 threads): generic forward / adjoint kernels with state spilled to the
+    L2-resident scratch (the cfg5 route), against the C++ oracle"""
+    from difflexmm_b200 import _abi
+    from oracle import Oracle
+    P = _problem(n1_blocks=26, n2_blocks=22, simulation_time=0.004, n_timepoints=4, target_shift=(2, 2))
+    s = P.setup()
+    design = P.initial_design()
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(design, device="cuda")
+    ps = _abi.ParamSet(P.spec, 1, {k: v.contiguous() for k, v in leaves.items()}, pb, dpd)
+    ys, st = s.lib_forward(ps, y0, ts)
+    assert st.numpy()["status"][0] == 0
+    orc = Oracle(P.spec)
+    ph = orc.params(1, {k: v.cpu().numpy() for k, v in leaves.items()}, pb, dpd)
+    ys_h, st_h = orc.forward(ph, y0.cpu().numpy(), ts.cpu().numpy(), P.rtol, P.atol)
+    assert rel_l2(ys[0].cpu().numpy(), ys_h[0]) <= 1e-6
+    g = np.cos(ys_h) + 0.2
+    y0b_h, tsb_h, gr_h, _ = orc.adjoint(ph, ys_h, ts.cpu().numpy(), g, P.rtol, P.atol, aug)
+    y0b, tsb, gr, sb = s.lib_adjoint(ps, torch.as_tensor(ys_h, device="cuda"), ts, torch.as_tensor(g, device="cuda"), aug)
+    assert sb.numpy()["status"][0] == 0
+    for k in gr_h:
+        if np.abs(gr_h[k]).max() > 1e-9:
+            assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= 1e-5, k
+
+
+def test_static_tuning_multitask_objective():
+    """cfg4 recipe (static pre-compression ramp + delayed pulse, two tasks with weights 0.75 / -0.25, summed design
+    gradient; reference problems/quads_kinetic_energy_static_tuning.py:431-484) on a small lattice: the weighted
+    multi-task gradient equals the gradient of the weighted sum, and one task matches the C++ oracle"""
+    from difflexmm_b200 import _abi
+    from difflexmm_b200.parallel import multitask_value_and_grad
+    from difflexmm_b200.problems import QuadsStaticTuning
+    from oracle import Oracle
+    base = dict(n1_blocks=8, n2_blocks=8, simulation_time_dynamic=0.008, n_timepoints=6, target_shift=(1, 1),
+                compressive_strain_rate=25.0)
+    tasks = [dict(compressive_strain=0.01), dict(compressive_strain=0.03)]
+    weights = [0.75, -0.25]
+    probs = [QuadsStaticTuning(**base, **t) for t in tasks]
+    for p in probs:
+        p.setup()
+    hs, vs = probs[0].initial_design()
+
+    def task_vg(design, p, weight):
+        h = design[0].clone().requires_grad_(True)
+        v = design[1].clone().requires_grad_(True)
+        J = weight * p.target_kinetic_energy((h, v))
+        J.backward()
+        return J.detach(), [h.grad, v.grad]
+
+    design = [hs.cuda(), vs.cuda()]
+    J, grads = multitask_value_and_grad(task_vg, design, probs, weights)
+    h = design[0].clone().requires_grad_(True)
+    v = design[1].clone().requires_grad_(True)
+    Jsum = sum(w * p.target_kinetic_energy((h, v)) for w, p in zip(weights, probs))
+    Jsum.backward()
+    assert torch.allclose(J, Jsum.detach(), rtol=1e-12)
+    for a, b in zip(grads, (h.grad, v.grad)):
+        assert (a - b).abs().max() <= 1e-10 * b.abs().max()
+    # one task against the oracle at the boundary
+    p = probs[1]
+    leaves, pb, dpd, aug, y0, ts = p.boundary_inputs((hs, vs))
+    orc = Oracle(p.spec)
+    ph = orc.params(1, {k: x.numpy() for k, x in leaves.items()}, pb, dpd)
+    ys_h, _ = orc.forward(ph, y0.numpy(), ts.numpy(), p.rtol, p.atol)
+    dl = {k: x.cuda().contiguous() for k, x in leaves.items()}
+    ys_d, st = p.solver.lib_forward(_abi.ParamSet(p.spec, 1, dl, pb, dpd), y0.cuda(), ts.cuda())
+    assert st.numpy()["status"][0] == 0
+    assert rel_l2(ys_d[0].cpu().numpy(), ys_h[0]) <= 1e-6

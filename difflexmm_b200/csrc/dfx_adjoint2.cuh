@@ -142,6 +142,7 @@ struct Adj2Args {
   const int* node_bond;      // [n_nodes] bond*2+side of the bond attached to the node, or -1
   long long tp_scratch_per_design;  // doubles of global scratch per design: constants tier overflow + quadratures
   int ns_slots;              // thread-private slots placed in shared memory
+  int scratch_slots;         // > 0: scratch indexed by SM id (slots available); 0: by design
   int tmem_cols_per_warp;    // columns of TMEM owned by one warp
 };
 
@@ -183,7 +184,11 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
   TP<NT, NS, TT> tp;
   tp.ns = A.ns_slots;
   tp.s = tp_s + tid;
-  double* gbase = a.scratch + (long long)design * A.tp_scratch_per_design;
+  // the scratch is indexed by SM, not by design: one CTA is resident per SM (shared-memory footprint), so the same
+  // lines are reused by every design the SM processes and stay in L2 (A.scratch_slots = %nsmid bound, else per design)
+  unsigned smid;
+  asm("mov.u32 %0, %%smid;" : "=r"(smid));
+  double* gbase = a.scratch + (long long)(A.scratch_slots > 0 && (int)smid < A.scratch_slots ? (int)smid : design) * A.tp_scratch_per_design;
   tp.g = gbase + tid;
   tp.taddr = NT > 0 ? (tmem_base_sh + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * A.tmem_cols_per_warp)) : 0u;
   // quadrature arrays [NQA][NE][T] behind the constants-tier overflow
@@ -285,8 +290,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
   // y_bar = g[-1]
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    tp.st(S_LU0 + j, is_free[j] ? gg[(long long)(a.n_t - 1) * 2 * nf + fidx[j]] : 0.0);
-    tp.st(S_LV0 + j, is_free[j] ? gg[(long long)(a.n_t - 1) * 2 * nf + nf + fidx[j]] : 0.0);
+    tp.st(S_LU0 + j, is_free[j] ? __ldcs(&gg[(long long)(a.n_t - 1) * 2 * nf + fidx[j]]) : 0.0);
+    tp.st(S_LV0 + j, is_free[j] ? __ldcs(&gg[(long long)(a.n_t - 1) * 2 * nf + nf + fidx[j]]) : 0.0);
   }
   tp.fence_st();
   __syncthreads();
@@ -378,14 +383,14 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
   // `time_next`: real time of the next evaluation when it is already known (drive channels are prepared for it).
   auto aug_BC = [&](double time, int kidx, double time_next) -> double {
     const bool want_q = qc.mode != 1;
-    double qv[NE];
+    constexpr int NEB = NE - E_REF;  // bond-owned entries: reference vector (+ per-bond stiffnesses)
+    double qb[NEB];                  // integrands of the bond-owned entries (live from phase B to the end of phase C)
 #pragma unroll
-    for (int e = 0; e < NE; ++e) qv[e] = 0.0;
+    for (int e = 0; e < NEB; ++e) qb[e] = 0.0;
     __syncthreads();
     // ============ phase B: bonds ============
     double p_ks = 0, p_ksh = 0, p_kr = 0, p_c0 = 0, p_c1 = 0, p_c2 = 0;
     const AccCoef ac = acc_coef();
-    constexpr int NEB = NE - E_REF;  // bond-owned entries: reference vector (+ per-bond stiffnesses)
     if (tid == nthr - 1 && T.drive_kind != DFX_DRIVE_ZERO) {  // drive channels: now (with derivatives) and next
       DriveEval de;
       drive_eval(T.drive_kind, time, g_drive, true, de);
@@ -433,11 +438,12 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
         if (contact) { SL[12 * NDS + b] = a1; SL[13 * NDS + b] = a2; }
         // d(w.F)/dp = -(dual part of dE/dp)
         // (static indices keep qv in registers although the bond loop is not unrolled)
-        if (i == 0) { qv[E_REF] = -o.gr0[0].d; qv[E_REF + 1] = -o.gr0[1].d; }
-        else { qv[E_REF + 2] = -o.gr0[0].d; qv[E_REF + 3] = -o.gr0[1].d; }
-        if (ks_pb) { if (i == 0) qv[E_KPB] = -o.gks.d; else qv[E_KPB + 3] = -o.gks.d; } else p_ks -= o.gks.d;
-        if (ksh_pb) { if (i == 0) qv[E_KPB + 1] = -o.gksh.d; else qv[E_KPB + 4] = -o.gksh.d; } else p_ksh -= o.gksh.d;
-        if (kr_pb) { if (i == 0) qv[E_KPB + 2] = -o.gkr.d; else qv[E_KPB + 5] = -o.gkr.d; } else p_kr -= o.gkr.d;
+        if (i == 0) { qb[0] = -o.gr0[0].d; qb[1] = -o.gr0[1].d; }
+        else { qb[2] = -o.gr0[0].d; qb[3] = -o.gr0[1].d; }
+        constexpr int KP = E_KPB - E_REF;
+        if (ks_pb) { if (i == 0) qb[KP] = -o.gks.d; else qb[KP + 3] = -o.gks.d; } else p_ks -= o.gks.d;
+        if (ksh_pb) { if (i == 0) qb[KP + 1] = -o.gksh.d; else qb[KP + 4] = -o.gksh.d; } else p_ksh -= o.gksh.d;
+        if (kr_pb) { if (i == 0) qb[KP + 2] = -o.gkr.d; else qb[KP + 5] = -o.gkr.d; } else p_kr -= o.gkr.d;
       }
     }
     if (ac.on && want_q) {
@@ -447,8 +453,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
       for (int k = 0; k < NEB; ++k) if (E_REF + k < ne_used) { bs_in[k] = Q(ac.a_s, E_REF + k); be_in[k] = Q(ac.a_e, E_REF + k); }
 #pragma unroll
       for (int k = 0; k < NEB; ++k) if (E_REF + k < ne_used) {
-        Q(QA_SOL, E_REF + k) = fma(qc.cs, qv[E_REF + k], ac.fs * bs_in[k]);
-        Q(QA_ERR, E_REF + k) = fma(qc.ce, qv[E_REF + k], ac.fe * be_in[k]);
+        Q(QA_SOL, E_REF + k) = fma(qc.cs, qb[k], ac.fs * bs_in[k]);
+        Q(QA_ERR, E_REF + k) = fma(qc.ce, qb[k], ac.fe * be_in[k]);
       }
     }
     if (want_q) {
@@ -461,6 +467,9 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     }
     __syncthreads();
     // ============ phase C: this thread's unit ============
+    double qv[NE];  // unit-owned integrands in [0, E_REF); the bond-owned ones are appended only for the rare modes
+#pragma unroll
+    for (int e = 0; e < E_REF; ++e) qv[e] = 0.0;
     double F[3] = {0, 0, 0}, HW[3] = {0, 0, 0}, An[4] = {0, 0, 0, 0}, Ap[4] = {0, 0, 0, 0};
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
@@ -564,9 +573,13 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
         }
         if (qc.crossing) {  // midpoint sums: one step in ~25, not prefetched
 #pragma unroll
-          for (int k = 0; k < NE; ++k) if (k < ne_used) Q(ac.a_k7, k) = fma(qc.cm, qv[k], ac.fm * Q(ac.a_m, k));
+          for (int k = 0; k < E_REF; ++k) Q(ac.a_k7, k) = fma(qc.cm, qv[k], ac.fm * Q(ac.a_m, k));
+#pragma unroll
+          for (int k = 0; k < NEB; ++k) if (E_REF + k < ne_used) Q(ac.a_k7, E_REF + k) = fma(qc.cm, qb[k], ac.fm * Q(ac.a_m, E_REF + k));
         }
       } else {
+#pragma unroll
+        for (int k = 0; k < NEB; ++k) qv[E_REF + k] = qb[k];
         probe = quad_apply(qv);
       }
       // t0_bar and the drive parameters only receive contributions from constrained or loaded DOFs
@@ -685,8 +698,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
         tp.template ldn<3>(S_LV0, 1, lvs);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          us[j] = is_free[j] ? yi[fidx[j]] : 0.0;
-          vs[j] = is_free[j] ? yi[nf + fidx[j]] : 0.0;
+          us[j] = is_free[j] ? __ldcs(&yi[fidx[j]]) : 0.0;
+          vs[j] = is_free[j] ? __ldcs(&yi[nf + fidx[j]]) : 0.0;
           tp.st(S_U0 + j, us[j]); tp.st(S_V0 + j, vs[j]);
         }
         time = -s0; kidx = 0; qc.mode = 0;
@@ -726,7 +739,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
         tp.template ldn<3>(S_KV + j, 21, k0);
         if (is_free[j]) {
           // t_bar = func(ys[i], ts[i]) . g[i] with func = (v0, -kv[0])
-          pt += y0[1] * gi[fidx[j]] - k0[0] * gi[nf + fidx[j]];
+          pt += y0[1] * __ldcs(&gi[fidx[j]]) - k0[0] * __ldcs(&gi[nf + fidx[j]]);
           const double su = atol + fabs(y0[0]) * rtol, sv = atol + fabs(y0[1]) * rtol;
           const double slu = atol + fabs(y0[2]) * rtol, slv = atol + fabs(y0[3]) * rtol;
           const double a0 = y0[0] / su, a1 = y0[1] / sv, a2 = y0[2] / slu, a3 = y0[3] / slv;
@@ -858,8 +871,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
               for (int l = 0; l < 7; ++l) { mlu = fma(tab.c_mid[l], klu[l], mlu); mlv = fma(tab.c_mid[l], klv[l], mlv); }
               const double nlu = interp_eval(y0[2], y1[j][2], y0[2] + h * mlu, h * klu[0], h * klu[6], qc.x);
               const double nlv = interp_eval(y0[3], y1[j][3], y0[3] + h * mlv, h * klv[0], h * klv[6], qc.x);
-              tp.st(S_LU0 + j, is_free[j] ? nlu + gp[fidx[j]] : 0.0);
-              tp.st(S_LV0 + j, is_free[j] ? nlv + gp[nf + fidx[j]] : 0.0);
+              tp.st(S_LU0 + j, is_free[j] ? nlu + __ldcs(&gp[fidx[j]]) : 0.0);
+              tp.st(S_LV0 + j, is_free[j] ? nlv + __ldcs(&gp[nf + fidx[j]]) : 0.0);
             }
             interval_done = true;
           } else {

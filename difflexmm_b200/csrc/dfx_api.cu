@@ -33,6 +33,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr size_t kSmemBytes = 232448;  // 227 KB: the opt-in maximum of one CTA on sm_100
 constexpr int kRedDoubles = 40;
+constexpr int kScratchSlots = 256;  // >= %nsmid of any sm_100 part: SM-indexed scratch of the fast adjoint kernel
 
 template <class T>
 cudaError_t upload(const std::vector<T>& h, T** d) {
@@ -353,7 +354,8 @@ size_t dfx_adjoint_workspace_bytes(const DfxTopology* t, int batch) {
   // worst case of the two kernels (the fast one assumes S_TOTAL slots with no TMEM)
   long long fast = f.ok ? (long long)(S_NCONST - f.ns + (NQA + 1) * NE) * f.threads + 32 : 0;
   if (fast > g) g = fast;
-  return (size_t)g * sizeof(double) * (size_t)batch;
+  const int units = f.ok && batch < kScratchSlots ? kScratchSlots : batch;  // the fast kernel indexes scratch by SM id
+  return (size_t)g * sizeof(double) * (size_t)units;
 }
 
 int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const double* y0, int64_t y0_bstride,
@@ -452,8 +454,10 @@ int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const 
   if (fp.ok) g = fp.scratch;
   a.scratch_per_design = g;
   bool own_ws = false;
+  // fast kernel: scratch indexed by SM id when that is smaller than one slice per design
+  const int scratch_slots = (fp.ok && batch > kScratchSlots) ? kScratchSlots : 0;
   if (g > 0) {
-    const size_t need = (size_t)g * sizeof(double) * (size_t)batch;
+    const size_t need = (size_t)g * sizeof(double) * (size_t)(scratch_slots ? scratch_slots : batch);
     if (workspace) {
       if (workspace_bytes < need) return fail(DFX_ERR_INVALID, "workspace too small: %zu < %zu", workspace_bytes, need);
       a.scratch = (double*)workspace;
@@ -468,6 +472,7 @@ int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const 
     A2.node_bond = t->node_bond;
     A2.tp_scratch_per_design = fp.scratch;
     A2.ns_slots = fp.ns;
+    A2.scratch_slots = scratch_slots;
     A2.tmem_cols_per_warp = fp.cols_per_warp;
     if (fp.nt == 84 && fp.ns == 32) adjoint2_kernel<84, 32, 384><<<batch, 384, fp.smem, stream>>>(A2);
     else if (fp.nt == 84) adjoint2_kernel<84, -1, 384><<<batch, 384, fp.smem, stream>>>(A2);

@@ -161,3 +161,34 @@ def test_static_tuning_multitask_objective():
     ys_d, st = p.solver.lib_forward(_abi.ParamSet(p.spec, 1, dl, pb, dpd), y0.cuda(), ts.cuda())
     assert st.numpy()["status"][0] == 0
     assert rel_l2(ys_d[0].cpu().numpy(), ys_h[0]) <= 1e-6
+
+
+def test_cfg5_lattice_100x100_with_active_contact():
+    """cfg5 of BASELINE.json: quads 100 x 100 (10^4 units, 19 800 bonds, ~30k free DOFs) with the contact window
+    moved to [+15, +25] degrees so that contact is active (rest void angles are 40 / 140 degrees; SURVEY section 8d);
+    short horizon so that the C++ oracle finishes in seconds.  Generic kernels (state in the L2-resident scratch)."""
+    from difflexmm_b200 import _abi
+    from oracle import Oracle
+    P = _problem(n1_blocks=100, n2_blocks=100, simulation_time=0.006, n_timepoints=3, target_shift=(2, 2),
+                 min_angle=15 * math.pi / 180, cutoff_angle=45 * math.pi / 180)
+    s = P.setup()
+    design = P.initial_design()
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(design, device="cuda")
+    ps = _abi.ParamSet(P.spec, 1, {k: v.contiguous() for k, v in leaves.items()}, pb, dpd)
+    ys, st = s.lib_forward(ps, y0, ts)
+    assert st.numpy()["status"][0] == 0
+    orc = Oracle(P.spec)
+    ph = orc.params(1, {k: v.cpu().numpy() for k, v in leaves.items()}, pb, dpd)
+    ys_h, st_h = orc.forward(ph, y0.cpu().numpy(), ts.cpu().numpy(), P.rtol, P.atol)
+    assert int(st.numpy()["steps"][0]) == int(st_h["steps"][0])
+    assert rel_l2(ys[0].cpu().numpy(), ys_h[0]) <= 1e-6
+    nf = P.spec.n_free
+    g = np.zeros_like(ys_h)
+    g[:, :, nf:] = ys_h[:, :, nf:] * leaves["inertia"].cpu().numpy()
+    y0b_h, tsb_h, gr_h, sb_h = orc.adjoint(ph, ys_h, ts.cpu().numpy(), g, P.rtol, P.atol, aug)
+    y0b, tsb, gr, sb = s.lib_adjoint(ps, torch.as_tensor(ys_h, device="cuda"), ts, torch.as_tensor(g, device="cuda"), aug)
+    assert sb.numpy()["status"][0] == 0
+    assert np.abs(gr_h["contact"]).max() > 0  # contact really is active
+    for k in gr_h:
+        if np.abs(gr_h[k]).max() > 1e-9:
+            assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= 1e-5, k

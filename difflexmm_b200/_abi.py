@@ -9,7 +9,7 @@ import ctypes as C
 import numpy as np
 
 DFX_BOND_LIGAMENT, DFX_BOND_LINEARIZED = 0, 1
-DFX_DRIVE_ZERO, DFX_DRIVE_PULSE, DFX_DRIVE_HARMONIC, DFX_DRIVE_RAMP, DFX_DRIVE_STATIC_PULSE = range(5)
+DFX_DRIVE_ZERO, DFX_DRIVE_PULSE, DFX_DRIVE_HARMONIC, DFX_DRIVE_RAMP, DFX_DRIVE_STATIC_PULSE, DFX_DRIVE_TABLE = range(6)
 DFX_LOAD_NONE, DFX_LOAD_RAMP, DFX_LOAD_SECH2 = range(3)
 DFX_MAX_DRIVE_PARAMS = 5
 DFX_MAX_LOAD_CONSTS = 4
@@ -23,6 +23,7 @@ DRIVE_PARAM_NAMES = {
     DFX_DRIVE_RAMP: ("amplitude", "loading_rate"),
     DFX_DRIVE_STATIC_PULSE: ("amplitude", "loading_rate", "compressive_strain",
                              "compressive_strain_rate", "input_delay"),
+    DFX_DRIVE_TABLE: (),
 }
 
 _i32p = C.POINTER(C.c_int32)
@@ -36,6 +37,7 @@ class DfxTopologyDesc(C.Structure):
         ("n_constrained", C.c_int32), ("constrained_dofs", _i32p),
         ("bond_energy", C.c_int32), ("contact", C.c_int32), ("drive_kind", C.c_int32),
         ("drive_vec0", _f64p), ("drive_vec1", _f64p),
+        ("drive_table_len", C.c_int32), ("drive_table_t", _f64p), ("drive_table_v", _f64p),
         ("load_kind", C.c_int32), ("n_loaded", C.c_int32),
         ("loaded_dofs", _i32p), ("load_vec", _f64p),
         ("load_consts", C.c_double * DFX_MAX_LOAD_CONSTS),
@@ -84,7 +86,8 @@ class TopologySpec:
 
     def __init__(self, n_blocks, n_npb, bond_nodes, constrained_dofs=(), bond_energy=DFX_BOND_LIGAMENT,
                  contact=False, drive_kind=DFX_DRIVE_ZERO, drive_vec0=None, drive_vec1=None,
-                 load_kind=DFX_LOAD_NONE, loaded_dofs=(), load_vec=None, load_consts=(), damped_blocks=()):
+                 load_kind=DFX_LOAD_NONE, loaded_dofs=(), load_vec=None, load_consts=(), damped_blocks=(),
+                 drive_table=None):
         self.n_blocks, self.n_npb = int(n_blocks), int(n_npb)
         self.bond_nodes = np.ascontiguousarray(np.asarray(bond_nodes, dtype=np.int32).reshape(-1, 2))
         self.constrained_dofs = np.ascontiguousarray(np.asarray(constrained_dofs, dtype=np.int32).reshape(-1))
@@ -99,6 +102,14 @@ class TopologySpec:
                 raise ValueError(f"drive vector has {len(v)} entries, expected n_constrained={nc}")
             return v
         self.drive_vec0, self.drive_vec1 = vec(drive_vec0), vec(drive_vec1)
+        self.drive_table = None
+        if drive_table is not None:
+            tt, tv = (np.ascontiguousarray(np.asarray(x, dtype=np.float64).reshape(-1)) for x in drive_table)
+            if len(tt) != len(tv) or len(tt) < 1 or np.any(np.diff(tt) < 0):
+                raise ValueError("tabulated drive needs equally long, increasing times and values")
+            self.drive_table = (tt, tv)
+        if (self.drive_kind == DFX_DRIVE_TABLE) != (self.drive_table is not None):
+            raise ValueError("drive_table must be given exactly for DFX_DRIVE_TABLE")
         self.load_kind = int(load_kind)
         self.loaded_dofs = np.ascontiguousarray(np.asarray(loaded_dofs, dtype=np.int32).reshape(-1))
         self.load_vec = None if load_vec is None else np.ascontiguousarray(
@@ -128,6 +139,10 @@ class TopologySpec:
         d.bond_energy, d.contact, d.drive_kind = self.bond_energy, int(self.contact), self.drive_kind
         d.drive_vec0 = self.drive_vec0.ctypes.data_as(_f64p) if self.drive_vec0 is not None else None
         d.drive_vec1 = self.drive_vec1.ctypes.data_as(_f64p) if self.drive_vec1 is not None else None
+        if self.drive_table is not None:
+            d.drive_table_len = len(self.drive_table[0])
+            d.drive_table_t = self.drive_table[0].ctypes.data_as(_f64p)
+            d.drive_table_v = self.drive_table[1].ctypes.data_as(_f64p)
         d.load_kind, d.n_loaded = self.load_kind, len(self.loaded_dofs)
         d.loaded_dofs = self.loaded_dofs.ctypes.data_as(_i32p)
         d.load_vec = self.load_vec.ctypes.data_as(_f64p) if self.load_vec is not None else None

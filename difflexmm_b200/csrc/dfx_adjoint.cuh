@@ -283,7 +283,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
           const int c = T.cons_slot[dof];
           if (c >= 0 && T.drive_kind != DFX_DRIVE_ZERO) {
             DriveEval de;
-            drive_eval(T.drive_kind, time, g_drive, true, de);
+            drive_eval(T.drive_kind, time, g_drive, true, de, T.table);
             const double v0_ = T.drive_vec0[c], v1_ = T.drive_vec1[c];
             p_t0 -= HW * (v0_ * de.sdot[0] + v1_ * de.sdot[1]);
             for (int q = 0; q < ndp; ++q) p_dr[q] -= HW * (v0_ * de.dsdp[0][q] + v1_ * de.dsdp[1][q]);
@@ -327,7 +327,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
       const int c = T.cons_slot[3 * blk + j];
       if (c >= 0 && T.drive_kind != DFX_DRIVE_ZERO) {
         DriveEval de;
-        drive_eval(T.drive_kind, time, g_drive, false, de);
+        drive_eval(T.drive_kind, time, g_drive, false, de, T.table);
         u = T.drive_vec0[c] * de.s[0] + T.drive_vec1[c] * de.s[1];
       }
     }

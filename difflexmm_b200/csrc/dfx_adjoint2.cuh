@@ -393,11 +393,11 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     const AccCoef ac = acc_coef();
     if (tid == nthr - 1 && T.drive_kind != DFX_DRIVE_ZERO) {  // drive channels: now (with derivatives) and next
       DriveEval de;
-      drive_eval(T.drive_kind, time, g_drive, true, de);
+      drive_eval(T.drive_kind, time, g_drive, true, de, T.table);
       drv[2] = de.sdot[0]; drv[3] = de.sdot[1];
 #pragma unroll
       for (int q = 0; q < DFX_MAX_DRIVE_PARAMS; ++q) { drv[4 + q] = de.dsdp[0][q]; drv[9 + q] = de.dsdp[1][q]; }
-      drive_eval(T.drive_kind, time_next, g_drive, false, de);
+      drive_eval(T.drive_kind, time_next, g_drive, false, de, T.table);
       drv[28] = de.s[0]; drv[29] = de.s[1]; drv[30] = time_next;
     }
 #pragma unroll
@@ -603,7 +603,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
       if (drv[30] == time) { s0_ = drv[28]; s1_ = drv[29]; }
       else {
         DriveEval de;
-        drive_eval(T.drive_kind, time, g_drive, false, de);
+        drive_eval(T.drive_kind, time, g_drive, false, de, T.table);
         s0_ = de.s[0]; s1_ = de.s[1];
       }
 #pragma unroll

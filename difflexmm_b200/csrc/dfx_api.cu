@@ -225,7 +225,7 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   if (d->n_blocks <= 0 || d->n_npb < 2 || d->n_bonds < 0) return fail(DFX_ERR_INVALID, "bad sizes");
   if (d->bond_energy != DFX_BOND_LIGAMENT && d->bond_energy != DFX_BOND_LINEARIZED)
     return fail(DFX_ERR_UNSUPPORTED, "unknown bond energy %d", d->bond_energy);
-  if (d->drive_kind < DFX_DRIVE_ZERO || d->drive_kind > DFX_DRIVE_STATIC_PULSE)
+  if (d->drive_kind < DFX_DRIVE_ZERO || d->drive_kind > DFX_DRIVE_TABLE)
     return fail(DFX_ERR_UNSUPPORTED, "unknown drive kind %d", d->drive_kind);
   if (d->load_kind < DFX_LOAD_NONE || d->load_kind > DFX_LOAD_SECH2)
     return fail(DFX_ERR_UNSUPPORTED, "unknown load kind %d", d->load_kind);
@@ -280,7 +280,13 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   D.bond_energy = d->bond_energy; D.contact = d->contact ? 1 : 0; D.drive_kind = d->drive_kind;
   D.load_kind = d->load_kind; D.n_drive_params = n_drive_params_of(d->drive_kind); D.n_damped = d->n_damped;
   for (int i = 0; i < DFX_MAX_LOAD_CONSTS; ++i) D.load_consts[i] = d->load_consts[i];
-  int2 *dbn, *dbb; int *dfo, *dcs, *dds, *dfd, *dnb; double *dv0, *dv1, *dlm;
+  int2 *dbn, *dbb; int *dfo, *dcs, *dds, *dfd, *dnb; double *dv0, *dv1, *dlm, *dtt = nullptr, *dtv = nullptr;
+  std::vector<double> tab_t, tab_v;
+  if (d->drive_kind == DFX_DRIVE_TABLE) {
+    if (d->drive_table_len < 1 || !d->drive_table_t || !d->drive_table_v) { delete t; cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "tabulated drive needs drive_table_t / drive_table_v"); }
+    tab_t.assign(d->drive_table_t, d->drive_table_t + d->drive_table_len);
+    tab_v.assign(d->drive_table_v, d->drive_table_v + d->drive_table_len);
+  }
   cudaError_t e = cudaSuccess;
   if (e == cudaSuccess) e = upload(bn, &dbn);
   if (e == cudaSuccess) e = upload(bb, &dbb);
@@ -292,11 +298,14 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   if (e == cudaSuccess) e = upload(v1, &dv1);
   if (e == cudaSuccess) e = upload(load_mul, &dlm);
   if (e == cudaSuccess) e = upload(node_bond, &dnb);
+  if (e == cudaSuccess) e = upload(tab_t, &dtt);
+  if (e == cudaSuccess) e = upload(tab_v, &dtv);
   if (e != cudaSuccess) { delete t; cudaSetDevice(cur); return fail(DFX_ERR_CUDA, "topology upload failed: %s", cudaGetErrorString(e)); }
   D.bond_nodes = dbn; D.bond_blocks = dbb; D.free_of_dof = dfo; D.cons_slot = dcs; D.damp_slot = dds; D.free_dofs = dfd;
   D.drive_vec0 = dv0; D.drive_vec1 = dv1; D.load_mul = dlm;
   t->node_bond = dnb;
-  t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm, dnb};
+  D.table.t = dtt; D.table.v = dtv; D.table.n = (int)tab_t.size();
+  t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm, dnb, dtt, dtv};
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
   cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   cudaFuncSetAttribute(forward2_kernel<42, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes / 2 - 1024);
@@ -502,7 +511,7 @@ __global__ void expand_fields_kernel(DevTopo T, DfxLeaf drive, const double* ys,
   const double t = ts[(long long)design * ts_bstride + i];
   const double* dp = drive.ptr ? drive.ptr + (long long)design * drive.bstride : nullptr;
   DriveEval de;
-  drive_eval(T.drive_kind, t, dp, true, de);
+  drive_eval(T.drive_kind, t, dp, true, de, T.table);
   for (int dof = threadIdx.x; dof < nd; dof += blockDim.x) {
     const int f = T.free_of_dof[dof];
     double u, v;

@@ -315,6 +315,11 @@ __device__ __forceinline__ void bond_gradient(int energy_kind, const BlockState<
 struct DriveEval {
   double s[2], sdot[2], dsdp[2][DFX_MAX_DRIVE_PARAMS];
 };
+struct DriveTable {  // tabulated drive (jnp.interp): device arrays
+  const double* t;
+  const double* v;
+  int n;
+};
 
 __device__ __forceinline__ void pulse_eval(double tau, double A, double f, bool windowed, bool want_grad, double& s,
                                            double& ds_dtau, double& ds_dA, double& ds_df) {
@@ -334,7 +339,7 @@ __device__ __forceinline__ void pulse_eval(double tau, double A, double f, bool 
   }
 }
 
-__device__ inline void drive_eval(int kind, double t, const double* p, bool want_grad, DriveEval& e) {
+__device__ inline void drive_eval(int kind, double t, const double* p, bool want_grad, DriveEval& e, DriveTable tab = DriveTable{nullptr, nullptr, 0}) {
   e.s[0] = e.s[1] = e.sdot[0] = e.sdot[1] = 0.0;
 #pragma unroll
   for (int j = 0; j < DFX_MAX_DRIVE_PARAMS; ++j) e.dsdp[0][j] = e.dsdp[1][j] = 0.0;
@@ -359,6 +364,20 @@ __device__ inline void drive_eval(int kind, double t, const double* p, bool want
       e.dsdp[0][2] = -dtau / csr; e.dsdp[0][3] = dtau * cs / (csr * csr); e.dsdp[0][4] = -dtau;
       if (t < cs / csr) { e.s[1] = t * csr; e.sdot[1] = csr; e.dsdp[1][3] = t; }
       else { e.s[1] = cs; e.dsdp[1][2] = 1.0; }
+    } break;
+    case DFX_DRIVE_TABLE: {
+      // jnp.interp(t, xp, fp): i = clip(searchsorted(xp, t, side='right'), 1, n-1); linear on [xp[i-1], xp[i]];
+      // constant (and zero slope) outside the table
+      if (tab.n <= 0) break;
+      if (tab.n == 1 || t < tab.t[0]) { e.s[0] = tab.v[0]; break; }
+      if (t > tab.t[tab.n - 1]) { e.s[0] = tab.v[tab.n - 1]; break; }
+      int lo = 0, hi = tab.n;  // first index with xp[idx] > t
+      while (lo < hi) { const int mid = (lo + hi) >> 1; if (tab.t[mid] <= t) lo = mid + 1; else hi = mid; }
+      int i = lo < 1 ? 1 : (lo > tab.n - 1 ? tab.n - 1 : lo);
+      const double dx = tab.t[i] - tab.t[i - 1], df = tab.v[i] - tab.v[i - 1];
+      if (dx == 0.0) { e.s[0] = tab.v[i]; break; }
+      e.s[0] = tab.v[i - 1] + (t - tab.t[i - 1]) / dx * df;
+      e.sdot[0] = df / dx;
     } break;
     default: break;
   }

@@ -29,6 +29,7 @@ struct DevTopo {
   const double* load_mul;   // [n_dof] load multiplier (0 = not loaded)
   const int* free_dofs;     // [n_free] natural DOF id of every free DOF
   double load_consts[DFX_MAX_LOAD_CONSTS];
+  DriveTable table;         // DFX_DRIVE_TABLE
 };
 
 // arrays of the forward kernel, in placement-priority order (doubles)
@@ -191,7 +192,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
       u = 0.0;
       if (c >= 0 && T.drive_kind != DFX_DRIVE_ZERO) {
         DriveEval de;
-        drive_eval(T.drive_kind, tstage, g_drive, false, de);
+        drive_eval(T.drive_kind, tstage, g_drive, false, de, T.table);
         u = T.drive_vec0[c] * de.s[0] + T.drive_vec1[c] * de.s[1];
       }
     }

@@ -150,7 +150,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
     __syncthreads();
     if (tid == nthr - 1 && T.drive_kind != DFX_DRIVE_ZERO) {  // drive channels of the next evaluation
       DriveEval de;
-      drive_eval(T.drive_kind, time_next, g_drive, false, de);
+      drive_eval(T.drive_kind, time_next, g_drive, false, de, T.table);
       drv[0] = de.s[0]; drv[1] = de.s[1]; drv[2] = time_next;
     }
 #pragma unroll
@@ -214,7 +214,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
       if (drv[2] == time) { s0_ = drv[0]; s1_ = drv[1]; }
       else {
         DriveEval de;
-        drive_eval(T.drive_kind, time, g_drive, false, de);
+        drive_eval(T.drive_kind, time, g_drive, false, de, T.table);
         s0_ = de.s[0]; s1_ = de.s[1];
       }
 #pragma unroll

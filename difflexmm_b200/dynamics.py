@@ -60,7 +60,7 @@ def lower_topology(geometry: Geometry, energy_fn, loaded_block_DOF_pairs=None, l
     else:
         raise TypeError(
             "constrained_DOFs_fn must be a difflexmm_b200.loading drive signal (pulse_drive, harmonic_drive, "
-            "ramp_drive, static_pulse_drive) or None; arbitrary Python callables cannot run inside the CUDA solver")
+            "ramp_drive, static_pulse_drive, tabulated_drive) or None; arbitrary Python callables cannot run inside the CUDA solver")
     load_kind, loaded, load_vec, load_consts = _abi.DFX_LOAD_NONE, (), None, ()
     if loaded_block_DOF_pairs is not None and loading_fn is not None:
         if not isinstance(loading_fn, LoadSignal):
@@ -72,6 +72,7 @@ def lower_topology(geometry: Geometry, energy_fn, loaded_block_DOF_pairs=None, l
         n_blocks=geometry.n_blocks, n_npb=geometry.n_npb, bond_nodes=energy_fn.bond_connectivity,
         constrained_dofs=constrained, bond_energy=energy_fn.bond_kind, contact=energy_fn.contact,
         drive_kind=drive.kind, drive_vec0=drive.vec0, drive_vec1=drive.vec1,
+        drive_table=(drive.times, drive.values) if drive.kind == _abi.DFX_DRIVE_TABLE else None,
         load_kind=load_kind, loaded_dofs=loaded, load_vec=load_vec, load_consts=load_consts,
         damped_blocks=_np_int(damped_blocks) if damped_blocks is not None else ())
     return spec, drive
@@ -268,7 +269,7 @@ class DynamicSolver:
         free = torch.as_tensor(spec.free_dofs, device=dev)
         out = torch.zeros((B, n_t, 2, nd), dtype=_F64, device=dev)
         out = out.index_copy(3, free, ys.reshape(B, n_t, 2, nf))
-        if len(spec.constrained_dofs) and spec.n_drive_params:
+        if len(spec.constrained_dofs) and spec.drive_kind != _abi.DFX_DRIVE_ZERO:
             cons = torch.as_tensor(spec.constrained_dofs.astype(np.int64), device=dev)
             u_c, v_c = drive_values(self.drive, ts if ts.dim() == 2 else ts[None].expand(B, n_t),
                                     control_params.constraint_params, dev)

@@ -103,6 +103,27 @@ class static_pulse_drive(DriveSignal):
         return s0, s1
 
 
+class tabulated_drive(DriveSignal):
+    """`excited_blocks_fn(t) * loading_vector` with `excited_blocks_fn = lambda t: jnp.interp(t, times, values)`: the
+    measured input signal of the experiment notebooks (reference `problems/quads_focusing.py:223-227`,
+    exp/.../experiment_vs_simulation.ipynb cell 12).  No differentiable parameters."""
+    kind = _abi.DFX_DRIVE_TABLE
+
+    def __init__(self, times, values, loading_vector):
+        super().__init__(loading_vector)
+        self.times = np.asarray(times, dtype=np.float64).reshape(-1)
+        self.values = np.asarray(values, dtype=np.float64).reshape(-1)
+
+    def channels(self, t):
+        xp = torch.as_tensor(self.times, device=t.device)
+        fp = torch.as_tensor(self.values, device=t.device)
+        i = torch.clamp(torch.searchsorted(xp, t.detach().contiguous(), right=True), 1, len(xp) - 1)
+        dx, df = xp[i] - xp[i - 1], fp[i] - fp[i - 1]
+        f = torch.where(dx == 0, fp[i], fp[i - 1] + (t - xp[i - 1]) / torch.where(dx == 0, torch.ones_like(dx), dx) * df)
+        f = torch.where(t < xp[0], fp[0].expand_as(f), torch.where(t > xp[-1], fp[-1].expand_as(f), f))
+        return f, torch.zeros_like(t)
+
+
 class LoadSignal:
     """external force on the loaded DOFs, load_vec[l]*s(t) with captured constants."""
     kind = _abi.DFX_LOAD_NONE

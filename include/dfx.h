@@ -49,6 +49,9 @@ enum {
   DFX_DRIVE_HARMONIC = 2, /* problems/quads_spin.py:210-221; same params, on tau>0          */
   DFX_DRIVE_RAMP = 3,     /* problems/hinge_characterization.py:134-139; (amplitude,
                              loading_rate): A*(t<1/f ? t*f : 1)                              */
+  DFX_DRIVE_TABLE = 5,    /* `excited_blocks_fn = jnp.interp(t, table_t, table_v)` of the experiment notebooks
+                             (exp/.../experiment_vs_simulation.ipynb cell 12; problems/quads_focusing.py:223-227):
+                             s0 = interp(t), constant outside the table, 0 params                           */
   DFX_DRIVE_STATIC_PULSE = 4 /* problems/quads_kinetic_energy_static_tuning.py:176-196;
                              (amplitude, loading_rate, compressive_strain,
                              compressive_strain_rate, input_delay):
@@ -82,6 +85,9 @@ typedef struct DfxTopologyDesc {
   int32_t drive_kind;        /* DFX_DRIVE_*                                             */
   const double* drive_vec0;  /* [n_constrained] or NULL (= zeros)                       */
   const double* drive_vec1;  /* [n_constrained] or NULL                                 */
+  int32_t drive_table_len;   /* DFX_DRIVE_TABLE: samples of the tabulated signal        */
+  const double* drive_table_t; /* [drive_table_len] increasing times                    */
+  const double* drive_table_v; /* [drive_table_len] values                              */
   int32_t load_kind;         /* DFX_LOAD_*                                              */
   int32_t n_loaded;
   const int32_t* loaded_dofs;/* [n_loaded] global DOF ids                               */

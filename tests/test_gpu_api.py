@@ -192,3 +192,38 @@ def test_cfg5_lattice_100x100_with_active_contact():
     for k in gr_h:
         if np.abs(gr_h[k]).max() > 1e-9:
             assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= 1e-5, k
+
+
+def test_tabulated_drive_matches_oracle():
+    """measured-input style drive (jnp.interp table) through libdfx vs the C++ oracle, forward and adjoint"""
+    from difflexmm_b200 import _abi, _lib
+    from difflexmm_b200.dynamics import lower_topology
+    from difflexmm_b200.loading import tabulated_drive
+    from oracle import Oracle
+    P = _problem()
+    spec0, drive0 = P.lower()
+    times = np.linspace(0.0, 0.012, 25)
+    values = 7.5 * (1 - np.cos(2 * np.pi * 30 * np.clip(times - 0.001, 0, None))) / 2
+    drive = tabulated_drive(times, values, drive0.vec0)
+    spec, _ = lower_topology(P.geometry, P.energy(P.geometry.bond_connectivity()), None, None,
+                             P.constrained_block_DOF_pairs, drive, np.arange(P.geometry.n_blocks))
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(P.initial_design())
+    leaves = {k: v for k, v in leaves.items() if k != "drive"}
+    orc = Oracle(spec)
+    ph = orc.params(1, {k: v.numpy() for k, v in leaves.items()}, pb, dpd)
+    ys_h, st_h = orc.forward(ph, y0.numpy(), ts.numpy(), P.rtol, P.atol)
+    g = np.sin(ys_h) + 0.1
+    y0b_h, tsb_h, gr_h, _ = orc.adjoint(ph, ys_h, ts.numpy(), g, P.rtol, P.atol)
+    topo = _lib.Topology(spec, torch.cuda.current_device())
+    ps = _abi.ParamSet(spec, 1, {k: v.cuda().contiguous() for k, v in leaves.items()}, pb, dpd)
+    opt = _abi.DfxOptions(0, 0, 0)
+    ys, st = _lib.forward(topo, ps, y0.cuda(), ts.cuda(), P.rtol, P.atol, opt)
+    assert st.numpy()["status"][0] == 0 and np.abs(ys_h).max() > 0
+    assert rel_l2(ys[0].cpu().numpy(), ys_h[0]) <= 1e-6
+    y0b, tsb, gr, sb = _lib.adjoint(topo, ps, torch.as_tensor(ys_h, device="cuda"), ts.cuda(), torch.as_tensor(g, device="cuda"),
+                                    P.rtol, P.atol, 0, opt)
+    assert sb.numpy()["status"][0] == 0
+    assert rel_l2(tsb[0].cpu().numpy(), tsb_h[0]) <= 1e-5
+    for k in gr_h:
+        if np.abs(gr_h[k]).max() > 1e-9:
+            assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= 1e-5, k

@@ -146,3 +146,34 @@ def test_solver_refuses_to_run_without_cuda():
     g.compute_geometry()
     with pytest.raises(RuntimeError):
         setup_dynamic_solver(g, build_strain_energy(g.bond_connectivity(), ligament_energy), device="cpu")
+
+
+def test_tabulated_drive_matches_numpy_interp():
+    """`excited_blocks_fn = jnp.interp(t, times, values)` (reference problems/quads_focusing.py:223-227): oracle,
+    torch post-processing and numpy agree, including the clamped ends and the slope used as velocity"""
+    from difflexmm_b200.dynamics import drive_values
+    from difflexmm_b200.loading import tabulated_drive
+    from oracle import Oracle
+    times = np.linspace(0.002, 0.03, 15)
+    values = 3.0 * np.sin(40 * times) ** 2
+    g = QuadGeometry(4, 3, spacing=15., bond_length=2.25)
+    g.compute_geometry()
+    drive = tabulated_drive(times, values, [1., 0., -0.5])
+    spec, drive = lower_topology(g, build_strain_energy(g.bond_connectivity(), ligament_energy), None, None,
+                                 [[0, 0], [0, 1], [5, 2]], drive, np.arange(g.n_blocks))
+    assert spec.drive_kind == _abi.DFX_DRIVE_TABLE and spec.n_drive_params == 0
+    ts = np.linspace(0.0, 0.035, 23)
+    u, v = drive_values(drive, torch.as_tensor(ts)[None], {}, "cpu")
+    ref = np.interp(ts, times, values)
+    assert np.allclose(u[0, :, 0].numpy(), ref, rtol=1e-14, atol=1e-15)
+    assert np.allclose(u[0, :, 2].numpy(), -0.5 * ref, rtol=1e-14, atol=1e-15)
+    orc = Oracle(spec)
+    cnv = g.centroid_node_vectors(*g.get_design_from_rotated_square(0.3)).numpy()
+    leaves = dict(centroid_node_vectors=cnv, reference_vector=g.reference_bond_vectors().numpy(), k_stretch=1., k_shear=1.,
+                  k_rot=1., damping=0.1, inertia=np.ones(spec.n_free))
+    ps = orc.params(1, leaves)
+    f = orc.expand_fields(ps, np.zeros((1, len(ts), 2 * spec.n_free)), ts).reshape(1, len(ts), 2, -1)
+    assert np.allclose(f[0, :, 0, 0], ref, rtol=1e-14, atol=1e-15)
+    assert np.allclose(f[0, :, 1, 0], v[0, :, 0].numpy(), rtol=1e-12, atol=1e-12)
+    inside = (ts > times[0]) & (ts < times[-1])
+    assert np.all(f[0, ~inside, 1, 0] == 0.0) and np.any(f[0, inside, 1, 0] != 0.0)

@@ -227,3 +227,39 @@ def test_tabulated_drive_matches_oracle():
     for k in gr_h:
         if np.abs(gr_h[k]).max() > 1e-9:
             assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= 1e-5, k
+
+
+def test_status_flags_and_per_design_inputs():
+    """per-design y0 / ts (batch strides), max_steps -> DFX_STATUS_MAX_STEPS with NaN outputs, init_step_variant switch"""
+    from difflexmm_b200 import _abi, _lib
+    from oracle import Oracle
+    P = _problem()
+    P.lower()
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(P.initial_design())
+    spec = P.spec
+    topo = _lib.Topology(spec, torch.cuda.current_device())
+    B = 3
+    dl = {k: v.cuda().contiguous() for k, v in leaves.items()}
+    ps = _abi.ParamSet(spec, B, dl, pb, dpd)
+    rng = np.random.default_rng(0)
+    y0b = 1e-3 * rng.standard_normal((B, 2 * spec.n_free))
+    tsb = np.stack([ts.numpy() * s for s in (1.0, 0.8, 0.5)])
+    ys, st = _lib.forward(topo, ps, torch.as_tensor(y0b, device="cuda"), torch.as_tensor(tsb, device="cuda"), P.rtol, P.atol,
+                          _abi.DfxOptions(0, 0, 0))
+    assert (st.numpy()["status"] == 0).all()
+    orc = Oracle(spec)
+    ph = orc.params(B, {k: v.numpy() for k, v in leaves.items()}, pb, dpd)
+    ys_h, _ = orc.forward(ph, y0b, tsb, P.rtol, P.atol)
+    for b in range(B):
+        assert rel_l2(ys[b].cpu().numpy(), ys_h[b]) <= 1e-6
+    # later jax releases use max(d1, d2) in initial_step_size: a different, equally valid step sequence
+    ys1, st1 = _lib.forward(topo, ps, torch.as_tensor(y0b, device="cuda"), torch.as_tensor(tsb, device="cuda"), P.rtol, P.atol,
+                            _abi.DfxOptions(1, 0, 0))
+    ys1_h, _ = orc.forward(ph, y0b, tsb, P.rtol, P.atol, variant=1)
+    assert rel_l2(ys1.cpu().numpy(), ys1_h) <= 1e-6
+    # a step budget that cannot reach the first output: status flag + NaN outputs, never garbage
+    ys2, st2 = _lib.forward(topo, ps, torch.as_tensor(y0b, device="cuda"), torch.as_tensor(tsb, device="cuda"), P.rtol, P.atol,
+                            _abi.DfxOptions(0, 0, 3))
+    s2 = st2.numpy()
+    assert (s2["status"] & _abi.DFX_STATUS_MAX_STEPS).all() and (s2["steps"] == 3).all()
+    assert torch.isnan(ys2[:, 1:]).all() and torch.isfinite(ys2[:, 0]).all()

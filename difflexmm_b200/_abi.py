@@ -69,6 +69,10 @@ class DfxOptions(C.Structure):
     _fields_ = [("init_step_variant", C.c_int32), ("threads", C.c_int32), ("max_steps", C.c_int64)]
 
 
+class DfxKineticObjective(C.Structure):
+    _fields_ = [("target_free_ids", C.c_void_p), ("n_target", C.c_int32), ("weights", C.c_void_p)]
+
+
 class DfxStats(C.Structure):
     _fields_ = [("steps", C.c_int64), ("accepted", C.c_int64), ("rhs_evals", C.c_int64),
                 ("status", C.c_int32), ("reserved", C.c_int32), ("last_dt", C.c_double)]

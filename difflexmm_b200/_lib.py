@@ -46,7 +46,7 @@ lib.dfx_fp64_peak.restype = C.c_double
 
 EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free", "dfx_drive_n_params",
            "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
-           "dfx_expand_fields", "dfx_fp64_peak", "dfx_math_selftest", "dfx_last_error", "dfx_version")
+           "dfx_expand_fields", "dfx_kinetic_energy", "dfx_adjoint_kinetic", "dfx_fp64_peak", "dfx_math_selftest", "dfx_last_error", "dfx_version")
 
 
 def _check(rc, what):
@@ -127,6 +127,55 @@ def adjoint(topo: Topology, ps: _abi.ParamSet, ys, ts, g, rtol, atol, aug_size, 
                                C.c_void_p(y0_bar.data_ptr()), C.c_void_p(ts_bar.data_ptr()), C.byref(gs),
                                C.c_void_p(stats.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes),
                                _stream_ptr(dev)), "dfx_adjoint")
+    return y0_bar, ts_bar, grads, _Stats(stats)
+
+
+def kinetic_energy(topo: Topology, ps: _abi.ParamSet, ys, target_free_ids, want_inertia_bar=True):
+    """-> J (B,) = sum_t sum_{f in target} 1/2 m_f v_f^2, and dJ/d(inertia) (B, n_free) or None."""
+    spec, B = topo.spec, ps.batch
+    dev = ys.device
+    n_t = ys.shape[1]
+    ys = ys.contiguous()
+    ids = target_free_ids.to(device=dev, dtype=torch.int32).contiguous()
+    value = torch.empty((B,), dtype=torch.float64, device=dev)
+    ibar = torch.empty((B, spec.n_free), dtype=torch.float64, device=dev) if want_inertia_bar else None
+    obj = _abi.DfxKineticObjective(ids.data_ptr(), ids.numel(), None)
+    p = ps.to_struct()
+    with torch.cuda.device(dev):
+        _check(lib.dfx_kinetic_energy(topo._h, C.byref(p), B, C.c_void_p(ys.data_ptr()), n_t, C.byref(obj),
+                                      C.c_void_p(value.data_ptr()), C.c_void_p(ibar.data_ptr() if ibar is not None else None),
+                                      _stream_ptr(dev)), "dfx_kinetic_energy")
+    return value, ibar
+
+
+def adjoint_kinetic(topo: Topology, ps: _abi.ParamSet, ys, ts, target_free_ids, weights, rtol, atol, aug_size,
+                    options: _abi.DfxOptions):
+    """`adjoint` with the cotangent of the kinetic objective generated in the kernel (weights[b] = dL/dJ_b)."""
+    spec, B = topo.spec, ps.batch
+    N = 2 * spec.n_free
+    dev = ys.device
+    n_t = ts.shape[-1]
+    ys, ts = ys.contiguous(), ts.contiguous()
+    ids = target_free_ids.to(device=dev, dtype=torch.int32).contiguous()
+    w = weights.to(device=dev, dtype=torch.float64).expand(B).contiguous()
+    y0_bar = torch.zeros((B, N), dtype=torch.float64, device=dev)
+    ts_bar = torch.zeros((B, n_t), dtype=torch.float64, device=dev)
+    grads = {n: torch.zeros((B,) + ps.base_shapes[n], dtype=torch.float64, device=dev) for n in ps.leaves}
+    gs = _abi.DfxParamGrads()
+    for n, t in grads.items():
+        setattr(gs, n, t.data_ptr())
+    stats = torch.zeros((B, _abi.STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
+    obj = _abi.DfxKineticObjective(ids.data_ptr(), ids.numel(), w.data_ptr())
+    p = ps.to_struct()
+    with torch.cuda.device(dev):
+        ws_bytes = lib.dfx_adjoint_workspace_bytes(topo._h, B)
+        ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
+        _check(lib.dfx_adjoint_kinetic(topo._h, C.byref(p), B, C.c_void_p(ys.data_ptr()), C.c_void_p(ts.data_ptr()),
+                                       C.c_int64(n_t if ts.dim() == 2 else 0), n_t, C.byref(obj),
+                                       C.c_double(rtol), C.c_double(atol), C.c_int64(int(aug_size)), C.byref(options),
+                                       C.c_void_p(y0_bar.data_ptr()), C.c_void_p(ts_bar.data_ptr()), C.byref(gs),
+                                       C.c_void_p(stats.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes),
+                                       _stream_ptr(dev)), "dfx_adjoint_kinetic")
     return y0_bar, ts_bar, grads, _Stats(stats)
 
 

@@ -50,7 +50,8 @@ struct AdjArgs {
   Tableau tab;
   PlacementA place;
   const double* ys; const double* ts; long long ts_bstride; int n_t;
-  const double* g;
+  const double* g;            // cotangent of ys, or NULL when the kinetic objective generates it in the kernel
+  const int* obj_ids; int obj_n; const double* obj_w;  // kinetic objective (fast kernel only)
   double rtol, atol;
   long long aug_size;
   int init_step_variant; long long max_steps;

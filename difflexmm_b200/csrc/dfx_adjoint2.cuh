@@ -146,8 +146,23 @@ struct Adj2Args {
   int tmem_cols_per_warp;    // columns of TMEM owned by one warp
 };
 
+// Cotangent of ys[design][i][(is_v ? n_free : 0) + f].  Either read from the caller's tensor `g`, or (g == NULL) formed
+// here for the kinetic objective J = w * sum 1/2 m v^2 over the target DOFs: dJ/dv_f = w m_f v_f, dJ/du = 0.
+// Called once per output time and DOF (cold); kept out of line so that it costs the integration loop no registers.
+__device__ __noinline__ double cotangent_nl(const AdjArgs& a, int design, int i, int f, bool is_v) {
+  const int nf = a.topo.n_free;
+  const long long at = ((long long)design * a.n_t + i) * 2 * nf + (is_v ? nf : 0) + f;
+  if (a.g) return __ldcs(&a.g[at]);
+  if (!is_v) return 0.0;
+  bool target = false;
+  for (int k = 0; k < a.obj_n; ++k) target |= a.obj_ids[k] == f;
+  if (!target) return 0.0;
+  const double w = a.obj_w ? a.obj_w[design] : 1.0;
+  return w * a.p.inertia.ptr[(long long)design * a.p.inertia.bstride + f] * __ldcs(&a.ys[at]);
+}
+
 template <int NT, int NS, int TT>
-__global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
+__global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__ Adj2Args A) {
   extern __shared__ double smem[];
   __shared__ uint32_t tmem_base_sh;
   const AdjArgs& a = A.a;
@@ -219,7 +234,6 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
   const double* g_drive = leaf_ptr(a.p.drive, design);
   const double* ts = a.ts + (long long)design * a.ts_bstride;
   const double* ys = a.ys + (long long)design * a.n_t * 2 * nf;
-  const double* gg = a.g + (long long)design * a.n_t * 2 * nf;
   const double rtol = a.rtol, atol = a.atol;
   const bool ks_pb = a.p.k_per_bond[0], ksh_pb = a.p.k_per_bond[1], kr_pb = a.p.k_per_bond[2];
   const bool any_pb = ks_pb || ksh_pb || kr_pb;
@@ -242,6 +256,9 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     cslot[j] = has_blk ? T.cons_slot[dof] : -1;
     dslot[j] = T.damp_slot[dof];
   }
+  // cotangent of output i for DOF j of this unit (displacement part, velocity part); cold, out of line
+  auto cot_u = [&](int i, int j) { return cotangent_nl(a, design, i, fidx[j], false); };
+  auto cot_v = [&](int i, int j) { return cotangent_nl(a, design, i, fidx[j], true); };
   const bool has_cons = cslot[0] >= 0 || cslot[1] >= 0 || cslot[2] >= 0;
   bool has_load = false;
   if (T.load_kind != DFX_LOAD_NONE && has_blk)
@@ -290,8 +307,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
   // y_bar = g[-1]
 #pragma unroll
   for (int j = 0; j < 3; ++j) {
-    tp.st(S_LU0 + j, is_free[j] ? __ldcs(&gg[(long long)(a.n_t - 1) * 2 * nf + fidx[j]]) : 0.0);
-    tp.st(S_LV0 + j, is_free[j] ? __ldcs(&gg[(long long)(a.n_t - 1) * 2 * nf + nf + fidx[j]]) : 0.0);
+    tp.st(S_LU0 + j, is_free[j] ? cot_u(a.n_t - 1, j) : 0.0);
+    tp.st(S_LV0 + j, is_free[j] ? cot_v(a.n_t - 1, j) : 0.0);
   }
   tp.fence_st();
   __syncthreads();
@@ -730,7 +747,6 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
     n_rhs++;
     // ---------------- what follows the evaluation ----------------
     if (ev == EV_INIT) {
-      const double* gi = gg + (long long)i * 2 * nf;
       double sd0 = 0, sd1 = 0, pt = 0.0;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -739,7 +755,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
         tp.template ldn<3>(S_KV + j, 21, k0);
         if (is_free[j]) {
           // t_bar = func(ys[i], ts[i]) . g[i] with func = (v0, -kv[0])
-          pt += y0[1] * __ldcs(&gi[fidx[j]]) - k0[0] * __ldcs(&gi[nf + fidx[j]]);
+          pt += y0[1] * cot_u(i, j) - k0[0] * cot_v(i, j);
           const double su = atol + fabs(y0[0]) * rtol, sv = atol + fabs(y0[1]) * rtol;
           const double slu = atol + fabs(y0[2]) * rtol, slv = atol + fabs(y0[3]) * rtol;
           const double a0 = y0[0] / su, a1 = y0[1] / sv, a2 = y0[2] / slu, a3 = y0[3] / slv;
@@ -859,7 +875,6 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
           ++n_acc;
           if (qc.crossing) {
             // interval finished: cotangents interpolated at s_target, plus g[i-1]
-            const double* gp = gg + (long long)(i - 1) * 2 * nf;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               double klu[7], klv[7], y0[4];
@@ -871,8 +886,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const Adj2Args A) {
               for (int l = 0; l < 7; ++l) { mlu = fma(tab.c_mid[l], klu[l], mlu); mlv = fma(tab.c_mid[l], klv[l], mlv); }
               const double nlu = interp_eval(y0[2], y1[j][2], y0[2] + h * mlu, h * klu[0], h * klu[6], qc.x);
               const double nlv = interp_eval(y0[3], y1[j][3], y0[3] + h * mlv, h * klv[0], h * klv[6], qc.x);
-              tp.st(S_LU0 + j, is_free[j] ? nlu + __ldcs(&gp[fidx[j]]) : 0.0);
-              tp.st(S_LV0 + j, is_free[j] ? nlv + __ldcs(&gp[nf + fidx[j]]) : 0.0);
+              tp.st(S_LU0 + j, is_free[j] ? nlu + cot_u(i - 1, j) : 0.0);
+              tp.st(S_LV0 + j, is_free[j] ? nlv + cot_v(i - 1, j) : 0.0);
             }
             interval_done = true;
           } else {

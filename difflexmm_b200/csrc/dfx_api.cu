@@ -422,11 +422,48 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
   return DFX_OK;
 }
 
-int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
-                int64_t ts_bstride, int n_t, const double* g_, double rtol, double atol, int64_t aug_size,
-                const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
-                void* workspace, size_t workspace_bytes, void* stream_) {
-  if (!t || !ys || !ts || !g_) return fail(DFX_ERR_INVALID, "NULL argument");
+}  // extern "C"
+
+namespace {
+__global__ void kinetic_cotangent_kernel(DevTopo T, DfxLeaf inertia, const double* ys, int n_t, const int* ids, int n_ids,
+                                         const double* w, double* g) {
+  // g[b][i][:] = 0 except g[b][i][n_free + f] = w_b * m_f * v_f for the target DOFs (generic-kernel route)
+  const int b = blockIdx.y, i = blockIdx.x, nf = T.n_free;
+  double* gi = g + ((long long)b * n_t + i) * 2 * nf;
+  const double* yi = ys + ((long long)b * n_t + i) * 2 * nf;
+  for (int k = threadIdx.x; k < 2 * nf; k += blockDim.x) gi[k] = 0.0;
+  __syncthreads();
+  const double* m = inertia.ptr + (long long)b * inertia.bstride;
+  const double wb = w ? w[b] : 1.0;
+  for (int k = threadIdx.x; k < n_ids; k += blockDim.x) gi[nf + ids[k]] = wb * m[ids[k]] * yi[nf + ids[k]];
+}
+
+__global__ void kinetic_energy_kernel(DevTopo T, DfxLeaf inertia, const double* ys, int n_t, const int* ids, int n_ids,
+                                      double* value, double* inertia_bar) {
+  // one CTA per design: J = sum_t sum_f 1/2 m v^2 ; dJ/dm_f = sum_t 1/2 v^2
+  __shared__ double red[40];
+  const int b = blockIdx.x, nf = T.n_free;
+  const double* m = inertia.ptr + (long long)b * inertia.bstride;
+  if (inertia_bar) for (int k = threadIdx.x; k < nf; k += blockDim.x) inertia_bar[(long long)b * nf + k] = 0.0;
+  __syncthreads();
+  double acc = 0.0;
+  for (int k = threadIdx.x; k < n_ids; k += blockDim.x) {
+    const int f = ids[k];
+    double s2 = 0.0;
+    for (int i = 0; i < n_t; ++i) { const double v = ys[((long long)b * n_t + i) * 2 * nf + nf + f]; s2 = fma(v, v, s2); }
+    acc += 0.5 * m[f] * s2;
+    if (inertia_bar) inertia_bar[(long long)b * nf + f] = 0.5 * s2;
+  }
+  acc = block_sum(acc, red);
+  if (threadIdx.x == 0) value[b] = acc;
+}
+
+int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
+                 int64_t ts_bstride, int n_t, const double* g_, const DfxKineticObjective* obj, double rtol, double atol,
+                 int64_t aug_size, const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads,
+                 DfxStats* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!t || !ys || !ts || (!g_ && !obj)) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (obj && (obj->n_target < 0 || (obj->n_target > 0 && !obj->target_free_ids))) return fail(DFX_ERR_INVALID, "bad objective");
   if (batch <= 0 || n_t < 1) return fail(DFX_ERR_INVALID, "batch and n_t must be positive");
   if (int rc = check_params(t->dev, params)) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -442,6 +479,7 @@ int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const 
   adjoint_sizes(T, q, sz);
   plan(sz, a.place.off, &smem, &g);
   a.ys = ys; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t; a.g = g_;
+  if (obj) { a.obj_ids = obj->target_free_ids; a.obj_n = obj->n_target; a.obj_w = obj->weights; }
   a.rtol = rtol; a.atol = atol;
   if (aug_size <= 0) {
     // count the leaves listed in DfxParams: y, y_bar, t0_bar, then every leaf
@@ -489,14 +527,55 @@ int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const 
     else if (fp.threads == 384) adjoint2_kernel<0, -1, 384><<<batch, 384, fp.smem, stream>>>(A2);
     else adjoint2_kernel<0, -1, 512><<<batch, 512, fp.smem, stream>>>(A2);
   } else {
+    // generic kernel: it reads a materialised cotangent
+    double* gtmp = nullptr;
+    if (!g_) {
+      CUDA_TRY(cudaMallocAsync((void**)&gtmp, (size_t)batch * n_t * 2 * T.n_free * sizeof(double), stream));
+      kinetic_cotangent_kernel<<<dim3(n_t, batch), 256, 0, stream>>>(T, params->inertia, ys, n_t, obj->target_free_ids,
+                                                                    obj->n_target, obj->weights, gtmp);
+      a.g = gtmp;
+    }
     const int threads = pick_threads(T, opt ? opt->threads : 0);
     adjoint_kernel<<<batch, threads, smem, stream>>>(a);
+    if (gtmp) cudaFreeAsync(gtmp, stream);
   }
   cudaError_t e = cudaGetLastError();
   if (own_ws) cudaFreeAsync(a.scratch, stream);
   if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "adjoint_kernel launch failed: %s", cudaGetErrorString(e));
   return DFX_OK;
 }
+}  // namespace
+
+extern "C" {
+
+int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
+                int64_t ts_bstride, int n_t, const double* g_, double rtol, double atol, int64_t aug_size,
+                const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
+                void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!g_) return fail(DFX_ERR_INVALID, "NULL argument");
+  return adjoint_impl(t, params, batch, ys, ts, ts_bstride, n_t, g_, nullptr, rtol, atol, aug_size, opt, y0_bar, ts_bar, grads,
+                      stats, workspace, workspace_bytes, stream_);
+}
+
+int dfx_adjoint_kinetic(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
+                        int64_t ts_bstride, int n_t, const DfxKineticObjective* obj, double rtol, double atol,
+                        int64_t aug_size, const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads,
+                        DfxStats* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+  if (!obj) return fail(DFX_ERR_INVALID, "NULL argument");
+  return adjoint_impl(t, params, batch, ys, ts, ts_bstride, n_t, nullptr, obj, rtol, atol, aug_size, opt, y0_bar, ts_bar, grads,
+                      stats, workspace, workspace_bytes, stream_);
+}
+
+int dfx_kinetic_energy(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, int n_t,
+                       const DfxKineticObjective* obj, double* value, double* inertia_bar, void* stream_) {
+  if (!t || !params || !ys || !obj || !value || !params->inertia.ptr) return fail(DFX_ERR_INVALID, "NULL argument");
+  kinetic_energy_kernel<<<batch, 128, 0, (cudaStream_t)stream_>>>(t->dev, params->inertia, ys, n_t, obj->target_free_ids,
+                                                                 obj->n_target, value, inertia_bar);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "kinetic_energy launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
+
 
 }  // extern "C"
 

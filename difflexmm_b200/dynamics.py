@@ -211,6 +211,42 @@ class _OdeSolve(torch.autograd.Function):
         return (None, None, y0_bar, ts_bar, *out)
 
 
+class _KineticObjective(torch.autograd.Function):
+    """J[b] = kinetic energy of the target DOFs summed over the output times, evaluated on the device
+    (dfx_forward + dfx_kinetic_energy); backward = dfx_adjoint_kinetic, whose kernel forms the cotangent
+    dJ/dys = m v itself, plus the explicit dJ/d(inertia).  The trajectory never leaves libdfx buffers."""
+
+    @staticmethod
+    def forward(ctx, solver, meta, target_ids, y0, ts, *leaf_tensors):
+        names = meta["names"]
+        leaves = dict(zip(names, leaf_tensors))
+        ps = _abi.ParamSet(solver.spec, meta["batch"], leaves, meta["per_bond"], meta["damping_per_dof"])
+        ys, stats = solver.lib_forward(ps, y0, ts)
+        solver.last_forward_stats = stats
+        value, ibar = solver._lib.kinetic_energy(solver.handle, ps, ys, target_ids, want_inertia_bar=True)
+        ctx.solver, ctx.meta, ctx.ps, ctx.target_ids = solver, meta, ps, target_ids
+        ctx.save_for_backward(ys, ts, y0, ibar)
+        return value
+
+    @staticmethod
+    def backward(ctx, gJ):
+        solver, meta, ps = ctx.solver, ctx.meta, ctx.ps
+        ys, ts, y0, ibar = ctx.saved_tensors
+        y0_bar, ts_bar, grads, stats = solver._lib.adjoint_kinetic(
+            solver.handle, ps, ys, ts, ctx.target_ids, gJ, solver.rtol, solver.atol, meta["aug_size"], solver.options)
+        solver.last_adjoint_stats = stats
+        grads["inertia"] = grads["inertia"] + gJ[:, None] * ibar  # explicit dependence of J on the masses
+        out = []
+        for n in meta["names"]:
+            gl = grads[n]
+            out.append(gl if ps.batched[n] else gl.sum(0))
+        if y0.dim() == 1:
+            y0_bar = y0_bar.sum(0)
+        if ts.dim() == 1:
+            ts_bar = ts_bar.sum(0)
+        return (None, None, None, y0_bar, ts_bar, *out)
+
+
 class DynamicSolver:
     """Device-side solver for one topology: owns the libdfx handle, launches forward / adjoint."""
 
@@ -244,6 +280,15 @@ class DynamicSolver:
                     aug_size=int(aug_size))
         return _OdeSolve.apply(self, meta, y0.contiguous(), ts.contiguous(), *[leaves[n].contiguous() for n in names])
 
+    def odeint_kinetic(self, y0, ts, leaves, target_free_ids, batch, per_bond=(), damping_per_dof=False, aug_size=0):
+        """J[B] = sum_t sum_{f in target_free_ids} 1/2 m_f v_f(t)^2 of the solution of `odeint`; differentiable
+        (forward + objective + adjoint inside libdfx, see `_KineticObjective`)."""
+        names = [n for n in _abi.LEAF_NAMES if n in leaves]
+        meta = dict(names=names, batch=batch, per_bond=tuple(per_bond), damping_per_dof=damping_per_dof,
+                    aug_size=int(aug_size))
+        return _KineticObjective.apply(self, meta, target_free_ids, y0.contiguous(), ts.contiguous(),
+                                       *[leaves[n].contiguous() for n in names])
+
     # -- reference-level solve ---------------------------------------------------------------
     def solve(self, state0, timepoints, control_params: ControlParams, batch: Optional[int] = None, per_bond=()):
         spec, dev = self.spec, self.device
@@ -257,6 +302,29 @@ class DynamicSolver:
         ys = self.odeint(y0, ts, leaves, 1 if B is None else B, pb, dpd, aug_size)
         fields = self.expand_fields(ys, ts, control_params)
         return fields[0] if B is None else fields
+
+    def target_free_ids(self, target_blocks):
+        """positions, in the free-DOF vector, of the three DOFs of every target block (they must be free)."""
+        dofs = (np.asarray(target_blocks, dtype=np.int64)[:, None] * 3 + np.arange(3)[None]).reshape(-1)
+        pos = np.searchsorted(self.spec.free_dofs, dofs)
+        if np.any(pos >= self.spec.n_free) or np.any(np.asarray(self.spec.free_dofs)[np.minimum(pos, self.spec.n_free - 1)] != dofs):
+            raise ValueError("target blocks of the on-device kinetic objective must not have constrained DOFs")
+        return torch.as_tensor(pos.astype(np.int32), device=self.device)
+
+    def kinetic_objective(self, state0, timepoints, control_params: ControlParams, target_blocks,
+                          batch: Optional[int] = None, per_bond=()):
+        """Fused objective of the reference's focusing problems (`problems/quads_focusing.py:453-467`):
+        sum over output times of the kinetic energy of `target_blocks`.  -> (B,) tensor (scalar without batch),
+        differentiable w.r.t. control_params; forward, objective and adjoint all run inside libdfx."""
+        spec, dev = self.spec, self.device
+        leaves, pb, dpd, aug_size = lower_params(spec, self.drive, control_params, batch, dev, per_bond)
+        free = torch.as_tensor(spec.free_dofs, device=dev)
+        state0 = _as_t(state0, dev)
+        y0 = state0.reshape(*state0.shape[:-3], 2, spec.n_blocks * 3)[..., free]
+        y0 = y0.reshape(*y0.shape[:-2], 2 * spec.n_free)
+        J = self.odeint_kinetic(y0, _as_t(timepoints, dev), leaves, self.target_free_ids(target_blocks),
+                                1 if batch is None else batch, pb, dpd, aug_size)
+        return J[0] if batch is None else J
 
     def expand_fields(self, ys, ts, control_params):
         """(B, n_t, 2, n_blocks, 3) from the free-DOF solution (reference `dynamics.py:129-136,

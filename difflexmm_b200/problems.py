@@ -84,9 +84,14 @@ class _ProblemBase:
         return SolutionData(cp.geometrical_params.block_centroids, cp.geometrical_params.centroid_node_vectors,
                             self.geometry.bond_connectivity(), self.timepoints(s.device), fields)
 
-    def target_kinetic_energy(self, design, batch=None):
+    def target_kinetic_energy(self, design, batch=None, fused=False):
         """objective of the reference OptimizationProblem (`quads_focusing.py:453-467`): kinetic energy of the
-        target blocks summed over the output times."""
+        target blocks summed over the output times.  `fused=True` evaluates it inside libdfx
+        (`DynamicSolver.kinetic_objective`): no fields, no cotangent tensor."""
+        if fused:
+            s = self.solver
+            return s.kinetic_objective(self.state0(s.device), self.timepoints(s.device),
+                                       self.control_params(design, s.device), self.target_blocks(), batch=batch)
         sol = self.solve(design, batch)
         tb = torch.as_tensor(self.target_blocks(), device=sol.fields.device)
         inertia = compute_inertia(sol.centroid_node_vectors, torch.as_tensor(self.density, dtype=_F64,

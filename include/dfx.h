@@ -180,6 +180,29 @@ int dfx_adjoint(const DfxTopology* topo, const DfxParams* params, int batch,
                 double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
                 void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- objective on the device: the reference's target kinetic energy
+ *   J_b = w_b * sum_t sum_{f in target} 1/2 m_f v_f(t)^2     (problems/quads_focusing.py:453-467, energy.py:494-499)
+ * `target_free_ids` are indices into the free-DOF vector (the three DOFs of every target block; they must be free).
+ * dfx_kinetic_energy evaluates J (w = 1) and, optionally, its explicit derivative w.r.t. the reduced inertia;
+ * dfx_adjoint_kinetic is dfx_adjoint with the cotangent g = dJ/dys generated inside the kernel (g is never
+ * materialised: no 3.5 MB per design of cotangent traffic), weights[b] = dL/dJ_b. */
+typedef struct DfxKineticObjective {
+  const int32_t* target_free_ids; /* device, [n_target] */
+  int32_t n_target;
+  const double* weights;          /* device, [B], or NULL (= 1) */
+} DfxKineticObjective;
+
+int dfx_kinetic_energy(const DfxTopology* topo, const DfxParams* params, int batch, const double* ys, int n_t,
+                       const DfxKineticObjective* obj, double* value /*[B]*/, double* inertia_bar /*[B][n_free] or NULL*/,
+                       void* stream);
+
+int dfx_adjoint_kinetic(const DfxTopology* topo, const DfxParams* params, int batch,
+                        const double* ys, const double* ts, int64_t ts_bstride, int n_t,
+                        const DfxKineticObjective* obj, double rtol, double atol, int64_t aug_size,
+                        const DfxOptions* opt,
+                        double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
+                        void* workspace, size_t workspace_bytes, void* stream);
+
 /* fields[b][i][0][blk][dof] = displacement, fields[b][i][1][blk][dof] = velocity of every
  * block DOF (constrained DOFs follow the drive and its time derivative). */
 int dfx_expand_fields(const DfxTopology* topo, const DfxParams* params, int batch,

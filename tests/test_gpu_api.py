@@ -263,3 +263,39 @@ def test_status_flags_and_per_design_inputs():
     s2 = st2.numpy()
     assert (s2["status"] & _abi.DFX_STATUS_MAX_STEPS).all() and (s2["steps"] == 3).all()
     assert torch.isnan(ys2[:, 1:]).all() and torch.isfinite(ys2[:, 0]).all()
+
+
+@pytest.mark.parametrize("kernel", ["fast", "generic"])
+def test_fused_kinetic_objective_equals_the_unfused_path(kernel, monkeypatch):
+    """dfx_forward + dfx_kinetic_energy + dfx_adjoint_kinetic (cotangent formed inside the adjoint kernel)
+    against the torch objective on the expanded fields + dfx_adjoint with a materialised cotangent; batch of designs
+    with non-uniform upstream weights; the generic adjoint kernel takes the cotangent-materialising route."""
+    if kernel == "generic":
+        monkeypatch.setenv("DFX_ADJOINT_KERNEL", "generic")
+        monkeypatch.setenv("DFX_FORWARD_KERNEL", "generic")
+    P = _problem()
+    P.setup()
+    B = 3
+    hs0, vs0 = P.random_ensemble(B, noise=0.05)
+    w = torch.tensor([1.0, -0.5, 2.0], dtype=torch.float64, device="cuda")
+    res = []
+    for fused in (False, True):
+        hs, vs = hs0.clone().requires_grad_(True), vs0.clone().requires_grad_(True)
+        J = P.target_kinetic_energy((hs, vs), batch=B, fused=fused)
+        assert J.shape == (B,)
+        (J * w.to(J.device)).sum().backward()
+        assert (P.solver.last_adjoint_stats.numpy()["status"] == 0).all()
+        res.append((J.detach().cpu(), hs.grad.cpu(), vs.grad.cpu()))
+    (J0, gh0, gv0), (J1, gh1, gv1) = res
+    assert torch.allclose(J0, J1, rtol=1e-12, atol=0)
+    assert rel_l2(gh1.numpy(), gh0.numpy()) <= 1e-10 and rel_l2(gv1.numpy(), gv0.numpy()) <= 1e-10
+    # unbatched call returns a scalar
+    J_s = P.target_kinetic_energy((hs0[0], vs0[0]), fused=True)
+    assert J_s.dim() == 0 and abs(J_s.item() - J0[0].item()) <= 1e-12 * abs(J0[0].item())
+
+
+def test_fused_objective_rejects_constrained_targets():
+    P = _problem()
+    s = P.setup()
+    with pytest.raises(ValueError):
+        s.target_free_ids(np.array([int(np.asarray(P.spec.constrained_dofs)[0]) // 3]))

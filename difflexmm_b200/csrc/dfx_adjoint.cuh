@@ -112,13 +112,15 @@ __device__ __forceinline__ void quad_update(const QuadCtx& c, int idx, double va
 
 // scalar leaves: per-warp partial sums of the same linear recurrences (combined once per step)
 struct ScalCtx {
-  double *wk1, *wk7, *wsol, *werr, *wmid;  // [NSCAL][32]
+  double *wk1, *wk7, *wsol, *werr, *wmid;  // [NSCAL][scw]
+  int scw;    // warps per design (SCW for one CTA, SCW * cluster size for a cluster)
+  int gwarp;  // this thread's warp index within the design
 };
 __device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, int which, double partial) {
   // most warps contribute nothing to the sparse scalars (contact, drive, t0): skip their shuffles
   const double v = __any_sync(0xffffffffu, partial != 0.0) ? warp_sum(partial) : 0.0;
   if ((threadIdx.x & 31) != 0) return;
-  const int idx = which * SCW + (threadIdx.x >> 5);
+  const int idx = which * s.scw + s.gwarp;
   switch (c.mode) {
     case 0: s.wk1[idx] = v; break;
     case 7: s.wk7[idx] = v; break;
@@ -141,23 +143,32 @@ __device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, 
   }
 }
 
-__global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
+// CL = 0: one CTA per design.  CL = 1: one thread-block cluster per design (see forward_kernel).
+template <int CL>
+__global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__ AdjArgs a) {
   extern __shared__ double smem[];
   const DevTopo& T = a.topo;
   const Tableau& tab = a.tab;
-  const int design = blockIdx.x;
-  const int tid = threadIdx.x, nthr = blockDim.x, nwarp = (nthr + 31) >> 5;
+  const int crank = CL ? (int)cluster_ctarank() : 0, ncta = CL ? (int)cluster_nctarank() : 1;
+  const int design = blockIdx.x / ncta;
+  const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x, nwarp = (nthr + 31) >> 5;
+  const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, cnwarp = (blockDim.x + 31) >> 5;
+  const int scw = SCW * ncta;
+  int cpar = 0;
   const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;
   const int NQ = a.nq;
   double* red = smem;
   double* scratch = a.scratch ? a.scratch + (long long)design * a.scratch_per_design : nullptr;
+  double* cred = scratch;  // CL: cluster-sum partials at the start of the scratch
+  auto SYNC = [&]() { if (CL) cluster_sync_all(); else __syncthreads(); };
+  auto SUM = [&](double v) { return CL ? cluster_sum(v, red, cred, crank, ncta, cpar) : block_sum(v, red); };
   auto P = [&](int i) -> double* {
     const long long o = a.place.off[i];
     return o >= 0 ? smem + o : scratch + (-(o + 1));
   };
   double *Us = P(AA_US), *Ws = P(AA_WS), *Vs = P(AA_VS), *Lus = P(AA_LUS), *Lvs = P(AA_LVS);
   double *Fs = P(AA_FS), *Hs = P(AA_HS), *Gs = P(AA_GS), *Ga = T.contact ? P(AA_GA) : nullptr;
-  double* SC = P(AA_SC);  // [2][NSCAL] q0,qnew + [5][NSCAL][32] per-warp partials
+  double* SC = P(AA_SC);  // [2][NSCAL] q0,qnew + [5][NSCAL][scw] per-warp partials
   double *invm = P(AA_INVM), *cd = P(AA_CD);
   double *u0 = P(AA_U0), *v0 = P(AA_V0), *lu0 = P(AA_LU0), *lv0 = P(AA_LV0);
   double *kv = P(AA_KV), *klu = P(AA_KLU), *klv = P(AA_KLV);
@@ -169,8 +180,9 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
   double* Sq0 = SC;
   double* Sqnew = SC + NSCAL;
   ScalCtx sc;
-  sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * SCW; sc.wsol = sc.wk7 + NSCAL * SCW;
-  sc.werr = sc.wsol + NSCAL * SCW; sc.wmid = sc.werr + NSCAL * SCW;
+  sc.scw = scw; sc.gwarp = tid >> 5;
+  sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * scw; sc.wsol = sc.wk7 + NSCAL * scw;
+  sc.werr = sc.wsol + NSCAL * scw; sc.wmid = sc.werr + NSCAL * scw;
 
   const double* g_ks = leaf_ptr(a.p.k_stretch, design);
   const double* g_ksh = leaf_ptr(a.p.k_shear, design);
@@ -185,11 +197,11 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
   const bool damp_pd = a.p.damping_per_dof != 0, has_damp = T.n_damped > 0 && a.p.damping.ptr != nullptr;
   const int ndp = T.n_drive_params;
 
-  setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd);
+  setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd, tid, nthr);
   for (int i = tid; i < 3 * NN; i += nthr) { Fs[i] = 0.0; Hs[i] = 0.0; }
   for (int i = tid; i < 2 * NN; i += nthr) { Gs[i] = 0.0; if (Ga) Ga[i] = 0.0; }
   for (int i = tid; i < NQ; i += nthr) { qc.q0[i] = 0.0; qc.k1[i] = 0.0; qc.k7[i] = 0.0; qc.qnew[i] = 0.0; qc.asol[i] = 0.0; qc.aerr[i] = 0.0; qc.amid[i] = 0.0; }
-  for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * SCW; i += nthr) SC[i] = 0.0;
+  for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * scw; i += nthr) SC[i] = 0.0;
   double cmin = 0, ccut = 0, ckc = 0;
   if (T.contact) { cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
   // y_bar = g[-1]
@@ -199,12 +211,12 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
     lu0[e] = f >= 0 ? gg[(long long)(a.n_t - 1) * 2 * nf + f] : 0.0;
     lv0[e] = f >= 0 ? gg[(long long)(a.n_t - 1) * 2 * nf + nf + f] : 0.0;
   }
-  __syncthreads();
+  SYNC();
 
   // ---- augmented RHS, phases B and C.  kidx: which k-slot (0..6) receives the dynamic derivatives
   auto aug_BC = [&](double time, double* kv_out, double* klu_out, double* klv_out) {
     const bool want_q = qc.mode != 1;
-    __syncthreads();
+    SYNC();
     double p_ks = 0, p_ksh = 0, p_kr = 0, p_c0 = 0, p_c1 = 0, p_c2 = 0, probe = 0;
     for (int b = tid; b < NBONDS; b += nthr) {
       const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
@@ -251,7 +263,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
       if (!kr_pb) scal_update(qc, sc, SC_KR, p_kr);
       if (T.contact) { scal_update(qc, sc, SC_CONTACT, p_c0); scal_update(qc, sc, SC_CONTACT + 1, p_c1); scal_update(qc, sc, SC_CONTACT + 2, p_c2); }
     }
-    __syncthreads();
+    SYNC();
     double ls = 0.0, lsd = 0.0;
     if (T.load_kind != DFX_LOAD_NONE) load_eval(T.load_kind, time, T.load_consts, ls, lsd);
     double p_t0 = 0, p_damp = 0, p_dr[DFX_MAX_DRIVE_PARAMS] = {0, 0, 0, 0, 0};
@@ -340,11 +352,12 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
     }
   };
 
-  // total of a scalar leaf's per-warp partials
+  // total of a scalar leaf's per-warp partials; evaluated by a whole warp (lanes stride over the design's warps).
+  // Scalar leaf `which` is owned by warp (which % cnwarp) of the first CTA; its lane 0 holds Sq0 / Sqnew[which].
   auto wtotal = [&](const double* wa, int which) {
     double s = 0.0;
-    for (int w = 0; w < nwarp; ++w) s += wa[which * SCW + w];
-    return s;
+    for (int w = lane; w < nwarp; w += 32) s += wa[which * scw + w];
+    return warp_sum(s);
   };
 
   long long n_steps = 0, n_acc = 0, n_rhs = 0;
@@ -376,12 +389,12 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
       const int f = T.free_of_dof[3 * blk + j];
       pt += v0[e] * gi[f] - kv[e] * gi[nf + f];
     }
-    const double t_bar = block_sum(pt, red);
+    const double t_bar = SUM(pt);
     if (tid == 0) {
       if (a.ts_bar) a.ts_bar[(long long)design * a.n_t + i] = t_bar;
       Sq0[SC_T0] -= t_bar;
     }
-    __syncthreads();
+    SYNC();
     // ---- initial_step_size over the whole augmented vector ---------------------------------------
     {
       double sd0 = 0, sd1 = 0;
@@ -399,13 +412,16 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
         const double a0 = qc.q0[q] / s, b0 = qc.k1[q] / s;
         sd0 += a0 * a0; sd1 += b0 * b0;
       }
-      if (tid < NSCAL) {
-        const double s = atol + fabs(Sq0[tid]) * rtol;
-        const double a0 = Sq0[tid] / s, b0 = wtotal(sc.wk1, tid) / s;
-        sd0 += a0 * a0; sd1 += b0 * b0;
+      if (crank == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) {
+        const double k1 = wtotal(sc.wk1, w);
+        if (lane == 0) {
+          const double s = atol + fabs(Sq0[w]) * rtol;
+          const double a0 = Sq0[w] / s, b0 = k1 / s;
+          sd0 += a0 * a0; sd1 += b0 * b0;
+        }
       }
-      const double d0 = sqrt(block_sum(sd0, red));
-      const double d1 = sqrt(block_sum(sd1, red));
+      const double d0 = sqrt(SUM(sd0));
+      const double d1 = sqrt(SUM(sd1));
       const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
       for (int e = tid; e < ND; e += nthr)
         put_stage(e, u0[e] - h0 * v0[e], v0[e] + h0 * kv[e], lu0[e] + h0 * klu[e], lv0[e] + h0 * klv[e], -(s0 + h0));
@@ -420,13 +436,16 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
         const double b2 = (klu[ND + e] - klu[e]) / slu, b3 = (klv[ND + e] - klv[e]) / slv;
         sd2 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
       }
-      __syncthreads();  // per-warp probe partials (wk7) complete
-      if (tid < NSCAL) {
-        const double s = atol + fabs(Sq0[tid]) * rtol;
-        const double b0 = (wtotal(sc.wk7, tid) - wtotal(sc.wk1, tid)) / s;
-        sd2 += b0 * b0;
+      SYNC();  // per-warp probe partials (wk7) complete
+      if (crank == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) {
+        const double k7 = wtotal(sc.wk7, w), k1 = wtotal(sc.wk1, w);
+        if (lane == 0) {
+          const double s = atol + fabs(Sq0[w]) * rtol;
+          const double b0 = (k7 - k1) / s;
+          sd2 += b0 * b0;
+        }
       }
-      const double d2 = sqrt(block_sum(sd2, red)) / h0;
+      const double d2 = sqrt(SUM(sd2)) / h0;
       double h1;
       if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
       else h1 = pow(0.01 / (a.init_step_variant == 0 ? d1 + d2 : fmax(d1, d2)), 0.2);
@@ -486,15 +505,19 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
         const double r3 = elv / (atol + rtol * fmax(fabs(lv0[e]), fabs(Lvs[e])));
         se += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
       }
-      __syncthreads();  // per-warp scalar partials of the last stage complete
-      if (tid < NSCAL) {
-        const double q0 = Sq0[tid], k1 = wtotal(sc.wk1, tid), k7 = wtotal(sc.wk7, tid);
-        const double q1 = q0 + h * wtotal(sc.wsol, tid);
-        const double r = h * wtotal(sc.werr, tid) / (atol + rtol * fmax(fabs(q0), fabs(q1)));
-        se += r * r;
-        Sqnew[tid] = qc.crossing ? interp_eval(q0, q1, q0 + h * wtotal(sc.wmid, tid), h * k1, h * k7, qc.x) : q1;
+      SYNC();  // per-warp scalar partials of the last stage complete
+      if (crank == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) {
+        const double k1 = wtotal(sc.wk1, w), k7 = wtotal(sc.wk7, w);
+        const double tsol = wtotal(sc.wsol, w), terr = wtotal(sc.werr, w), tmid = wtotal(sc.wmid, w);
+        if (lane == 0) {
+          const double q0 = Sq0[w];
+          const double q1 = q0 + h * tsol;
+          const double r = h * terr / (atol + rtol * fmax(fabs(q0), fabs(q1)));
+          se += r * r;
+          Sqnew[w] = qc.crossing ? interp_eval(q0, q1, q0 + h * tmid, h * k1, h * k7, qc.x) : q1;
+        }
       }
-      const double ratio = sqrt(block_sum(se, red) * inv_n);
+      const double ratio = sqrt(SUM(se) * inv_n);
       ++n_steps; ++istep;
       if (!isfinite(ratio)) { status |= DFX_STATUS_NONFINITE; break; }
       if (ratio <= 1.0) {
@@ -523,22 +546,22 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const AdjArgs a) {
             u0[e] = Us[e]; v0[e] = Vs[e]; lu0[e] = Lus[e]; lv0[e] = Lvs[e];
             kv[e] = kv[6 * ND + e]; klu[e] = klu[6 * ND + e]; klv[e] = klv[6 * ND + e];
           }
-          if (tid < NSCAL) for (int w = 0; w < nwarp; ++w) sc.wk1[tid * SCW + w] = sc.wk7[tid * SCW + w];
+          if (lane == 0) for (int w = 0; w < NSCAL; ++w) sc.wk1[w * scw + sc.gwarp] = sc.wk7[w * scw + sc.gwarp];
           double* tmp = qc.k1; qc.k1 = qc.k7; qc.k7 = tmp;
         }
-        if (tid < NSCAL) Sq0[tid] = Sqnew[tid];
+        if (crank == 0 && lane == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) Sq0[w] = Sqnew[w];
         double* tmp = qc.q0; qc.q0 = qc.qnew; qc.qnew = tmp;
         s_cur = s_new;
       }
       const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
       const double factor = fmin(10.0, fmax(pow(ratio, -0.2) * 0.9, dfactor));
       h = (ratio == 0.0) ? h * 10.0 : h * factor;
-      __syncthreads();
+      SYNC();
     }
   }
 
   // ---- outputs ---------------------------------------------------------------------------------------
-  __syncthreads();
+  SYNC();
   const double nanv = nan("");
   const bool bad = status != 0;
   for (int e = tid; e < ND; e += nthr) {

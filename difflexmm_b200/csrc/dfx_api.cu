@@ -67,10 +67,12 @@ int n_drive_params_of(int kind) {
 }
 
 // greedy placement: arrays in priority order go to shared memory while they fit
+// cluster launches (cluster > 1): everything goes to the global scratch, whose first 2 * kMaxCluster doubles hold
+// the cluster-sum partials
 template <int N>
-void plan(const long long (&sizes)[N], long long* off, size_t* smem_bytes, long long* scratch_doubles) {
-  long long s = kRedDoubles, g = 0;
-  const long long cap = (long long)(kSmemBytes / sizeof(double));
+void plan(const long long (&sizes)[N], long long* off, size_t* smem_bytes, long long* scratch_doubles, int cluster = 1) {
+  long long s = kRedDoubles, g = cluster > 1 ? 2 * kMaxCluster : 0;
+  const long long cap = cluster > 1 ? s : (long long)(kSmemBytes / sizeof(double));
   for (int i = 0; i < N; ++i) {
     const long long n = (sizes[i] + 1) & ~1LL;  // keep 16-byte alignment
     if (n == 0) { off[i] = 0; continue; }
@@ -104,11 +106,11 @@ QuadLayout quad_layout(const DevTopo& T, const DfxParams& p) {
   return q;
 }
 
-void adjoint_sizes(const DevTopo& T, const QuadLayout& q, long long (&sz)[AA_COUNT]) {
+void adjoint_sizes(const DevTopo& T, const QuadLayout& q, long long (&sz)[AA_COUNT], int cluster = 1) {
   const long long NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds;
   sz[AA_US] = 5 * NB; sz[AA_WS] = 3 * NB; sz[AA_VS] = 3 * NB; sz[AA_LUS] = 3 * NB; sz[AA_LVS] = 3 * NB;
   sz[AA_FS] = 3 * NN; sz[AA_HS] = 3 * NN; sz[AA_GS] = 2 * NN; sz[AA_GA] = T.contact ? 2 * NN : 0;
-  sz[AA_SC] = 2 * NSCAL + 5 * NSCAL * SCW;
+  sz[AA_SC] = 2 * NSCAL + 5 * NSCAL * SCW * cluster;
   sz[AA_INVM] = 3 * NB; sz[AA_CD] = 3 * NB;
   sz[AA_U0] = 3 * NB; sz[AA_V0] = 3 * NB; sz[AA_LU0] = 3 * NB; sz[AA_LV0] = 3 * NB;
   sz[AA_KV] = 21 * NB; sz[AA_KLU] = 21 * NB; sz[AA_KLV] = 21 * NB;
@@ -133,6 +135,43 @@ int pick_threads(const DevTopo& T, int requested) {
   if (t < 32) t = 32;
   if (t > 512) t = 512;
   return t;
+}
+
+// Cluster size of the generic kernels: lattices with many bonds per thread are spread over a thread-block cluster
+// when the batch alone cannot fill the GPU.  DFX_CLUSTER=1|2|4|8|16 overrides.
+int pick_cluster(const DevTopo& T, int batch, int sm_count) {
+  int cl = 1;
+  if (const char* e = std::getenv("DFX_CLUSTER")) {
+    cl = std::atoi(e);
+  } else {
+    int by_size = 1;
+    while (by_size < kMaxCluster && (long long)by_size * 1024 < T.n_bonds) by_size *= 2;
+    int by_batch = 1;
+    while (by_batch * 2 * (long long)batch <= sm_count && by_batch < kMaxCluster) by_batch *= 2;
+    cl = by_size < by_batch ? by_size : by_batch;
+  }
+  if (cl < 1) cl = 1;
+  if (cl > kMaxCluster) cl = kMaxCluster;
+  while (cl & (cl - 1)) cl &= cl - 1;  // power of two
+  return cl;
+}
+
+template <class Kernel, class Args>
+cudaError_t launch_cluster(Kernel kernel, int batch, int cluster, int threads, size_t smem, cudaStream_t stream, const Args& args) {
+  if (cluster > 8) {
+    cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeNonPortableClusterSizeAllowed, 1);
+    if (e != cudaSuccess) return e;
+  }
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)batch * cluster, 1, 1);
+  cfg.blockDim = dim3(threads, 1, 1);
+  cfg.dynamicSmemBytes = smem;
+  cfg.stream = stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = cluster; attr[0].val.clusterDim.y = 1; attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr; cfg.numAttrs = 1;
+  return cudaLaunchKernelEx(&cfg, kernel, args);
 }
 
 // launch plan of the fast adjoint kernel (dfx_adjoint2.cuh); ok=false -> use the generic kernel
@@ -307,14 +346,14 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   D.table.t = dtt; D.table.v = dtv; D.table.n = (int)tab_t.size();
   t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm, dnb, dtt, dtv};
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
-  cudaFuncSetAttribute(forward_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaFuncSetAttribute(forward_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   cudaFuncSetAttribute(forward2_kernel<42, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes / 2 - 1024);
   cudaFuncSetAttribute(forward2_kernel<0, 384, 2>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes / 2 - 1024);
   cudaFuncSetAttribute(forward2_kernel<42, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(forward2_kernel<0, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(forward2_kernel<42, 384, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(forward2_kernel<0, 384, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
-  cudaFuncSetAttribute(adjoint_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
+  cudaFuncSetAttribute(adjoint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   cudaFuncSetAttribute(adjoint2_kernel<84, 32, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(adjoint2_kernel<84, -1, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(adjoint2_kernel<64, -1, 512>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
@@ -339,9 +378,9 @@ size_t dfx_forward_workspace_bytes(const DfxTopology* t, int batch) {
   if (!t) return 0;
   long long sz[FA_COUNT], off[FA_COUNT], g;
   size_t smem;
-  forward_sizes(t->dev, sz);
-  plan(sz, off, &smem, &g);
   FastFwdPlan f = plan_fast_forward(t->dev);
+  forward_sizes(t->dev, sz);
+  plan(sz, off, &smem, &g, f.ok ? 1 : pick_cluster(t->dev, batch, t->sm_count));
   const long long fast = f.ok ? (long long)F_NSLOT * f.threads + 32 : 0;
   if (fast > g) g = fast;
   return (size_t)g * sizeof(double) * (size_t)batch;
@@ -357,9 +396,10 @@ size_t dfx_adjoint_workspace_bytes(const DfxTopology* t, int batch) {
   QuadLayout q = quad_layout(t->dev, p);
   long long sz[AA_COUNT], off[AA_COUNT], g;
   size_t smem;
-  adjoint_sizes(t->dev, q, sz);
-  plan(sz, off, &smem, &g);
   FastPlan f = plan_fast_adjoint(t->dev);
+  const int cluster = f.ok ? 1 : pick_cluster(t->dev, batch, t->sm_count);
+  adjoint_sizes(t->dev, q, sz, cluster);
+  plan(sz, off, &smem, &g, cluster);
   // worst case of the two kernels (the fast one assumes S_TOTAL slots with no TMEM)
   long long fast = f.ok ? (long long)(S_NCONST - f.ns + (NQA + 1) * NE) * f.threads + 32 : 0;
   if (fast > g) g = fast;
@@ -379,14 +419,15 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
   a.topo = t->dev; a.p = *params; a.tab = make_tableau();
   long long sz[FA_COUNT], g;
   size_t smem;
+  const FastFwdPlan fp = plan_fast_forward(t->dev);
+  const int cluster = fp.ok ? 1 : pick_cluster(t->dev, batch, t->sm_count);
   forward_sizes(t->dev, sz);
-  plan(sz, a.place.off, &smem, &g);
+  plan(sz, a.place.off, &smem, &g, cluster);
   a.y0 = y0; a.y0_bstride = y0_bstride; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t;
   a.rtol = rtol; a.atol = atol;
   a.init_step_variant = opt ? opt->init_step_variant : 0;
   a.max_steps = (opt && opt->max_steps > 0) ? opt->max_steps : (1LL << 40);
   a.ys = ys; a.stats = stats;
-  const FastFwdPlan fp = plan_fast_forward(t->dev);
   if (fp.ok) g = fp.scratch;
   a.scratch_per_design = g;
   bool own_ws = false;
@@ -414,7 +455,12 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
     else forward2_kernel<0, 512, 1><<<batch, 512, fp.smem, stream>>>(A2);
   } else {
     const int threads = pick_threads(t->dev, opt ? opt->threads : 0);
-    forward_kernel<<<batch, threads, smem, stream>>>(a);
+    if (cluster > 1) {
+      cudaError_t le = launch_cluster(forward_kernel<1>, batch, cluster, 512, smem, stream, a);
+      if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "forward_kernel cluster launch (%d CTAs) failed: %s", cluster, cudaGetErrorString(le)); }
+    } else {
+      forward_kernel<0><<<batch, threads, smem, stream>>>(a);
+    }
   }
   cudaError_t e = cudaGetLastError();
   if (own_ws) cudaFreeAsync(a.scratch, stream);
@@ -476,8 +522,10 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   a.qo_damp = q.qo_damp; a.qo_inertia = q.qo_inertia; a.nq = q.nq;
   long long sz[AA_COUNT], g;
   size_t smem;
-  adjoint_sizes(T, q, sz);
-  plan(sz, a.place.off, &smem, &g);
+  const FastPlan fp = plan_fast_adjoint(T);
+  const int cluster = fp.ok ? 1 : pick_cluster(T, batch, t->sm_count);
+  adjoint_sizes(T, q, sz, cluster);
+  plan(sz, a.place.off, &smem, &g, cluster);
   a.ys = ys; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t; a.g = g_;
   if (obj) { a.obj_ids = obj->target_free_ids; a.obj_n = obj->n_target; a.obj_w = obj->weights; }
   a.rtol = rtol; a.atol = atol;
@@ -497,7 +545,6 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   a.y0_bar = y0_bar; a.ts_bar = ts_bar;
   if (grads) a.grads = *grads;
   a.stats = stats;
-  const FastPlan fp = plan_fast_adjoint(T);
   if (fp.ok) g = fp.scratch;
   a.scratch_per_design = g;
   bool own_ws = false;
@@ -536,8 +583,11 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
       a.g = gtmp;
     }
     const int threads = pick_threads(T, opt ? opt->threads : 0);
-    adjoint_kernel<<<batch, threads, smem, stream>>>(a);
+    cudaError_t le = cudaSuccess;
+    if (cluster > 1) le = launch_cluster(adjoint_kernel<1>, batch, cluster, 512, smem, stream, a);
+    else adjoint_kernel<0><<<batch, threads, smem, stream>>>(a);
     if (gtmp) cudaFreeAsync(gtmp, stream);
+    if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "adjoint_kernel cluster launch (%d CTAs) failed: %s", cluster, cudaGetErrorString(le)); }
   }
   cudaError_t e = cudaGetLastError();
   if (own_ws) cudaFreeAsync(a.scratch, stream);

@@ -423,4 +423,35 @@ __device__ __forceinline__ double block_sum(double v, double* red) {
   return red[32];
 }
 
+// ------------------------------------------------------------------------------------------
+// thread-block clusters: one lattice spread over the CTAs of a cluster (large lattices, small batches).
+// barrier.cluster arrive.release / wait.acquire orders global-memory traffic between the CTAs
+// (ptxas adds the L1 invalidate), so stage arrays exchanged through the L2-resident scratch are coherent.
+// ------------------------------------------------------------------------------------------
+__device__ __forceinline__ unsigned cluster_ctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ unsigned cluster_nctarank() {
+  unsigned r;
+  asm volatile("mov.u32 %0, %%cluster_nctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+constexpr int kMaxCluster = 16;
+// Sum over every thread of the cluster; identical (bitwise) on all CTAs, so control flow stays uniform.
+// cred: [2][kMaxCluster] doubles in the design's global scratch; `parity` alternates between calls.
+__device__ __forceinline__ double cluster_sum(double v, double* red, double* cred, int rank, int ncta, int& parity) {
+  const double part = block_sum(v, red);
+  if (threadIdx.x == 0) cred[parity * kMaxCluster + rank] = part;
+  cluster_sync_all();
+  double s = 0.0;
+  for (int r = 0; r < ncta; ++r) s += cred[parity * kMaxCluster + r];
+  parity ^= 1;
+  return s;
+}
+
 }  // namespace dfx

@@ -68,20 +68,20 @@ __device__ __forceinline__ const double* leaf_ptr(const L& l, int b) {
 // damping coefficient per DOF in component-major layout e = dof*NB + block)
 __device__ inline void setup_design_constants(const DevTopo& T, const DfxParams& p, int design, double* bondc /*[4][nbonds]*/,
                                               double* cnv /*[2][nnodes] or null*/, double* alpha /*[2][nnodes] or null*/,
-                                              double* invm, double* cd) {
+                                              double* invm, double* cd, int tid, int nthr) {
   const int NB = T.n_blocks, NN = T.n_nodes, npb = T.n_npb;
   const double* g_cnv = leaf_ptr(p.centroid_node_vectors, design);
   const double* g_ref = leaf_ptr(p.reference_vector, design);
   const double* g_inertia = leaf_ptr(p.inertia, design);
   const double* g_damp = leaf_ptr(p.damping, design);
-  for (int b = threadIdx.x; b < T.n_bonds; b += blockDim.x) {
+  for (int b = tid; b < T.n_bonds; b += nthr) {
     const double rx = g_ref[2 * b], ry = g_ref[2 * b + 1];
     bondc[b] = rx;
     bondc[T.n_bonds + b] = ry;
     bondc[2 * T.n_bonds + b] = sqrt(rx * rx + ry * ry);
     bondc[3 * T.n_bonds + b] = 1.0 / bondc[2 * T.n_bonds + b];
   }
-  for (int n = threadIdx.x; n < NN; n += blockDim.x) {
+  for (int n = tid; n < NN; n += nthr) {
     const double rx = g_cnv[2 * n], ry = g_cnv[2 * n + 1];
     if (cnv) { cnv[n] = rx; cnv[NN + n] = ry; }
     if (alpha) {
@@ -91,7 +91,7 @@ __device__ inline void setup_design_constants(const DevTopo& T, const DfxParams&
       alpha[NN + n] = atan2(g_cnv[2 * np + 1] - ry, g_cnv[2 * np] - rx);  // previous edge
     }
   }
-  for (int e = threadIdx.x; e < 3 * NB; e += blockDim.x) {
+  for (int e = tid; e < 3 * NB; e += nthr) {
     const int j = e / NB, blk = e - j * NB, dof = 3 * blk + j;
     const int f = T.free_of_dof[dof];
     invm[e] = f >= 0 ? 1.0 / g_inertia[f] : 0.0;
@@ -100,14 +100,23 @@ __device__ inline void setup_design_constants(const DevTopo& T, const DfxParams&
   }
 }
 
-__global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
+// CL = 0: one CTA per design.  CL = 1: one thread-block cluster per design -- the element loops are strided over
+// all threads of the cluster, every array lives in the design's global scratch (L2), CTA barriers become cluster
+// barriers and the norms are summed over the cluster (cfg5-sized lattices).
+template <int CL>
+__global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ double smem[];
   const DevTopo& T = a.topo;
-  const int design = blockIdx.x;
-  const int tid = threadIdx.x, nthr = blockDim.x;
+  const int crank = CL ? (int)cluster_ctarank() : 0, ncta = CL ? (int)cluster_nctarank() : 1;
+  const int design = blockIdx.x / ncta;
+  const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
+  int cpar = 0;
   const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb;
   double* red = smem;  // 40 doubles reserved at the start of shared memory
   double* scratch = a.scratch ? a.scratch + (long long)design * a.scratch_per_design : nullptr;
+  double* cred = scratch;  // CL: the first 2 * kMaxCluster doubles of the scratch hold the cluster-sum partials
+  auto SYNC = [&]() { if (CL) cluster_sync_all(); else __syncthreads(); };
+  auto SUM = [&](double v) { return CL ? cluster_sum(v, red, cred, crank, ncta, cpar) : block_sum(v, red); };
   double* Us = placed(a.place, FA_US, smem, scratch);      // [5][NB]  x, y, theta, sin, cos
   double* Vs = placed(a.place, FA_VS, smem, scratch);      // [3][NB]  stage velocity
   double* Fs = placed(a.place, FA_FS, smem, scratch);      // [3][NN]  node force slots
@@ -132,7 +141,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
   const double rtol = a.rtol, atol = a.atol;
   const Tableau& tab = a.tab;
 
-  setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd);
+  setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd, tid, nthr);
   for (int i = tid; i < 3 * NN; i += nthr) Fs[i] = 0.0;
   for (int e = tid; e < ND; e += nthr) {
     const int j = e / NB, blk = e - j * NB;
@@ -143,11 +152,11 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
   }
   double cmin = 0, ccut = 0, ckc = 0;
   if (T.contact) { cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
-  __syncthreads();
+  SYNC();
 
   // ---- RHS phases B and C (phase A is written by the caller into Us / Vs) ---------------------
   auto rhs_BC = [&](double tstage, double* kout) {
-    __syncthreads();
+    SYNC();
     for (int b = tid; b < NBONDS; b += nthr) {
       const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
       BlockState<double> s1, s2;
@@ -170,7 +179,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
       Fs[nd.x] = -o.f1[0]; Fs[NN + nd.x] = -o.f1[1]; Fs[2 * NN + nd.x] = -o.f1[2];
       Fs[nd.y] = -o.f2[0]; Fs[NN + nd.y] = -o.f2[1]; Fs[2 * NN + nd.y] = -o.f2[2];
     }
-    __syncthreads();
+    SYNC();
     double ls = 0.0, lsd;
     if (T.load_kind != DFX_LOAD_NONE) load_eval(T.load_kind, tstage, T.load_consts, ls, lsd);
     for (int e = tid; e < ND; e += nthr) {
@@ -226,8 +235,8 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
       sd0 += a0 * a0 + a1 * a1;
       sd1 += b0 * b0 + b1 * b1;
     }
-    const double d0 = sqrt(block_sum(sd0, red));
-    const double d1 = sqrt(block_sum(sd1, red));
+    const double d0 = sqrt(SUM(sd0));
+    const double d1 = sqrt(SUM(sd1));
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
     for (int e = tid; e < ND; e += nthr) put_stage(e, u0[e] + h0 * v0[e], v0[e] + h0 * kv[e], t + h0);
     rhs_BC(t + h0, kv + ND);
@@ -239,7 +248,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
       const double b0 = (Vs[e] - v0[e]) / su, b1 = (kv[ND + e] - kv[e]) / sv;
       sd2 += b0 * b0 + b1 * b1;
     }
-    const double d2 = sqrt(block_sum(sd2, red)) / h0;
+    const double d2 = sqrt(SUM(sd2)) / h0;
     double h1;
     if (d1 <= 1e-15 && d2 <= 1e-15) h1 = fmax(1e-6, h0 * 1e-3);
     else h1 = pow(0.01 / (a.init_step_variant == 0 ? d1 + d2 : fmax(d1, d2)), 0.2);
@@ -290,7 +299,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const FwdArgs a) {
         const double ru = eu / tu, rv = ev / tv;
         se += ru * ru + rv * rv;
       }
-      const double ratio = sqrt(block_sum(se, red) * inv_n);
+      const double ratio = sqrt(SUM(se) * inv_n);
       ++n_steps; ++istep;
       if (!isfinite(ratio)) { status |= DFX_STATUS_NONFINITE; break; }
       if (ratio <= 1.0) {

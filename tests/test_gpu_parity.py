@@ -32,15 +32,23 @@ def _significant(ref, key):
     return np.abs(ref[key]).max() > 1e-9
 
 
-@pytest.fixture(params=["fast_tmem", "notmem", "generic"])
-def forward_kernel_mode(request, monkeypatch):
-    """the three forward code paths of libdfx (fast kernel with TMEM-resident stage history, fast kernel without
-    TMEM, generic kernel for any lattice size)"""
-    if request.param == "fast_tmem":
-        monkeypatch.delenv("DFX_FORWARD_KERNEL", raising=False)
+def _kernel_mode(monkeypatch, var, mode):
+    monkeypatch.setenv("DFX_CLUSTER", "1")
+    if mode == "fast_tmem":
+        monkeypatch.delenv(var, raising=False)
+    elif mode.startswith("cluster"):
+        monkeypatch.setenv(var, "generic")
+        monkeypatch.setenv("DFX_CLUSTER", mode[len("cluster"):])
     else:
-        monkeypatch.setenv("DFX_FORWARD_KERNEL", request.param)
-    return request.param
+        monkeypatch.setenv(var, mode)
+    return mode
+
+
+@pytest.fixture(params=["fast_tmem", "notmem", "generic", "cluster4", "cluster16"])
+def forward_kernel_mode(request, monkeypatch):
+    """the forward code paths of libdfx: fast kernel with TMEM-resident stage history, fast kernel without TMEM,
+    generic kernel for any lattice size, generic kernel spread over a thread-block cluster (4 and 16 CTAs per design)"""
+    return _kernel_mode(monkeypatch, "DFX_FORWARD_KERNEL", request.param)
 
 
 @pytest.mark.parametrize("name", golden_names())
@@ -57,15 +65,11 @@ def test_forward_matches_golden(name, forward_kernel_mode):
     assert abs(int(st["steps"]) - int(c.ref["fwd_steps"])) <= max(2, int(0.01 * c.ref["fwd_steps"]))
 
 
-@pytest.fixture(params=["fast_tmem", "notmem", "generic"])
+@pytest.fixture(params=["fast_tmem", "notmem", "generic", "cluster4", "cluster16"])
 def adjoint_kernel_mode(request, monkeypatch):
-    """the three adjoint code paths of libdfx: fast kernel with TMEM-resident stage history (default), fast
-    kernel without TMEM, generic kernel (any lattice size)"""
-    if request.param == "fast_tmem":
-        monkeypatch.delenv("DFX_ADJOINT_KERNEL", raising=False)
-    else:
-        monkeypatch.setenv("DFX_ADJOINT_KERNEL", request.param)
-    return request.param
+    """the adjoint code paths of libdfx: fast kernel with TMEM-resident stage history (default), fast kernel
+    without TMEM, generic kernel (any lattice size), generic kernel over a thread-block cluster"""
+    return _kernel_mode(monkeypatch, "DFX_ADJOINT_KERNEL", request.param)
 
 
 @pytest.mark.parametrize("name", golden_names())

@@ -15,9 +15,9 @@
 //   C  per block-DOF : gather slots;  dv/ds = -(F - c v + load)/m,  dlambda_u/ds = -(H w),
 //                      dlambda_v/ds = lambda_u - c w,  quadrature integrands for inertia, damping,
 //                      centroid_node_vectors (contact chain), drive parameters and t0_bar
-// Parameter cotangents are pure quadratures: their stage values never feed the RHS, so only the
-// running solution / error / midpoint combinations are kept (k1 and k7 for FSAL and the dense
-// output).  Scalar leaves (k_stretch, ..., contact and drive parameters, t0_bar) are reduced with
+// Parameter cotangents are pure quadratures: their stage values never feed the RHS.  Stages 3..6 only STORE
+// their integrand (no read-modify-write round trip to the L2-resident arrays); the solution / error / midpoint
+// combinations are formed once, at the last stage.  Scalar leaves (k_stretch, ..., contact and drive parameters, t0_bar) are reduced with
 // warp shuffles into per-warp partials and combined once per step.
 #pragma once
 
@@ -33,8 +33,8 @@ enum {
   AA_INVM, AA_CD,
   AA_U0, AA_V0, AA_LU0, AA_LV0,
   AA_KV, AA_KLU, AA_KLV,
-  AA_BONDC, AA_CNV, AA_ALPHA,
-  AA_QSOL, AA_QERR, AA_QMID, AA_QK1, AA_QK7, AA_Q0, AA_QNEW,
+  AA_BONDC, AA_CNV, AA_ALPHA, AA_EDGED,
+  AA_QK3, AA_QK4, AA_QK5, AA_QK6, AA_QK1, AA_QK7, AA_Q0, AA_QNEW,
   AA_COUNT
 };
 
@@ -64,7 +64,8 @@ struct AdjArgs {
 };
 
 struct QuadCtx {
-  double *q0, *qnew, *k1, *k7, *asol, *aerr, *amid;
+  double *q0, *qnew, *k1, *k7, *ks[4];  // ks: stage values k3..k6
+  const Tableau* tab;
   double h, atol, rtol, x;
   int mode;  // 0: k1 at interval start | 2..5: stage | 6: last stage | 7: initial-step probe
   bool crossing;
@@ -87,40 +88,35 @@ __device__ __forceinline__ void quad_update(const QuadCtx& c, int idx, double va
       const double d = (val - c.k1[idx]) / sc;
       acc += d * d;
     } break;
-    case 2: {
-      const double k1 = c.k1[idx];
-      c.asol[idx] = c.cs0 * k1 + c.cs * val;
-      c.aerr[idx] = c.ce0 * k1 + c.ce * val;
-      c.amid[idx] = c.cm0 * k1 + c.cm * val;
-    } break;
     case 6: {
-      const double aerr = c.aerr[idx] + c.ce * val, amid = c.amid[idx] + c.cm * val;
-      const double q0 = c.q0[idx], q1 = q0 + c.h * c.asol[idx];
+      const Tableau& t = *c.tab;
+      const double k1 = c.k1[idx], k3 = c.ks[0][idx], k4 = c.ks[1][idx], k5 = c.ks[2][idx], k6 = c.ks[3][idx];
+      const double asol = t.c_sol[0] * k1 + t.c_sol[2] * k3 + t.c_sol[3] * k4 + t.c_sol[4] * k5 + t.c_sol[5] * k6;
+      const double aerr = t.c_err[0] * k1 + t.c_err[2] * k3 + t.c_err[3] * k4 + t.c_err[4] * k5 + t.c_err[5] * k6 + t.c_err[6] * val;
+      const double amid = t.c_mid[0] * k1 + t.c_mid[2] * k3 + t.c_mid[3] * k4 + t.c_mid[4] * k5 + t.c_mid[5] * k6 + t.c_mid[6] * val;
+      const double q0 = c.q0[idx], q1 = q0 + c.h * asol;
       const double tol = c.atol + c.rtol * fmax(fabs(q0), fabs(q1));
       const double r = c.h * aerr / tol;
       acc += r * r;
       c.k7[idx] = val;
-      c.qnew[idx] = c.crossing ? interp_eval(q0, q1, q0 + c.h * amid, c.h * c.k1[idx], c.h * val, c.x) : q1;
+      c.qnew[idx] = c.crossing ? interp_eval(q0, q1, q0 + c.h * amid, c.h * k1, c.h * val, c.x) : q1;
     } break;
-    default:
-      c.asol[idx] += c.cs * val;
-      c.aerr[idx] += c.ce * val;
-      c.amid[idx] += c.cm * val;
-      break;
+    default: c.ks[c.mode - 2][idx] = val; break;  // stages 3..6 of the step (mode 2..5)
   }
 }
 
 // scalar leaves: per-warp partial sums of the same linear recurrences (combined once per step)
 struct ScalCtx {
-  double *wk1, *wk7, *wsol, *werr, *wmid;  // [NSCAL][scw]
-  int scw;    // warps per design (SCW for one CTA, SCW * cluster size for a cluster)
-  int gwarp;  // this thread's warp index within the design
+  double *wk1, *wk7, *wsol, *werr, *wmid;  // [NSCAL][SCW], consecutive, private to the CTA
 };
+constexpr int kRedDoublesDev = 40;  // reduction scratch at the start of shared memory (kRedDoubles of dfx_api.cu)
+constexpr int kScalDoubles = 2 * NSCAL + 5 * NSCAL * SCW;                 // Sq0, Sqnew + per-warp partials
+constexpr int kClusterReserve = 2 * kMaxCluster + 5 * NSCAL * kMaxCluster;  // cluster-sum partials + CTA totals
 __device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, int which, double partial) {
   // most warps contribute nothing to the sparse scalars (contact, drive, t0): skip their shuffles
   const double v = __any_sync(0xffffffffu, partial != 0.0) ? warp_sum(partial) : 0.0;
   if ((threadIdx.x & 31) != 0) return;
-  const int idx = which * s.scw + s.gwarp;
+  const int idx = which * SCW + (threadIdx.x >> 5);
   switch (c.mode) {
     case 0: s.wk1[idx] = v; break;
     case 7: s.wk7[idx] = v; break;
@@ -151,15 +147,15 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   const Tableau& tab = a.tab;
   const int crank = CL ? (int)cluster_ctarank() : 0, ncta = CL ? (int)cluster_nctarank() : 1;
   const int design = blockIdx.x / ncta;
-  const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x, nwarp = (nthr + 31) >> 5;
+  const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
   const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, cnwarp = (blockDim.x + 31) >> 5;
-  const int scw = SCW * ncta;
   int cpar = 0;
   const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;
   const int NQ = a.nq;
   double* red = smem;
   double* scratch = a.scratch ? a.scratch + (long long)design * a.scratch_per_design : nullptr;
-  double* cred = scratch;  // CL: cluster-sum partials at the start of the scratch
+  double* cred = scratch;  // CL: cluster-sum partials at the start of the scratch ...
+  double* ctot = scratch + 2 * kMaxCluster;  // ... followed by the per-CTA totals of the scalar leaves [5][NSCAL][kMaxCluster]
   auto SYNC = [&]() { if (CL) cluster_sync_all(); else __syncthreads(); };
   auto SUM = [&](double v) { return CL ? cluster_sum(v, red, cred, crank, ncta, cpar) : block_sum(v, red); };
   auto P = [&](int i) -> double* {
@@ -168,21 +164,22 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   };
   double *Us = P(AA_US), *Ws = P(AA_WS), *Vs = P(AA_VS), *Lus = P(AA_LUS), *Lvs = P(AA_LVS);
   double *Fs = P(AA_FS), *Hs = P(AA_HS), *Gs = P(AA_GS), *Ga = T.contact ? P(AA_GA) : nullptr;
-  double* SC = P(AA_SC);  // [2][NSCAL] q0,qnew + [5][NSCAL][scw] per-warp partials
+  // [2][NSCAL] q0,qnew + [5][NSCAL][SCW] per-warp partials; always private to the CTA (shared memory in cluster mode)
+  double* SC = CL ? smem + kRedDoublesDev : P(AA_SC);
   double *invm = P(AA_INVM), *cd = P(AA_CD);
   double *u0 = P(AA_U0), *v0 = P(AA_V0), *lu0 = P(AA_LU0), *lv0 = P(AA_LV0);
   double *kv = P(AA_KV), *klu = P(AA_KLU), *klv = P(AA_KLV);
   double *bondc = P(AA_BONDC), *cnv = P(AA_CNV), *alpha = T.contact ? P(AA_ALPHA) : nullptr;
+  double* edged = T.contact ? P(AA_EDGED) : nullptr;  // [4][NN] d atan2(edge)/d(edge) of the next / previous edge of every node
   QuadCtx qc;
-  qc.asol = P(AA_QSOL); qc.aerr = P(AA_QERR); qc.amid = P(AA_QMID);
+  qc.ks[0] = P(AA_QK3); qc.ks[1] = P(AA_QK4); qc.ks[2] = P(AA_QK5); qc.ks[3] = P(AA_QK6); qc.tab = &a.tab;
   qc.k1 = P(AA_QK1); qc.k7 = P(AA_QK7); qc.q0 = P(AA_Q0); qc.qnew = P(AA_QNEW);
   qc.atol = a.atol; qc.rtol = a.rtol; qc.crossing = false; qc.x = 0; qc.h = 0; qc.mode = 0;
   double* Sq0 = SC;
   double* Sqnew = SC + NSCAL;
   ScalCtx sc;
-  sc.scw = scw; sc.gwarp = tid >> 5;
-  sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * scw; sc.wsol = sc.wk7 + NSCAL * scw;
-  sc.werr = sc.wsol + NSCAL * scw; sc.wmid = sc.werr + NSCAL * scw;
+  sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * SCW; sc.wsol = sc.wk7 + NSCAL * SCW;
+  sc.werr = sc.wsol + NSCAL * SCW; sc.wmid = sc.werr + NSCAL * SCW;
 
   const double* g_ks = leaf_ptr(a.p.k_stretch, design);
   const double* g_ksh = leaf_ptr(a.p.k_shear, design);
@@ -198,10 +195,23 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   const int ndp = T.n_drive_params;
 
   setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd, tid, nthr);
+  if (edged) {
+    const double* g_cnv = leaf_ptr(a.p.centroid_node_vectors, design);
+    for (int n = tid; n < NN; n += nthr) {
+      const int blk = n / npb, l = n - blk * npb;
+      const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
+      const double rx = g_cnv[2 * n], ry = g_cnv[2 * n + 1];
+      const double e1x = g_cnv[2 * nn] - rx, e1y = g_cnv[2 * nn + 1] - ry;  // own next edge (also nn's previous edge, reversed)
+      const double e2x = g_cnv[2 * np] - rx, e2y = g_cnv[2 * np + 1] - ry;  // own previous edge (also np's next edge, reversed)
+      const double i1 = 1.0 / (e1x * e1x + e1y * e1y), i2 = 1.0 / (e2x * e2x + e2y * e2y);
+      // d atan2(e)/d e = (-e_y, e_x)/|e|^2
+      edged[n] = -e1y * i1; edged[NN + n] = e1x * i1; edged[2 * NN + n] = -e2y * i2; edged[3 * NN + n] = e2x * i2;
+    }
+  }
   for (int i = tid; i < 3 * NN; i += nthr) { Fs[i] = 0.0; Hs[i] = 0.0; }
   for (int i = tid; i < 2 * NN; i += nthr) { Gs[i] = 0.0; if (Ga) Ga[i] = 0.0; }
-  for (int i = tid; i < NQ; i += nthr) { qc.q0[i] = 0.0; qc.k1[i] = 0.0; qc.k7[i] = 0.0; qc.qnew[i] = 0.0; qc.asol[i] = 0.0; qc.aerr[i] = 0.0; qc.amid[i] = 0.0; }
-  for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * scw; i += nthr) SC[i] = 0.0;
+  for (int i = tid; i < NQ; i += nthr) { qc.q0[i] = 0.0; qc.k1[i] = 0.0; qc.k7[i] = 0.0; qc.qnew[i] = 0.0; qc.ks[0][i] = 0.0; qc.ks[1][i] = 0.0; qc.ks[2][i] = 0.0; qc.ks[3][i] = 0.0; }
+  for (int i = threadIdx.x; i < kScalDoubles; i += blockDim.x) SC[i] = 0.0;
   double cmin = 0, ccut = 0, ckc = 0;
   if (T.contact) { cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
   // y_bar = g[-1]
@@ -304,19 +314,33 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
         }
       }
       if (want_q && j < 2) {
-        // centroid_node_vectors cotangent integrand of every node of this block, component j
-        for (int l = 0; l < npb; ++l) {
+        // centroid_node_vectors cotangent integrand of every node of this block, component j.  All loads first
+        // (one round trip), then the updates.
+        double vals[4];
+#pragma unroll
+        for (int l = 0; l < 4; ++l) {
+          vals[l] = 0.0;
+          if (l < npb) {
+            const int n = blk * npb + l;
+            double val = Gs[j * NN + n];
+            if (T.contact) {
+              const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
+              const double d1 = edged[j * NN + n], d2 = edged[(2 + j) * NN + n];
+              // own edges: d/dr_n = -d/de ; as far end of nn's previous edge (e = r_n - r_nn = -e1): also -d1
+              val += -Ga[n] * d1 - Ga[NN + n] * d2 - Ga[NN + nn] * d1 - Ga[np] * d2;
+            }
+            vals[l] = val;
+          }
+        }
+#pragma unroll
+        for (int l = 0; l < 4; ++l)
+          if (l < npb) quad_update(qc, a.qo_cnv + j * NN + blk * npb + l, vals[l], probe);
+        for (int l = 4; l < npb; ++l) {  // polygons with more than 4 vertices
           const int n = blk * npb + l;
           double val = Gs[j * NN + n];
           if (T.contact) {
-            const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
-            const double rx = cnv[n], ry = cnv[NN + n];
-            const double e1x = cnv[nn] - rx, e1y = cnv[NN + nn] - ry;   // own next edge (also nn's prev edge, reversed)
-            const double e2x = cnv[np] - rx, e2y = cnv[NN + np] - ry;   // own prev edge (also np's next edge, reversed)
-            const double i1 = 1.0 / (e1x * e1x + e1y * e1y), i2 = 1.0 / (e2x * e2x + e2y * e2y);
-            // d atan2(e)/d e = (-e_y, e_x)/|e|^2 ; component j
-            const double d1 = (j == 0 ? -e1y : e1x) * i1, d2 = (j == 0 ? -e2y : e2x) * i2;
-            // own edges: d/dr_n = -d/de ; as far end of nn's prev edge (e = r_n - r_nn = -e1): d/dr_n = +(-(-e1y), -e1x)/|e1|^2 = -d1
+            const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = n - 1;
+            const double d1 = edged[j * NN + n], d2 = edged[(2 + j) * NN + n];
             val += -Ga[n] * d1 - Ga[NN + n] * d2 - Ga[NN + nn] * d1 - Ga[np] * d2;
           }
           quad_update(qc, a.qo_cnv + j * NN + n, val, probe);
@@ -352,12 +376,28 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     }
   };
 
-  // total of a scalar leaf's per-warp partials; evaluated by a whole warp (lanes stride over the design's warps).
-  // Scalar leaf `which` is owned by warp (which % cnwarp) of the first CTA; its lane 0 holds Sq0 / Sqnew[which].
-  auto wtotal = [&](const double* wa, int which) {
-    double s = 0.0;
-    for (int w = lane; w < nwarp; w += 32) s += wa[which * scw + w];
-    return warp_sum(s);
+  // Scalar leaves: every warp integrates its own partial sums (arrays 0 wk1, 1 wk7, 2 wsol, 3 werr, 4 wmid).
+  // scal_sync(mask): barrier after which the totals of the arrays in `mask` can be read with wtotal().  In cluster
+  // mode each CTA first publishes its own totals (ctot); leaf `which` is owned by warp (which % cnwarp) of the first
+  // CTA, whose lane 0 keeps Sq0 / Sqnew[which].
+  auto scal_sync = [&](int mask) {
+    __syncthreads();
+    if (CL) {
+      for (int w = cwarp; w < NSCAL; w += cnwarp)
+        for (int k = 0; k < 5; ++k) {
+          if (!((mask >> k) & 1)) continue;
+          double v = lane < cnwarp ? sc.wk1[(k * NSCAL + w) * SCW + lane] : 0.0;
+          v = warp_sum(v);
+          if (lane == 0) ctot[(k * NSCAL + w) * kMaxCluster + crank] = v;
+        }
+      cluster_sync_all();
+    }
+  };
+  auto wtotal = [&](int k, int which) {  // whole warp
+    double v;
+    if (CL) v = lane < ncta ? ctot[(k * NSCAL + which) * kMaxCluster + lane] : 0.0;
+    else v = lane < cnwarp ? sc.wk1[(k * NSCAL + which) * SCW + lane] : 0.0;
+    return warp_sum(v);
   };
 
   long long n_steps = 0, n_acc = 0, n_rhs = 0;
@@ -394,7 +434,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       if (a.ts_bar) a.ts_bar[(long long)design * a.n_t + i] = t_bar;
       Sq0[SC_T0] -= t_bar;
     }
-    SYNC();
+    scal_sync(1);
     // ---- initial_step_size over the whole augmented vector ---------------------------------------
     {
       double sd0 = 0, sd1 = 0;
@@ -413,7 +453,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
         sd0 += a0 * a0; sd1 += b0 * b0;
       }
       if (crank == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) {
-        const double k1 = wtotal(sc.wk1, w);
+        const double k1 = wtotal(0, w);
         if (lane == 0) {
           const double s = atol + fabs(Sq0[w]) * rtol;
           const double a0 = Sq0[w] / s, b0 = k1 / s;
@@ -436,9 +476,9 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
         const double b2 = (klu[ND + e] - klu[e]) / slu, b3 = (klv[ND + e] - klv[e]) / slv;
         sd2 += b0 * b0 + b1 * b1 + b2 * b2 + b3 * b3;
       }
-      SYNC();  // per-warp probe partials (wk7) complete
+      scal_sync(2);  // per-warp probe partials (wk7) complete
       if (crank == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) {
-        const double k7 = wtotal(sc.wk7, w), k1 = wtotal(sc.wk1, w);
+        const double k7 = wtotal(1, w), k1 = wtotal(0, w);
         if (lane == 0) {
           const double s = atol + fabs(Sq0[w]) * rtol;
           const double b0 = (k7 - k1) / s;
@@ -505,10 +545,10 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
         const double r3 = elv / (atol + rtol * fmax(fabs(lv0[e]), fabs(Lvs[e])));
         se += r0 * r0 + r1 * r1 + r2 * r2 + r3 * r3;
       }
-      SYNC();  // per-warp scalar partials of the last stage complete
+      scal_sync(31);  // per-warp scalar partials of the last stage complete
       if (crank == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) {
-        const double k1 = wtotal(sc.wk1, w), k7 = wtotal(sc.wk7, w);
-        const double tsol = wtotal(sc.wsol, w), terr = wtotal(sc.werr, w), tmid = wtotal(sc.wmid, w);
+        const double k1 = wtotal(0, w), k7 = wtotal(1, w);
+        const double tsol = wtotal(2, w), terr = wtotal(3, w), tmid = wtotal(4, w);
         if (lane == 0) {
           const double q0 = Sq0[w];
           const double q1 = q0 + h * tsol;
@@ -546,7 +586,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
             u0[e] = Us[e]; v0[e] = Vs[e]; lu0[e] = Lus[e]; lv0[e] = Lvs[e];
             kv[e] = kv[6 * ND + e]; klu[e] = klu[6 * ND + e]; klv[e] = klv[6 * ND + e];
           }
-          if (lane == 0) for (int w = 0; w < NSCAL; ++w) sc.wk1[w * scw + sc.gwarp] = sc.wk7[w * scw + sc.gwarp];
+          if (lane == 0) for (int w = 0; w < NSCAL; ++w) sc.wk1[w * SCW + cwarp] = sc.wk7[w * SCW + cwarp];
           double* tmp = qc.k1; qc.k1 = qc.k7; qc.k7 = tmp;
         }
         if (crank == 0 && lane == 0) for (int w = cwarp; w < NSCAL; w += cnwarp) Sq0[w] = Sqnew[w];

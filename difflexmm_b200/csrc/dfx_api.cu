@@ -33,6 +33,7 @@ int fail(int code, const char* fmt, ...) {
 
 constexpr size_t kSmemBytes = 232448;  // 227 KB: the opt-in maximum of one CTA on sm_100
 constexpr int kRedDoubles = 40;
+static_assert(kRedDoubles == kRedDoublesDev, "shared-memory reduction area");
 constexpr int kScratchSlots = 256;  // >= %nsmid of any sm_100 part: SM-indexed scratch of the fast adjoint kernel
 
 template <class T>
@@ -71,7 +72,7 @@ int n_drive_params_of(int kind) {
 // the cluster-sum partials
 template <int N>
 void plan(const long long (&sizes)[N], long long* off, size_t* smem_bytes, long long* scratch_doubles, int cluster = 1) {
-  long long s = kRedDoubles, g = cluster > 1 ? 2 * kMaxCluster : 0;
+  long long s = kRedDoubles, g = cluster > 1 ? kClusterReserve : 0;
   const long long cap = cluster > 1 ? s : (long long)(kSmemBytes / sizeof(double));
   for (int i = 0; i < N; ++i) {
     const long long n = (sizes[i] + 1) & ~1LL;  // keep 16-byte alignment
@@ -110,12 +111,13 @@ void adjoint_sizes(const DevTopo& T, const QuadLayout& q, long long (&sz)[AA_COU
   const long long NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds;
   sz[AA_US] = 5 * NB; sz[AA_WS] = 3 * NB; sz[AA_VS] = 3 * NB; sz[AA_LUS] = 3 * NB; sz[AA_LVS] = 3 * NB;
   sz[AA_FS] = 3 * NN; sz[AA_HS] = 3 * NN; sz[AA_GS] = 2 * NN; sz[AA_GA] = T.contact ? 2 * NN : 0;
-  sz[AA_SC] = 2 * NSCAL + 5 * NSCAL * SCW * cluster;
+  sz[AA_SC] = cluster > 1 ? 0 : kScalDoubles;  // cluster mode keeps it in each CTA's shared memory
   sz[AA_INVM] = 3 * NB; sz[AA_CD] = 3 * NB;
   sz[AA_U0] = 3 * NB; sz[AA_V0] = 3 * NB; sz[AA_LU0] = 3 * NB; sz[AA_LV0] = 3 * NB;
   sz[AA_KV] = 21 * NB; sz[AA_KLU] = 21 * NB; sz[AA_KLV] = 21 * NB;
   sz[AA_BONDC] = 4 * NBONDS; sz[AA_CNV] = 2 * NN; sz[AA_ALPHA] = T.contact ? 2 * NN : 0;
-  for (int i = AA_QSOL; i <= AA_QNEW; ++i) sz[i] = q.nq;
+  sz[AA_EDGED] = T.contact ? 4 * NN : 0;
+  for (int i = AA_QK3; i <= AA_QNEW; ++i) sz[i] = q.nq;
 }
 
 int pick_threads(const DevTopo& T, int requested) {
@@ -584,7 +586,7 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
     }
     const int threads = pick_threads(T, opt ? opt->threads : 0);
     cudaError_t le = cudaSuccess;
-    if (cluster > 1) le = launch_cluster(adjoint_kernel<1>, batch, cluster, 512, smem, stream, a);
+    if (cluster > 1) le = launch_cluster(adjoint_kernel<1>, batch, cluster, 512, (size_t)(kRedDoubles + kScalDoubles) * sizeof(double), stream, a);
     else adjoint_kernel<0><<<batch, threads, smem, stream>>>(a);
     if (gtmp) cudaFreeAsync(gtmp, stream);
     if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "adjoint_kernel cluster launch (%d CTAs) failed: %s", cluster, cudaGetErrorString(le)); }

@@ -103,6 +103,7 @@ def build_problem(n_designs, seed0):
     spec, drive = prob.lower()
     hs, vs = prob.random_ensemble(n_designs, noise=0.15, seed0=seed0)
     leaves, pb, dpd, aug, y0, ts = prob.boundary_inputs((hs, vs), batch=n_designs, device="cpu")
+    prob.ensemble = (hs, vs)
     return prob, spec, drive, leaves, pb, dpd, aug, y0, ts
 
 
@@ -260,20 +261,21 @@ def main():
     # ---- e2e through the public API with host buffers ----------------------------------------------------
     e2e = None
     if not args.no_e2e:
-        host_names = ["centroid_node_vectors", "inertia"]  # the per-design leaves; the rest is shared by the ensemble
-        h2d = sum(leaves_pinned[k].numel() * 8 for k in host_names)
-        out_pinned = {k: torch.empty_like(leaves_pinned[k]).pin_memory() for k in host_names}
+        # the call a user makes: value and design gradient of the problem's objective for a batch of designs held in
+        # pinned host memory (design -> parameters, forward, objective, adjoint and geometry VJP all inside libdfx)
+        prob._solver = solver
+        design_pinned = [d.contiguous().pin_memory() for d in prob.ensemble]
+        grad_pinned = [torch.empty_like(d).pin_memory() for d in design_pinned]
         obj_pinned = torch.empty(B, dtype=torch.float64).pin_memory()
-        d2h = sum(v.numel() * 8 for v in out_pinned.values()) + obj_pinned.numel() * 8
+        h2d = sum(d.numel() * 8 for d in design_pinned)
+        d2h = sum(d.numel() * 8 for d in grad_pinned) + obj_pinned.numel() * 8
 
         def e2e_step():
-            lv = dict(leaves_d)
-            for k in host_names:
-                lv[k] = leaves_pinned[k].to(dev, non_blocking=True).requires_grad_(True)
-            obj = solver.odeint_kinetic(y0, ts, lv, tidx32, B, pb, dpd, aug)
+            design = [d.to(dev, non_blocking=True).requires_grad_(True) for d in design_pinned]
+            obj = prob.target_kinetic_energy(design, batch=B, fused=True)
             obj.sum().backward()
-            for k in host_names:
-                out_pinned[k].copy_(lv[k].grad, non_blocking=True)
+            for o, d in zip(grad_pinned, design):
+                o.copy_(d.grad, non_blocking=True)
             obj_pinned.copy_(obj.detach(), non_blocking=True)
             torch.cuda.synchronize()
 

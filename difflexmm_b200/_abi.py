@@ -69,6 +69,11 @@ class DfxOptions(C.Structure):
     _fields_ = [("init_step_variant", C.c_int32), ("threads", C.c_int32), ("max_steps", C.c_int64)]
 
 
+class DfxGeometryDesc(C.Structure):
+    _fields_ = [("n_blocks", C.c_int32), ("n_npb", C.c_int32), ("n_design", C.c_int32),
+                ("base_nodes", C.c_void_p), ("node_design", C.c_void_p)]
+
+
 class DfxKineticObjective(C.Structure):
     _fields_ = [("target_free_ids", C.c_void_p), ("n_target", C.c_int32), ("weights", C.c_void_p)]
 

@@ -46,7 +46,8 @@ lib.dfx_fp64_peak.restype = C.c_double
 
 EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free", "dfx_drive_n_params",
            "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
-           "dfx_expand_fields", "dfx_kinetic_energy", "dfx_adjoint_kinetic", "dfx_fp64_peak", "dfx_math_selftest", "dfx_last_error", "dfx_version")
+           "dfx_expand_fields", "dfx_kinetic_energy", "dfx_adjoint_kinetic",
+           "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp", "dfx_fp64_peak", "dfx_math_selftest", "dfx_last_error", "dfx_version")
 
 
 def _check(rc, what):
@@ -68,6 +69,53 @@ class Topology:
         h, self._h = getattr(self, "_h", None), None
         if h:
             lib.dfx_topology_destroy(h)
+
+
+class GeometryHandle:
+    """Owns one `DfxGeometry*`: polygon vertices = base_nodes + design[node_design]."""
+
+    def __init__(self, n_blocks, n_npb, n_design, base_nodes, node_design, device_index):
+        import numpy as np
+        self.n_blocks, self.n_npb, self.n_design = int(n_blocks), int(n_npb), int(n_design)
+        self._base = np.ascontiguousarray(base_nodes, dtype=np.float64).reshape(self.n_blocks * self.n_npb, 2)
+        self._nd = np.ascontiguousarray(node_design, dtype=np.int32).reshape(self.n_blocks * self.n_npb)
+        desc = _abi.DfxGeometryDesc(self.n_blocks, self.n_npb, self.n_design, self._base.ctypes.data, self._nd.ctypes.data)
+        self._h = C.c_void_p()
+        _check(lib.dfx_geometry_create(C.byref(desc), int(device_index), C.byref(self._h)), "dfx_geometry_create")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.dfx_geometry_destroy(h)
+
+
+def geometry_forward(geo: GeometryHandle, design, density):
+    """design (B, n_design, 2), density (B,) or () -> cnv (B, n_nodes, 2), centroid_shift (B, n_blocks, 2), inertia (B, n_blocks, 3)"""
+    dev, B = design.device, design.shape[0]
+    design, density = design.contiguous(), density.contiguous()
+    cnv = torch.empty((B, geo.n_blocks * geo.n_npb, 2), dtype=torch.float64, device=dev)
+    cen = torch.empty((B, geo.n_blocks, 2), dtype=torch.float64, device=dev)
+    inertia = torch.empty((B, geo.n_blocks, 3), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.dfx_geometry_forward(geo._h, B, C.c_void_p(design.data_ptr()), C.c_void_p(density.data_ptr()),
+                                        C.c_int64(1 if density.dim() == 1 else 0), C.c_void_p(cnv.data_ptr()),
+                                        C.c_void_p(cen.data_ptr()), C.c_void_p(inertia.data_ptr()), _stream_ptr(dev)),
+               "dfx_geometry_forward")
+    return cnv, cen, inertia
+
+
+def geometry_vjp(geo: GeometryHandle, design, density, cnv_bar, centroid_bar, inertia_bar, want_density_bar=False):
+    dev, B = design.device, design.shape[0]
+    design, density = design.contiguous(), density.contiguous()
+    cnv_bar, centroid_bar, inertia_bar = [None if t is None else t.contiguous() for t in (cnv_bar, centroid_bar, inertia_bar)]
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+    design_bar = torch.empty((B, geo.n_design, 2), dtype=torch.float64, device=dev)
+    density_bar = torch.empty((B,), dtype=torch.float64, device=dev) if want_density_bar else None
+    with torch.cuda.device(dev):
+        _check(lib.dfx_geometry_vjp(geo._h, B, C.c_void_p(design.data_ptr()), C.c_void_p(density.data_ptr()),
+                                    C.c_int64(1 if density.dim() == 1 else 0), ptr(cnv_bar), ptr(centroid_bar), ptr(inertia_bar),
+                                    C.c_void_p(design_bar.data_ptr()), ptr(density_bar), _stream_ptr(dev)), "dfx_geometry_vjp")
+    return design_bar, density_bar
 
 
 def _stream_ptr(device):

@@ -10,6 +10,7 @@
 #include <type_traits>
 
 #include "dfx_forward2.cuh"
+#include "dfx_geometry.cuh"
 
 using namespace dfx;
 
@@ -628,6 +629,95 @@ int dfx_kinetic_energy(const DfxTopology* t, const DfxParams* params, int batch,
   return DFX_OK;
 }
 
+
+}  // extern "C"
+
+// ---- design -> parameters (dfx_geometry.cuh) --------------------------------------------------------------------
+struct DfxGeometry {
+  int device;
+  DevGeometry dev;
+  std::vector<void*> allocs;
+};
+
+extern "C" {
+
+int dfx_geometry_create(const DfxGeometryDesc* d, int device, DfxGeometry** out) {
+  if (!d || !out || !d->base_nodes || !d->node_design) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (d->n_blocks <= 0 || d->n_npb < 3 || d->n_npb > kMaxPolygon || d->n_design < 0)
+    return fail(DFX_ERR_INVALID, "bad geometry sizes (polygons have 3..%d vertices)", kMaxPolygon);
+  const int nn = d->n_blocks * d->n_npb;
+  std::vector<int> off(d->n_design + 1, 0), nodes;
+  for (int n = 0; n < nn; ++n) {
+    const int k = d->node_design[n];
+    if (k >= d->n_design) return fail(DFX_ERR_INVALID, "node_design[%d] = %d out of range", n, k);
+    if (k >= 0) off[k + 1]++;
+  }
+  for (int k = 0; k < d->n_design; ++k) off[k + 1] += off[k];
+  nodes.resize(off[d->n_design]);
+  {
+    std::vector<int> fill(off.begin(), off.end() - 1);
+    for (int n = 0; n < nn; ++n) if (d->node_design[n] >= 0) nodes[fill[d->node_design[n]]++] = n;
+  }
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cudaSetDevice(device) != cudaSuccess) return fail(DFX_ERR_CUDA, "cudaSetDevice(%d) failed", device);
+  DfxGeometry* g = new (std::nothrow) DfxGeometry();
+  if (!g) { cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "out of host memory"); }
+  g->device = device;
+  std::vector<double> base(d->base_nodes, d->base_nodes + 2 * (size_t)nn);
+  std::vector<int> nd(d->node_design, d->node_design + nn);
+  double* dbase = nullptr; int *dnd = nullptr, *doff = nullptr, *dnodes = nullptr;
+  cudaError_t e = upload(base, &dbase);
+  if (e == cudaSuccess) e = upload(nd, &dnd);
+  if (e == cudaSuccess) e = upload(off, &doff);
+  if (e == cudaSuccess) e = upload(nodes, &dnodes);
+  g->allocs = {dbase, dnd, doff, dnodes};
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) { dfx_geometry_destroy(g); return fail(DFX_ERR_CUDA, "geometry upload failed: %s", cudaGetErrorString(e)); }
+  g->dev.n_blocks = d->n_blocks; g->dev.n_npb = d->n_npb; g->dev.n_nodes = nn; g->dev.n_design = d->n_design;
+  g->dev.base_nodes = dbase; g->dev.node_design = dnd; g->dev.design_off = doff; g->dev.design_nodes = dnodes;
+  *out = g;
+  return DFX_OK;
+}
+
+void dfx_geometry_destroy(DfxGeometry* g) {
+  if (!g) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(g->device);
+  for (void* p : g->allocs) if (p) cudaFree(p);
+  cudaSetDevice(cur);
+  delete g;
+}
+
+int dfx_geometry_forward(const DfxGeometry* g, int batch, const double* design, const double* density, int64_t density_bstride,
+                         double* cnv, double* centroid_shift, double* inertia, void* stream_) {
+  if (!g || !design || !cnv || (inertia && !density)) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (batch <= 0) return fail(DFX_ERR_INVALID, "batch must be positive");
+  const int threads = 128;
+  dim3 grid((g->dev.n_blocks + threads - 1) / threads, batch);
+  geometry_forward_kernel<<<grid, threads, 0, (cudaStream_t)stream_>>>(g->dev, design, density, density_bstride, cnv,
+                                                                      centroid_shift, inertia);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "geometry_forward launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
+
+int dfx_geometry_vjp(const DfxGeometry* g, int batch, const double* design, const double* density, int64_t density_bstride,
+                     const double* cnv_bar, const double* centroid_bar, const double* inertia_bar, double* design_bar,
+                     double* density_bar, void* stream_) {
+  if (!g || !design || !design_bar || (inertia_bar && !density)) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (batch <= 0) return fail(DFX_ERR_INVALID, "batch must be positive");
+  cudaStream_t stream = (cudaStream_t)stream_;
+  double* node_bar = nullptr;
+  CUDA_TRY(cudaMallocAsync((void**)&node_bar, (size_t)batch * g->dev.n_nodes * 2 * sizeof(double), stream));
+  geometry_vjp_kernel<<<batch, 256, 0, stream>>>(g->dev, design, density, density_bstride, cnv_bar, centroid_bar, inertia_bar,
+                                                 node_bar, design_bar, density_bar);
+  cudaError_t e = cudaGetLastError();
+  cudaFreeAsync(node_bar, stream);
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "geometry_vjp launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
 
 }  // extern "C"
 

@@ -84,7 +84,7 @@ def _as_t(x, device):
     return torch.as_tensor(np.asarray(x, dtype=np.float64), device=device)
 
 
-def lower_params(spec, drive, control_params: ControlParams, batch: Optional[int], device, per_bond=()):
+def lower_params(spec, drive, control_params: ControlParams, batch: Optional[int], device, per_bond=(), inertia_full=None):
     """ControlParams -> leaves of libdfx (differentiable torch) + size of the reference's
     augmented adjoint state for one design.
 
@@ -151,7 +151,9 @@ def lower_params(spec, drive, control_params: ControlParams, batch: Optional[int
         dens = density
         if B is not None and cnv_b and dens.dim() >= 1 and dens.shape[0] == B:
             dens = dens.reshape(B, *([1] * (1 if dens.dim() == 1 else 0)), *dens.shape[1:])
-        inertia_full = compute_inertia(cnv, dens)
+        # `inertia_full`: the same quantity already evaluated by the caller (libdfx geometry kernel)
+        if inertia_full is None:
+            inertia_full = compute_inertia(cnv, dens)
     else:
         inertia_full, _, n = split(mp.inertia, 2)
         n_entries += n
@@ -312,12 +314,12 @@ class DynamicSolver:
         return torch.as_tensor(pos.astype(np.int32), device=self.device)
 
     def kinetic_objective(self, state0, timepoints, control_params: ControlParams, target_blocks,
-                          batch: Optional[int] = None, per_bond=()):
+                          batch: Optional[int] = None, per_bond=(), inertia_full=None):
         """Fused objective of the reference's focusing problems (`problems/quads_focusing.py:453-467`):
         sum over output times of the kinetic energy of `target_blocks`.  -> (B,) tensor (scalar without batch),
         differentiable w.r.t. control_params; forward, objective and adjoint all run inside libdfx."""
         spec, dev = self.spec, self.device
-        leaves, pb, dpd, aug_size = lower_params(spec, self.drive, control_params, batch, dev, per_bond)
+        leaves, pb, dpd, aug_size = lower_params(spec, self.drive, control_params, batch, dev, per_bond, inertia_full)
         free = torch.as_tensor(spec.free_dofs, device=dev)
         state0 = _as_t(state0, dev)
         y0 = state0.reshape(*state0.shape[:-3], 2, spec.n_blocks * 3)[..., free]

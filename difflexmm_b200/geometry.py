@@ -245,6 +245,9 @@ class QuadGeometry(LatticeGeometry):
 
         self.centroid_node_vectors = centroid_node_vectors
         self.block_centroids = block_centroids
+        self.reference_node_vectors = reference_node_vectors
+        self.reference_points = ref_points
+        self.design_shapes = [(self.n1_blocks + 1, self.n2_blocks, 2), (self.n1_blocks, self.n2_blocks + 1, 2)]
         self.bond_connectivity = lambda: _square_grid_bonds(self.n1_blocks, self.n2_blocks)
         self.reference_bond_vectors = lambda: _square_grid_reference_bonds(
             self.n1_blocks, self.n2_blocks, self.bond_length)
@@ -336,6 +339,9 @@ class KagomeGeometry(LatticeGeometry):
 
         self.centroid_node_vectors = centroid_node_vectors
         self.block_centroids = block_centroids
+        self.reference_node_vectors = reference_node_vectors
+        self.reference_points = ref_points
+        self.design_shapes = [(n1c + 1, n2c, 2), (n1c, n2c + 1, 2), (n1c, n2c, 2)]
         self.bond_connectivity = bond_connectivity
         self.reference_bond_vectors = reference_bond_vectors
         self._computed = True

@@ -1,0 +1,85 @@
+"""Design -> (centroid_node_vectors, block_centroids, inertia) on the device with a hand-written VJP
+(libdfx `dfx_geometry_forward` / `dfx_geometry_vjp`).
+
+Works for the lattices whose polygon vertices are `base + one design 2-vector` -- the reference's QuadGeometry and
+KagomeGeometry (`geometry.py:607-952`).  The vertex -> design-variable table is not re-derived by hand: it is read off
+the (tested) torch map `reference_node_vectors`, which is affine with 0/1 coefficients, by probing it once on the CPU.
+"""
+from typing import Sequence
+
+import numpy as np
+import torch
+
+from . import _lib
+
+_F64 = torch.float64
+
+
+class _DesignToParams(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, dg, design, density):
+        cnv, cen, inertia = _lib.geometry_forward(dg.handle, design, density)
+        ctx.dg = dg
+        ctx.save_for_backward(design, density)
+        return cnv, cen, inertia
+
+    @staticmethod
+    def backward(ctx, cnv_bar, cen_bar, inertia_bar):
+        design, density = ctx.saved_tensors
+        want_rho = ctx.needs_input_grad[2]
+        design_bar, rho_bar = _lib.geometry_vjp(ctx.dg.handle, design, density, cnv_bar, cen_bar, inertia_bar, want_rho)
+        if want_rho and density.dim() == 0:
+            rho_bar = rho_bar.sum()
+        return None, design_bar, rho_bar
+
+
+class DeviceGeometry:
+    """Device-side design map of one lattice geometry (`QuadGeometry` or `KagomeGeometry` of `difflexmm_b200.geometry`)."""
+
+    def __init__(self, geometry, device="cuda"):
+        if not hasattr(geometry, "reference_node_vectors"):
+            geometry.compute_geometry()
+        if not hasattr(geometry, "reference_node_vectors"):
+            raise TypeError(f"{type(geometry).__name__} has no per-vertex design shifts (use its torch maps)")
+        self.geometry = geometry
+        self.device = torch.device(device)
+        self.shapes = [tuple(s) for s in geometry.design_shapes]
+        self.sizes = [int(np.prod(s[:-1])) for s in self.shapes]
+        self.n_design = sum(self.sizes)
+        zeros = [torch.zeros(s, dtype=_F64) for s in self.shapes]
+        base = geometry.reference_node_vectors(*zeros)
+        # probe: design 2-vector k = (k + 1, -(k + 1)) -> vertex offset identifies k
+        probe, k0 = [], 0
+        for s, n in zip(self.shapes, self.sizes):
+            k = torch.arange(k0 + 1, k0 + n + 1, dtype=_F64).reshape(s[:-1])
+            probe.append(torch.stack([k, -k], -1))
+            k0 += n
+        off = geometry.reference_node_vectors(*probe) - base
+        idx = torch.round(off[..., 0]).to(torch.int64)
+        tol = 1e-9 * max(1.0, float(base.abs().max()))
+        if (off[..., 0] - idx).abs().max() > tol or (off[..., 1] + idx).abs().max() > tol or idx.min() < 0:
+            raise ValueError("reference_node_vectors is not `base + one design vector per vertex`")
+        self.n_blocks, self.n_npb = base.shape[0], base.shape[1]
+        self.handle = _lib.GeometryHandle(self.n_blocks, self.n_npb, self.n_design, base.numpy(), (idx - 1).numpy(),
+                                          self.device.index if self.device.index is not None else torch.cuda.current_device())
+        self.reference_points = geometry.reference_points.to(self.device)
+
+    def flatten(self, design: Sequence[torch.Tensor]):
+        """tuple of design arrays (optionally with a leading batch axis) -> (B, n_design, 2), batched flag"""
+        parts = [torch.as_tensor(d, dtype=_F64, device=self.device) for d in design]
+        batched = parts[0].dim() == len(self.shapes[0]) + 1
+        B = parts[0].shape[0] if batched else 1
+        flat = torch.cat([p.reshape(B, n, 2) for p, n in zip(parts, self.sizes)], dim=1)
+        return flat, batched
+
+    def __call__(self, design, density):
+        """-> centroid_node_vectors ([B,] n_blocks, n_npb, 2), block_centroids ([B,] n_blocks, 2), inertia ([B,] n_blocks, 3);
+        differentiable w.r.t. the design arrays and the density."""
+        flat, batched = self.flatten(design)
+        rho = torch.as_tensor(density, dtype=_F64, device=self.device)
+        cnv, cen, inertia = _DesignToParams.apply(self, flat, rho)
+        cnv = cnv.reshape(flat.shape[0], self.n_blocks, self.n_npb, 2)
+        cen = cen + self.reference_points
+        if not batched:
+            return cnv[0], cen[0], inertia[0]
+        return cnv, cen, inertia

@@ -64,6 +64,24 @@ class _ProblemBase:
             self.setup()
         return self._solver
 
+    def _torch_geometry(self, design, device):
+        """design arrays (optionally with a leading batch axis) -> (centroid_node_vectors, block_centroids) with the
+        differentiable torch maps of `geometry.py` (one design at a time)."""
+        parts = [torch.as_tensor(d, dtype=_F64, device=device) for d in design]
+        geo = self.geometry
+        if parts[0].dim() == 4:  # batch of designs
+            cnv = torch.stack([geo.centroid_node_vectors(*d) for d in zip(*parts)])
+            cen = torch.stack([geo.block_centroids(*d) for d in zip(*parts)])
+            return cnv, cen
+        return geo.centroid_node_vectors(*parts), geo.block_centroids(*parts)
+
+    def device_geometry(self):
+        """libdfx design map of this problem's lattice (`geometry_device.DeviceGeometry`), created on first use."""
+        if getattr(self, "_device_geometry", None) is None:
+            from .geometry_device import DeviceGeometry
+            self._device_geometry = DeviceGeometry(self.geometry, self.solver.device)
+        return self._device_geometry
+
     def state0(self, device=None):
         return torch.zeros((2, self.geometry.n_blocks, 3), dtype=_F64, device=device)
 
@@ -89,9 +107,12 @@ class _ProblemBase:
         target blocks summed over the output times.  `fused=True` evaluates it inside libdfx
         (`DynamicSolver.kinetic_objective`): no fields, no cotangent tensor."""
         if fused:
+            # design -> parameters, forward solve, objective and both backward passes inside libdfx
             s = self.solver
-            return s.kinetic_objective(self.state0(s.device), self.timepoints(s.device),
-                                       self.control_params(design, s.device), self.target_blocks(), batch=batch)
+            cnv, cen, inertia = self.device_geometry()(design, self.density)
+            cp = self.control_params(design, s.device, geom=(cnv, cen))
+            return s.kinetic_objective(self.state0(s.device), self.timepoints(s.device), cp, self.target_blocks(),
+                                       batch=batch, inertia_full=inertia)
         sol = self.solve(design, batch)
         tb = torch.as_tensor(self.target_blocks(), device=sol.fields.device)
         inertia = compute_inertia(sol.centroid_node_vectors, torch.as_tensor(self.density, dtype=_F64,
@@ -172,15 +193,9 @@ class QuadsFocusing(_ProblemBase):
     def initial_design(self):
         return self.make_geometry().get_design_from_rotated_square(self.initial_angle)
 
-    def control_params(self, design, device=None):
-        hs, vs = design
-        hs, vs = torch.as_tensor(hs, dtype=_F64, device=device), torch.as_tensor(vs, dtype=_F64, device=device)
+    def control_params(self, design, device=None, geom=None):
         geo = self.geometry
-        if hs.dim() == 4:  # batch of designs
-            cnv = torch.stack([geo.centroid_node_vectors(h, v) for h, v in zip(hs, vs)])
-            cen = torch.stack([geo.block_centroids(h, v) for h, v in zip(hs, vs)])
-        else:
-            cnv, cen = geo.centroid_node_vectors(hs, vs), geo.block_centroids(hs, vs)
+        cnv, cen = geom if geom is not None else self._torch_geometry(design, device)
         amplitude = self.amplitude if self.loaded_side in ("left", "bottom") else -self.amplitude
         return ControlParams(
             geometrical_params=GeometricalParams(block_centroids=cen, centroid_node_vectors=cnv),
@@ -272,14 +287,9 @@ class KagomeFocusing(_ProblemBase):
         return (torch.zeros(n1 + 1, n2, 2, dtype=_F64), torch.zeros(n1, n2 + 1, 2, dtype=_F64),
                 torch.zeros(n1, n2, 2, dtype=_F64))
 
-    def control_params(self, design, device=None):
-        shifts = [torch.as_tensor(s, dtype=_F64, device=device) for s in design]
+    def control_params(self, design, device=None, geom=None):
         geo = self.geometry
-        if shifts[0].dim() == 4:
-            cnv = torch.stack([geo.centroid_node_vectors(*s) for s in zip(*shifts)])
-            cen = torch.stack([geo.block_centroids(*s) for s in zip(*shifts)])
-        else:
-            cnv, cen = geo.centroid_node_vectors(*shifts), geo.block_centroids(*shifts)
+        cnv, cen = geom if geom is not None else self._torch_geometry(design, device)
         return ControlParams(
             geometrical_params=GeometricalParams(block_centroids=cen, centroid_node_vectors=cnv),
             mechanical_params=MechanicalParams(
@@ -355,13 +365,11 @@ class QuadsStaticTuning(_ProblemBase):
                              dtype=_F64, device=device)
         return torch.cat([torch.zeros(1, dtype=_F64, device=device), dyn])
 
-    def control_params(self, design, device=None):
-        hs, vs = design
-        hs, vs = torch.as_tensor(hs, dtype=_F64, device=device), torch.as_tensor(vs, dtype=_F64, device=device)
+    def control_params(self, design, device=None, geom=None):
         geo = self.geometry
+        cnv, cen = geom if geom is not None else self._torch_geometry(design, device)
         return ControlParams(
-            geometrical_params=GeometricalParams(block_centroids=geo.block_centroids(hs, vs),
-                                                 centroid_node_vectors=geo.centroid_node_vectors(hs, vs)),
+            geometrical_params=GeometricalParams(block_centroids=cen, centroid_node_vectors=cnv),
             mechanical_params=MechanicalParams(
                 bond_params=LigamentParams(k_stretch=self.k_stretch, k_shear=self.k_shear, k_rot=self.k_rot,
                                            reference_vector=geo.reference_bond_vectors().to(device)),

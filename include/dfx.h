@@ -203,6 +203,32 @@ int dfx_adjoint_kinetic(const DfxTopology* topo, const DfxParams* params, int ba
                         double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
                         void* workspace, size_t workspace_bytes, void* stream);
 
+/* ---- design -> solver parameters on the device ------------------------------------------------
+ * Replaces the reference's design maps and their JAX-derived VJPs for lattices whose every polygon vertex is
+ * `base_node + design[node_design]`: QuadGeometry / KagomeGeometry reference_node_vectors, centroid_node_vectors,
+ * block_centroids (geometry.py:607-952) and compute_inertia (geometry.py:71-160).
+ *   cnv[b][n][:]            = vertex - polygon centroid
+ *   centroid_shift[b][k][:] = polygon centroid (block_centroids = lattice reference point + centroid_shift)
+ *   inertia[b][k][:]        = density * (area, area, polar moment about the centroid)
+ * dfx_geometry_vjp returns design_bar = J^T (cnv_bar, centroid_bar, inertia_bar) and optionally density_bar. */
+typedef struct DfxGeometryDesc {
+  int32_t n_blocks, n_npb;
+  int32_t n_design;            /* number of design 2-vectors */
+  const double* base_nodes;    /* host, [n_blocks * n_npb][2] */
+  const int32_t* node_design;  /* host, [n_blocks * n_npb]: design 2-vector added to the vertex, or -1 */
+} DfxGeometryDesc;
+typedef struct DfxGeometry DfxGeometry;
+
+int dfx_geometry_create(const DfxGeometryDesc* desc, int device, DfxGeometry** out);
+void dfx_geometry_destroy(DfxGeometry* geo);
+int dfx_geometry_forward(const DfxGeometry* geo, int batch, const double* design /*[B][n_design][2]*/,
+                         const double* density, int64_t density_bstride /* 0 = shared */,
+                         double* cnv, double* centroid_shift /* or NULL */, double* inertia /* or NULL */, void* stream);
+int dfx_geometry_vjp(const DfxGeometry* geo, int batch, const double* design, const double* density, int64_t density_bstride,
+                     const double* cnv_bar /* or NULL */, const double* centroid_bar /* or NULL */,
+                     const double* inertia_bar /* or NULL */, double* design_bar /*[B][n_design][2]*/,
+                     double* density_bar /*[B] or NULL*/, void* stream);
+
 /* fields[b][i][0][blk][dof] = displacement, fields[b][i][1][blk][dof] = velocity of every
  * block DOF (constrained DOFs follow the drive and its time derivative). */
 int dfx_expand_fields(const DfxTopology* topo, const DfxParams* params, int batch,

@@ -299,3 +299,43 @@ def test_fused_objective_rejects_constrained_targets():
     s = P.setup()
     with pytest.raises(ValueError):
         s.target_free_ids(np.array([int(np.asarray(P.spec.constrained_dofs)[0]) // 3]))
+
+
+@pytest.mark.parametrize("lattice", ["quads", "kagome"])
+def test_device_geometry_matches_the_torch_design_maps(lattice):
+    """dfx_geometry_forward / dfx_geometry_vjp against the differentiable torch restatement of the
+    reference's design maps (geometry.py:607-952) and compute_inertia (geometry.py:144-160): values and VJP."""
+    from difflexmm_b200.geometry import KagomeGeometry, QuadGeometry, compute_inertia
+    from difflexmm_b200.geometry_device import DeviceGeometry
+    rng = np.random.default_rng(3)
+    if lattice == "quads":
+        geo = QuadGeometry(7, 5, spacing=15.0, bond_length=2.25)
+        geo.compute_geometry()
+        base = geo.get_design_from_rotated_square(25 * math.pi / 180)
+    else:
+        geo = KagomeGeometry(5, 4, direct_basis=20.0 * np.array([[1, 0], [math.cos(math.pi / 3), math.sin(math.pi / 3)]]),
+                             bond_length=2.25)
+        geo.compute_geometry()
+        base = [torch.zeros(s, dtype=torch.float64) for s in geo.design_shapes]
+    B, rho = 3, 6.18e-9
+    designs = [torch.stack([b + torch.from_numpy(rng.uniform(-1, 1, b.shape)) for _ in range(B)]) for b in base]
+    dg = DeviceGeometry(geo, "cuda")
+    # reference: torch maps, one design at a time, on the CPU
+    d_ref = [d.clone().requires_grad_(True) for d in designs]
+    cnv_r = torch.stack([geo.centroid_node_vectors(*[d[i] for d in d_ref]) for i in range(B)])
+    cen_r = torch.stack([geo.block_centroids(*[d[i] for d in d_ref]) for i in range(B)])
+    ine_r = compute_inertia(cnv_r, torch.tensor(rho, dtype=torch.float64))
+    d_dev = [d.clone().cuda().requires_grad_(True) for d in designs]
+    cnv, cen, ine = dg(d_dev, rho)
+    assert rel_l2(cnv.detach().cpu().numpy(), cnv_r.detach().numpy()) <= 1e-14
+    assert rel_l2(cen.detach().cpu().numpy(), cen_r.detach().numpy()) <= 1e-14
+    assert rel_l2(ine.detach().cpu().numpy(), ine_r.detach().numpy()) <= 1e-13
+    w_cnv, w_cen = torch.from_numpy(rng.standard_normal(cnv_r.shape)), torch.from_numpy(rng.standard_normal(cen_r.shape))
+    w_ine = torch.from_numpy(rng.standard_normal(ine_r.shape)) / ine_r.detach().abs()
+    ((cnv_r * w_cnv).sum() + (cen_r * w_cen).sum() + (ine_r * w_ine).sum()).backward()
+    ((cnv * w_cnv.cuda()).sum() + (cen * w_cen.cuda()).sum() + (ine * w_ine.cuda()).sum()).backward()
+    for a, b in zip(d_dev, d_ref):
+        assert rel_l2(a.grad.cpu().numpy(), b.grad.numpy()) <= 1e-12
+    # unbatched call
+    cnv1, cen1, ine1 = dg([d[0] for d in designs], rho)
+    assert cnv1.shape == cnv_r.shape[1:] and torch.equal(cnv1, cnv[0].detach())

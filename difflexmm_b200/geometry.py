@@ -103,6 +103,34 @@ def compute_edge_lengths(centroid_node_vectors):
     return torch.linalg.norm(torch.roll(cnv, 1, dims=1) - cnv, dim=2)
 
 
+def angle_between_unit_vectors(u1, u2):
+    """Signed angle from u1 to u2, in [-pi, pi] (reference `geometry.py:221-231`); vectorised over leading axes."""
+    return torch.atan2(u1[..., 0] * u2[..., 1] - u1[..., 1] * u2[..., 0], u1[..., 0] * u2[..., 0] + u1[..., 1] * u2[..., 1])
+
+
+def compute_edge_unit_vectors(current_block_nodes, node_id):
+    """Unit vectors from vertex `node_id` (global ids, any shape) to the next / previous vertex of its block
+    (reference `geometry.py:181-202`)."""
+    nodes = _t(current_block_nodes)
+    npb = nodes.shape[-2]
+    node_id = torch.as_tensor(node_id, dtype=torch.int64, device=nodes.device)
+    blk, l = node_id // npb, node_id % npb
+    here = nodes[blk, l]
+    e1 = nodes[blk, (l + 1) % npb] - here
+    e2 = nodes[blk, (l - 1) % npb] - here
+    return e1 / torch.linalg.norm(e1, dim=-1, keepdim=True), e2 / torch.linalg.norm(e2, dim=-1, keepdim=True)
+
+
+def compute_edge_angles(current_block_nodes, nodes):
+    """(void_angle_1, void_angle_2, block_angle_1, block_angle_2) of the bonds `nodes` (n_bonds, 2)
+    (reference `geometry.py:234-253`, vectorised over the bonds)."""
+    nodes = torch.as_tensor(np.asarray(nodes), dtype=torch.int64)
+    b1n1, b1n2 = compute_edge_unit_vectors(current_block_nodes, nodes[..., 0])
+    b2n1, b2n2 = compute_edge_unit_vectors(current_block_nodes, nodes[..., 1])
+    return (angle_between_unit_vectors(b2n2, b1n1), angle_between_unit_vectors(b1n2, b2n1),
+            angle_between_unit_vectors(b1n1, b1n2), angle_between_unit_vectors(b2n1, b2n2))
+
+
 # ----------------------------------------------------------------------------------
 # Geometry classes
 # ----------------------------------------------------------------------------------

@@ -339,3 +339,22 @@ def test_device_geometry_matches_the_torch_design_maps(lattice):
     # unbatched call
     cnv1, cen1, ine1 = dg([d[0] for d in designs], rho)
     assert cnv1.shape == cnv_r.shape[1:] and torch.equal(cnv1, cnv[0].detach())
+
+
+def test_batched_mma_improves_an_ensemble_of_designs():
+    """several MMA instances advanced in lock-step, one batched forward + adjoint per iteration"""
+    from difflexmm_b200.optimization import OptimizationProblem
+    P = _problem()
+    P.setup()
+    B = 3
+    guesses = P.random_ensemble(B, noise=0.03)
+    opt = OptimizationProblem(P)
+    x0 = opt.flatten(guesses)
+    J0, g0 = opt.objective_and_grad(x0.cuda())
+    assert J0.shape == (B,) and g0.shape == x0.shape
+    best, best_f = opt.run_optimization_mma([g.cuda() for g in guesses], n_iterations=6,
+                                            lower_bound=float(x0.min()) - 1.0, upper_bound=float(x0.max()) + 1.0)
+    assert len(opt.objective_values) == 6
+    assert (best_f >= J0 * (1 - 1e-12)).all() and (best_f > J0 * 1.001).any()
+    sol = opt.compute_best_forward()
+    assert sol.fields.shape == (P.n_timepoints, 2, P.geometry.n_blocks, 3)

@@ -177,3 +177,112 @@ def test_tabulated_drive_matches_numpy_interp():
     assert np.allclose(f[0, :, 1, 0], v[0, :, 0].numpy(), rtol=1e-12, atol=1e-12)
     inside = (ts > times[0]) & (ts < times[-1])
     assert np.all(f[0, ~inside, 1, 0] == 0.0) and np.any(f[0, inside, 1, 0] != 0.0)
+
+
+# ---- optimisation layer -------------------------------------------------------------------------
+def test_batched_mma_converges_and_instances_are_independent():
+    import torch
+    from difflexmm_b200.optimization import BatchedMMA
+    torch.manual_seed(0)
+    B, n = 3, 6
+    A = torch.rand(B, n, dtype=torch.float64) + 0.5
+    c = torch.randn(B, n, dtype=torch.float64) * 2
+
+    def make(rows):
+        return lambda x: ((0.5 * A[rows] * (x - c[rows]) ** 2).sum(1), A[rows] * (x - c[rows]))
+
+    opt = BatchedMMA(make(slice(None)), torch.zeros(B, n, dtype=torch.float64), -1.0, 1.0, maximize=False)
+    bx, bf = opt.run(40)
+    assert opt.n_evals == 40 and len(opt.history) == 40
+    assert (bx - c.clamp(-1, 1)).abs().max() < 1e-5          # box-constrained minimiser
+    for i in range(B):                                        # lock-step batching does not couple the instances
+        o1 = BatchedMMA(make(slice(i, i + 1)), torch.zeros(1, n, dtype=torch.float64), -1.0, 1.0, maximize=False)
+        x1, f1 = o1.run(40)
+        assert torch.equal(x1[0], bx[i]) and torch.equal(f1[0], bf[i])
+    # maximisation, no bounds
+    opt = BatchedMMA(lambda x: (-(x ** 2).sum(1), -2 * x), torch.full((2, 3), 3.0, dtype=torch.float64), maximize=True)
+    bx, bf = opt.run(60)
+    assert bx.abs().max() < 1e-4 and (bf <= 0).all()
+
+
+def test_constraints_match_a_per_bond_restatement():
+    """angle / edge-length constraints (reference problems/quads_focusing.py:473-544) against a literal per-bond loop
+    over the reference's compute_edge_unit_vectors / angle_between_unit_vectors (geometry.py:181-253)"""
+    import math
+    import torch
+    from difflexmm_b200.geometry import QuadGeometry
+    from difflexmm_b200.optimization import angle_constraints, edge_length_constraints, quad_boundary_node_ids
+    geo = QuadGeometry(5, 4, spacing=15.0, bond_length=2.25)
+    geo.compute_geometry()
+    rng = np.random.default_rng(1)
+    design = [d + torch.from_numpy(rng.uniform(-1, 1, d.shape)) for d in geo.get_design_from_rotated_square(25 * math.pi / 180)]
+    nodes = geo.centroid_node_vectors(*design).numpy()
+
+    def unit(v):
+        return v / np.linalg.norm(v)
+
+    def edges(n):
+        blk, l = n // 4, n % 4
+        return unit(nodes[blk, (l + 1) % 4] - nodes[blk, l]), unit(nodes[blk, (l - 1) % 4] - nodes[blk, l])
+
+    def ang(u1, u2):
+        return math.atan2(u1[0] * u2[1] - u1[1] * u2[0], u1[0] * u2[0] + u1[1] * u2[1])
+
+    rows = []
+    for n1, n2 in geo.bond_connectivity():
+        a1, a2 = edges(n1)
+        b1, b2 = edges(n2)
+        rows.append([ang(b2, a1) % (2 * math.pi), ang(a2, b1) % (2 * math.pi), ang(a1, a2) % (2 * math.pi), ang(b1, b2) % (2 * math.pi)])
+    rows = np.array(rows)
+    bnd = np.array([ang(*edges(n)) % (2 * math.pi) for n in quad_boundary_node_ids(5, 4)])
+    mv, mb = 0.05, 0.3
+    want = np.concatenate([-(rows[:, 0] - mv), -(rows[:, 1] - mv), -(rows[:, 2] - mb), -(rows[:, 3] - mb), -(bnd - mb)])
+    got = angle_constraints(geo, mv, mb, boundary_angle_constraint=True)(design).numpy()
+    assert got.shape == (4 * len(rows) + 2 * (5 + 4),) and np.abs(got - want).max() < 1e-13
+    assert angle_constraints(geo, mv, mb)(design).shape == (4 * len(rows),)
+    el = edge_length_constraints(geo, 1.0)(design).numpy()
+    want_el = -(np.linalg.norm(np.roll(nodes, 1, axis=1) - nodes, axis=2).reshape(-1) - 1.0)
+    assert np.abs(el - want_el).max() < 1e-13
+    # Jacobian by autograd (the reference takes jax.jacobian)
+    d0 = [d.clone().requires_grad_(True) for d in design]
+    J = torch.autograd.functional.jacobian(lambda a, b: edge_length_constraints(geo, 1.0)([a, b]), tuple(d0))
+    assert J[0].shape == (20 * 4,) + tuple(design[0].shape) and torch.isfinite(J[0]).all()
+
+
+def test_save_load_data_is_pickle_compatible_with_the_reference(tmp_path):
+    """files written here load under the reference's class path `difflexmm.utils.SolutionData` (utils.py:9-25,166-201);
+    files from the reference side load here"""
+    import pickle
+    import sys
+    import types
+    from typing import Any, NamedTuple
+    import torch
+    from difflexmm_b200.utils import SolutionData, load_data, save_data
+    sd = SolutionData(torch.zeros(3, 2), torch.ones(3, 4, 2), np.array([[0, 5]]), torch.linspace(0, 1, 4), torch.zeros(4, 2, 3, 3))
+    path = save_data(tmp_path / "out" / "solution.pkl", {"solution": sd, "objective_values": [1.0, 2.0]})
+    assert "difflexmm" not in sys.modules
+    back = load_data(path)
+    assert isinstance(back["solution"], SolutionData) and isinstance(back["solution"].fields, np.ndarray)
+    assert back["solution"].fields.shape == (4, 2, 3, 3) and back["objective_values"] == [1.0, 2.0]
+
+    class RefSolutionData(NamedTuple):  # what the reference's unpickler resolves the global to
+        block_centroids: Any
+        centroid_node_vectors: Any
+        bond_connectivity: Any
+        timepoints: Any
+        fields: Any
+
+    mod = types.ModuleType("difflexmm.utils")
+    mod.SolutionData = RefSolutionData
+    RefSolutionData.__module__, RefSolutionData.__qualname__ = "difflexmm.utils", "SolutionData"
+    sys.modules["difflexmm"], sys.modules["difflexmm.utils"] = types.ModuleType("difflexmm"), mod
+    try:
+        with open(path, "rb") as f:
+            ref_side = pickle.load(f)
+        assert isinstance(ref_side["solution"], RefSolutionData)
+        ref_file = tmp_path / "ref.pkl"
+        with open(ref_file, "wb") as f:
+            pickle.dump(RefSolutionData(*[np.asarray(v) for v in back["solution"]]), f)
+    finally:
+        del sys.modules["difflexmm"], sys.modules["difflexmm.utils"]
+    assert isinstance(load_data(ref_file), SolutionData)

@@ -86,3 +86,11 @@ def combine_block_energies(*energy_fns):
 def kinetic_energy(block_velocity, inertia):
     """sum(inertia * v^2 / 2) (reference `energy.py:494-499`)."""
     return torch.sum(inertia * block_velocity ** 2 / 2)
+
+
+def angular_momentum(block_position, block_velocity, inertia, reference_point=(0.0, 0.0)):
+    """(position - reference) x (m v) + I omega per block, shape (..., n_blocks) (reference `energy.py:502-519`)."""
+    ref = torch.as_tensor(reference_point, dtype=block_position.dtype, device=block_position.device)
+    r = block_position[..., :2] - ref
+    p = block_velocity[..., :2] * inertia[..., :2]
+    return r[..., 0] * p[..., 1] - r[..., 1] * p[..., 0] + block_velocity[..., 2] * inertia[..., 2]

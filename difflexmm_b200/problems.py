@@ -18,7 +18,7 @@ import numpy as np
 import torch
 
 from .dynamics import DynamicSolver, lower_params, lower_topology
-from .energy import (build_contact_energy, build_strain_energy, combine_block_energies, kinetic_energy,
+from .energy import (angular_momentum, build_contact_energy, build_strain_energy, combine_block_energies, kinetic_energy,
                      ligament_energy, ligament_energy_linearized)
 from .geometry import KagomeGeometry, QuadGeometry, compute_inertia
 from .loading import pulse_drive, static_pulse_drive
@@ -122,6 +122,22 @@ class _ProblemBase:
         if batch is None:
             return kinetic_energy(v, m)
         return (m[:, None] * v ** 2 / 2).sum(dim=(1, 2, 3))
+
+    def target_angular_momentum(self, design, spin_center="center"):
+        """objective of the reference's spin problem (`problems/quads_spin.py:395-428`): angular momentum of the target
+        blocks about `spin_center`, summed over blocks and output times.  "center" = mean reference centroid of the
+        target blocks for THIS design, held fixed (not differentiated), as in the reference where it is evaluated
+        once from the forward input."""
+        sol = self.solve(design)
+        dev = sol.fields.device
+        tb = torch.as_tensor(self.target_blocks(), device=dev)
+        cen = sol.block_centroids.index_select(0, tb)
+        center = cen.mean(0).detach() if isinstance(spin_center, str) else torch.as_tensor(spin_center, dtype=_F64, device=dev)
+        inertia = compute_inertia(sol.centroid_node_vectors.index_select(0, tb),
+                                  torch.as_tensor(self.density, dtype=_F64, device=dev))
+        u = sol.fields[:, 0].index_select(1, tb)[..., :2]
+        v = sol.fields[:, 1].index_select(1, tb)
+        return angular_momentum(cen[None] + u, v, inertia[None], center).sum()
 
 
 @dataclass

@@ -358,3 +358,26 @@ def test_batched_mma_improves_an_ensemble_of_designs():
     assert (best_f >= J0 * (1 - 1e-12)).all() and (best_f > J0 * 1.001).any()
     sol = opt.compute_best_forward()
     assert sol.fields.shape == (P.n_timepoints, 2, P.geometry.n_blocks, 3)
+
+
+def test_angular_momentum_objective_gradient_matches_finite_differences():
+    """the spin objective of the reference (problems/quads_spin.py:395-428, energy.py:502-519): its cotangent has
+    displacement AND velocity parts, differentiated through dfx_adjoint"""
+    P = _problem(rtol=1e-10, atol=1e-10)
+    P.setup()
+    hs, vs = P.initial_design()
+    tb = P.target_blocks()
+    center = P.geometry.block_centroids(hs, vs)[tb].mean(0)
+    hs = hs.clone().requires_grad_(True)
+    vs = vs.clone().requires_grad_(True)
+    L = P.target_angular_momentum((hs, vs), spin_center=center)
+    L.backward()
+    rng = np.random.default_rng(5)
+    d_hs, d_vs = torch.from_numpy(rng.standard_normal(hs.shape)), torch.from_numpy(rng.standard_normal(vs.shape))
+    eps = 1e-5
+    with torch.no_grad():
+        Lp = P.target_angular_momentum((hs + eps * d_hs, vs + eps * d_vs), spin_center=center)
+        Lm = P.target_angular_momentum((hs - eps * d_hs, vs - eps * d_vs), spin_center=center)
+    fd = ((Lp - Lm) / (2 * eps)).item()
+    an = ((hs.grad * d_hs).sum() + (vs.grad * d_vs).sum()).item()
+    assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)), (fd, an)

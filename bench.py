@@ -311,7 +311,11 @@ def main():
         peak = 148 * 64 * 2 * (cl["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
     achieved = flops_adj / (adj_ms * 1e-3) / 1e12
     roofline = {"kernel": "adjoint_kernel", "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak, "traffic": None, "peak_source": peak_src,
+                "frac": achieved / peak,
+                # DRAM bytes of ONE 1024-design adjoint launch from the `ncu --set full` capture of round 1
+                # (dram__bytes_read.sum 26 GB + dram__bytes_write.sum 332 GB: L2 write-backs of the quadrature scratch,
+                # see DESIGN.md section 4); scaled to this launch's design count; the bound of this kernel is FP64 issue
+                "traffic": 358e9 * B / 1024.0, "traffic_unit": "bytes/launch (ncu, round 1)", "peak_source": peak_src,
                 "note": "HBM and tensor rooflines do not bind this path (10.7 MB and 10 Gflop per design, no dense contraction)",
                 "forward_kernel": {"achieved": flops_fwd / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms}, "adjoint_ms": adj_ms,
                 "steps_fwd_mean": float(st_f["steps"].mean()), "steps_bwd_mean": float(st_b["steps"].mean())}

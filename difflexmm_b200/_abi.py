@@ -8,7 +8,7 @@ import ctypes as C
 
 import numpy as np
 
-DFX_BOND_LIGAMENT, DFX_BOND_LINEARIZED = 0, 1
+DFX_BOND_LIGAMENT, DFX_BOND_LINEARIZED, DFX_BOND_SPRING = 0, 1, 2
 DFX_DRIVE_ZERO, DFX_DRIVE_PULSE, DFX_DRIVE_HARMONIC, DFX_DRIVE_RAMP, DFX_DRIVE_STATIC_PULSE, DFX_DRIVE_TABLE = range(6)
 DFX_LOAD_NONE, DFX_LOAD_RAMP, DFX_LOAD_SECH2 = range(3)
 DFX_MAX_DRIVE_PARAMS = 5

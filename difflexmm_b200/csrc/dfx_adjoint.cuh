@@ -236,8 +236,8 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       BondConst bc = {bondc[b], bondc[NBONDS + b], bondc[2 * NBONDS + b], bondc[3 * NBONDS + b]};
       const double ks = g_ks[ks_pb ? b : 0], ksh = g_ksh[ksh_pb ? b : 0], kr = g_kr[kr_pb ? b : 0];
       BondOut<Dual> o;
-      if (want_q) bond_gradient<Dual, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
-      else bond_gradient<Dual, false>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
+      if (want_q) bond_gradient<Dual, true, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
+      else bond_gradient<Dual, false, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
       if (T.contact) {
         Dual psi1 = wrapT(s1.th - s2.th + (alpha[nd.x] - alpha[NN + nd.y]));
         Dual psi2 = wrapT(s2.th - s1.th + (alpha[nd.y] - alpha[NN + nd.x]));

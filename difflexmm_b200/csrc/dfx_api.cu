@@ -184,6 +184,7 @@ FastPlan plan_fast_adjoint(const DevTopo& T) {
   FastPlan f = {};
   const char* mode = getenv("DFX_ADJOINT_KERNEL");  // "generic" | "notmem" | unset (fast + TMEM)
   if (mode && !strcmp(mode, "generic")) return f;
+  if (T.bond_energy == DFX_BOND_SPRING) return f;  // generic kernels only
   int t = T.n_blocks > (T.n_bonds + 1) / 2 ? T.n_blocks : (T.n_bonds + 1) / 2;
   t = t <= 384 ? 384 : 512;  // the CTA size is a compile-time constant of the kernel (addresses become immediates)
   if (T.n_npb > 4 || T.n_blocks > t || T.n_bonds > 2 * t) return f;
@@ -221,6 +222,7 @@ FastFwdPlan plan_fast_forward(const DevTopo& T) {
   FastFwdPlan f = {};
   const char* mode = getenv("DFX_FORWARD_KERNEL");  // "generic" | "notmem" | unset (fast + TMEM)
   if (mode && !strcmp(mode, "generic")) return f;
+  if (T.bond_energy == DFX_BOND_SPRING) return f;  // generic kernels only
   int t = T.n_blocks > (T.n_bonds + 1) / 2 ? T.n_blocks : (T.n_bonds + 1) / 2;
   t = t <= 384 ? 384 : 512;
   if (T.n_npb > 4 || T.n_blocks > t || T.n_bonds > 2 * t) return f;
@@ -265,7 +267,7 @@ int dfx_topology_n_free(const DfxTopology* t) { return t ? t->dev.n_free : -1; }
 int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out) {
   if (!d || !out) return fail(DFX_ERR_INVALID, "NULL argument");
   if (d->n_blocks <= 0 || d->n_npb < 2 || d->n_bonds < 0) return fail(DFX_ERR_INVALID, "bad sizes");
-  if (d->bond_energy != DFX_BOND_LIGAMENT && d->bond_energy != DFX_BOND_LINEARIZED)
+  if (d->bond_energy != DFX_BOND_LIGAMENT && d->bond_energy != DFX_BOND_LINEARIZED && d->bond_energy != DFX_BOND_SPRING)
     return fail(DFX_ERR_UNSUPPORTED, "unknown bond energy %d", d->bond_energy);
   if (d->drive_kind < DFX_DRIVE_ZERO || d->drive_kind > DFX_DRIVE_TABLE)
     return fail(DFX_ERR_UNSUPPORTED, "unknown drive kind %d", d->drive_kind);

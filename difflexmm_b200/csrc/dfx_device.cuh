@@ -226,7 +226,8 @@ __device__ __forceinline__ bool contact_term(T psi, double tmin, double tcut, do
   return false;
 }
 
-template <class T, bool PARAMS>
+// EXT: also compile the bond kinds that only the generic kernels support (DFX_BOND_SPRING)
+template <class T, bool PARAMS, bool EXT = false>
 __device__ __forceinline__ void bond_gradient(int energy_kind, const BlockState<T>& b1, const BlockState<T>& b2,
                                               double r1x, double r1y, double r2x, double r2y, const BondConst& bc,
                                               double ks, double ksh, double kr, BondOut<T>& o) {
@@ -273,6 +274,17 @@ __device__ __forceinline__ void bond_gradient(int energy_kind, const BlockState<
       o.gr0[1] = gdy + dE_dL0 * (bc.r0y / L0) - M * (bc.r0x / L0sq);
       o.gks = ext * ext * 0.5;
       o.gksh = gam * gam * (0.5 * L0sq);
+    }
+  } else if (EXT && energy_kind == DFX_BOND_SPRING) {
+    // zero-length spring (reference energy.py:49-66): E = ks |dU|^2 / 2 (+ kr dtheta^2 / 2 below)
+    gdx = dUx * ks;
+    gdy = dUy * ks;
+    tq = make_T<T>(0.0, 0.0);
+    if (PARAMS) {
+      o.gr0[0] = make_T<T>(0.0, 0.0);
+      o.gr0[1] = make_T<T>(0.0, 0.0);
+      o.gks = (dUx * dUx + dUy * dUy) * 0.5;
+      o.gksh = make_T<T>(0.0, 0.0);
     }
   } else {
     const double iL0 = 1.0 / L0;

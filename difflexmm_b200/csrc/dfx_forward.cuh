@@ -165,7 +165,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
       BondConst bc = {bondc[b], bondc[NBONDS + b], bondc[2 * NBONDS + b], bondc[3 * NBONDS + b]};
       const double ks = g_ks[a.p.k_per_bond[0] ? b : 0], ksh = g_ksh[a.p.k_per_bond[1] ? b : 0], kr = g_kr[a.p.k_per_bond[2] ? b : 0];
       BondOut<double> o;
-      bond_gradient<double, false>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
+      bond_gradient<double, false, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
       if (T.contact) {
         // void angles depend on the two rotations only
         const double psi1 = wrap_value(alpha[nd.x] - alpha[NN + nd.y] + s1.th - s2.th);

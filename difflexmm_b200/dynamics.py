@@ -114,10 +114,21 @@ def lower_params(spec, drive, control_params: ControlParams, batch: Optional[int
     n_entries += n
     if gp.block_centroids is not None:
         n_entries += split(gp.block_centroids, 2)[2]
-    leaves["reference_vector"], _, n = split(bp.reference_vector, 2)
-    n_entries += n
+    spring = spec.bond_energy == _abi.DFX_BOND_SPRING
+    if spring != (not hasattr(bp, "reference_vector")):
+        raise TypeError("stretching_torsional_spring_energy takes StretchingTorsionalSpringParams, the ligament energies "
+                        "take LigamentParams (reference utils.py:62-94)")
+    if spring:
+        # the reference pytree has neither leaf; libdfx wants valid pointers and ignores them (include/dfx.h)
+        leaves["reference_vector"] = torch.tensor([[1.0, 0.0]], dtype=_F64, device=device).repeat(spec.n_bonds, 1)
+    else:
+        leaves["reference_vector"], _, n = split(bp.reference_vector, 2)
+        n_entries += n
     pb = []
     for name in ("k_stretch", "k_shear", "k_rot"):
+        if spring and name == "k_shear":
+            leaves[name] = torch.zeros((), dtype=_F64, device=device)
+            continue
         k = _as_t(getattr(bp, name), device)
         is_pb = (name in per_bond) if B is not None else (k.dim() == 1)
         if is_pb:

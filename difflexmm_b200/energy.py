@@ -26,6 +26,9 @@ class _BondEnergy:
 ligament_energy = _BondEnergy("ligament_energy", _abi.DFX_BOND_LIGAMENT)
 #: linearised ligament (reference `energy.py:99-117`)
 ligament_energy_linearized = _BondEnergy("ligament_energy_linearized", _abi.DFX_BOND_LINEARIZED)
+#: zero-length stretching + torsional spring between coincident nodes (reference `energy.py:49-66`); bond_params must
+#: be `utils.StretchingTorsionalSpringParams`.  Runs on the generic kernels.
+stretching_torsional_spring_energy = _BondEnergy("stretching_torsional_spring_energy", _abi.DFX_BOND_SPRING)
 
 
 class BlockEnergy:
@@ -40,8 +43,8 @@ class StrainEnergy(BlockEnergy):
     def __init__(self, bond_connectivity, bond_energy_fn):
         if not isinstance(bond_energy_fn, _BondEnergy):
             raise TypeError(
-                "bond_energy_fn must be difflexmm_b200.energy.ligament_energy or "
-                "ligament_energy_linearized; arbitrary Python energies cannot run inside the CUDA solver")
+                "bond_energy_fn must be difflexmm_b200.energy.ligament_energy, ligament_energy_linearized or "
+                "stretching_torsional_spring_energy; arbitrary Python energies cannot run inside the CUDA solver")
         self.bond_connectivity = np.asarray(bond_connectivity, dtype=np.int64).reshape(-1, 2)
         self.bond_kind = bond_energy_fn.kind
 

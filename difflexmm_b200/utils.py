@@ -35,7 +35,14 @@ class LigamentParams(NamedTuple):
     reference_vector: Any  # (n_bonds, 2)
 
 
-BondParams = Union[LigamentParams]
+class StretchingTorsionalSpringParams(NamedTuple):
+    """reference `utils.py:80-91`: zero-length springs (`energy.stretching_torsional_spring_energy`)."""
+
+    k_stretch: Any
+    k_rot: Any
+
+
+BondParams = Union[LigamentParams, StretchingTorsionalSpringParams]
 
 
 class ContactParams(NamedTuple):
@@ -71,6 +78,7 @@ class ControlParams(NamedTuple):
 # ------------------------------------------------------------------------------------------------
 _REFERENCE_MODULE = "difflexmm.utils"
 _TUPLE_TYPES = {"SolutionData": SolutionData, "GeometricalParams": GeometricalParams, "LigamentParams": LigamentParams,
+                "StretchingTorsionalSpringParams": StretchingTorsionalSpringParams,
                 "ContactParams": ContactParams, "MechanicalParams": MechanicalParams, "ControlParams": ControlParams}
 
 

@@ -38,8 +38,12 @@ extern "C" {
 #endif
 
 /* ---- vocabulary ------------------------------------------ */
-enum { DFX_BOND_LIGAMENT = 0,     /* energy.py:158-176 ligament_energy            */
-       DFX_BOND_LINEARIZED = 1 }; /* energy.py:99-117  ligament_energy_linearized */
+enum { DFX_BOND_LIGAMENT = 0,    /* energy.py:158-176 ligament_energy            */
+       DFX_BOND_LINEARIZED = 1,  /* energy.py:99-117  ligament_energy_linearized */
+       DFX_BOND_SPRING = 2 };    /* energy.py:49-66   stretching_torsional_spring_energy: zero-length spring between
+                                    coincident nodes, k_stretch |dU|^2 / 2 + k_rot dtheta^2 / 2.  The k_shear and
+                                    reference_vector leaves are ignored (they must still be valid pointers; their
+                                    cotangents are zero).  Generic kernels only. */
 
 /* constrained-DOF drive u_c(t) = vec0[c]*s0(t) + vec1[c]*s1(t); parameter order fixed */
 enum {

@@ -73,13 +73,15 @@ def run_case(name, *, n_blocks, n_npb, bonds, cons, bond_energy, use_contact, dr
             c0, c1 = load["consts"]
             loading_fn = lambda state, t: 2 * c0 / c1 ** 2 * torch.cosh(t / c1 - 3) ** (-2) * torch.tanh(3 - t / c1)  # noqa: E731
 
-    prob = L.Problem(n_blocks, n_npb, bonds, cons, bond_energy={0: "ligament", 1: "linearized"}[bond_energy],
+    prob = L.Problem(n_blocks, n_npb, bonds, cons, bond_energy={0: "ligament", 1: "linearized", 2: "spring"}[bond_energy],
                      use_contact=use_contact, constrained_DOFs_fn=cfn, loaded_DOF_ids=loaded, loading_fn=loading_fn,
                      damped_blocks=damped_blocks)
     P = dict(block_centroids=block_centroids, centroid_node_vectors=leaves["centroid_node_vectors"],
              k_stretch=leaves["k_stretch"], k_shear=leaves["k_shear"], k_rot=leaves["k_rot"],
              reference_vector=leaves["reference_vector"], inertia=leaves["inertia"],
              constraint_params={n: T(drive_params[n]) for n in names}, loading_params={})
+    if bond_energy == _abi.DFX_BOND_SPRING:  # StretchingTorsionalSpringParams has no k_shear / reference_vector leaves
+        del P["k_shear"], P["reference_vector"]
     if damped_blocks is not None:
         P["damping"] = leaves["damping"]
     if use_contact:
@@ -155,6 +157,37 @@ def quad_case(name, n1, n2, *, contact_window, noise, n_t, t_end, rtol, atol, se
              drive_params=dict(amplitude=7.5, loading_rate=30., input_delay=0.1 / 30), load=None,
              damped_blocks=np.arange(geo.n_blocks), leaves=leaves, block_centroids=cent,
              ts=np.linspace(0, t_end, n_t), rtol=rtol, atol=atol, density_leaf=T(rho), g_mode=g_mode)
+
+
+def spring_case(name, n1, n2, *, n_t, t_end, rtol, atol, seed=4):
+    """quad lattice whose bonds are zero-length stretching / torsional springs (energy.py:49-66,
+    StretchingTorsionalSpringParams utils.py:80-91): no k_shear / reference_vector leaves in the reference pytree;
+    per-bond k_rot leaf, harmonic drive, scalar damping."""
+    torch.manual_seed(seed)
+    geo = QuadGeometry(n1, n2, spacing=15., bond_length=2.25)
+    bc, cnvf, bonds, refv = geo.get_parametrization()
+    hs, vs = geo.get_design_from_rotated_square(20 * math.pi / 180)
+    hs = hs + 0.3 * torch.randn_like(hs)
+    vs = vs + 0.3 * torch.randn_like(vs)
+    cnv, cent = cnvf(hs, vs), bc(hs, vs)
+    mid = (n2 // 2) * n1
+    pairs = np.array([[mid, 0], [mid, 1], [mid, 2], [0, 0], [0, 1], [0, 2], [n1 - 1, 0], [n1 - 1, 1], [n1 - 1, 2]])
+    cons = pairs[:, 0] * 3 + pairs[:, 1]
+    free, _, _ = DOFsInfo(geo.n_blocks, pairs)
+    lv = np.zeros(len(cons))
+    lv[0] = 1
+    rho = 6.18e-9
+    inertia = compute_inertia(cnv, rho).reshape(-1)[free]
+    nb = len(bonds())
+    # k_shear / reference_vector: placeholders required by the libdfx ABI, ignored by DFX_BOND_SPRING
+    leaves = dict(centroid_node_vectors=cnv, reference_vector=torch.tensor([[1., 0.]], dtype=F64).repeat(nb, 1),
+                  k_stretch=T(2.5), k_shear=T(0.), k_rot=1.5 * (1 + 0.2 * torch.rand(nb, dtype=F64)),
+                  damping=T(2.0e-5), inertia=inertia)
+    run_case(name, n_blocks=geo.n_blocks, n_npb=4, bonds=bonds(), cons=cons, bond_energy=_abi.DFX_BOND_SPRING, use_contact=False,
+             drive_kind=_abi.DFX_DRIVE_HARMONIC, drive_vec0=lv, drive_vec1=None,
+             drive_params=dict(amplitude=3., loading_rate=40., input_delay=0.002), load=None,
+             damped_blocks=np.arange(geo.n_blocks), leaves=leaves, block_centroids=cent,
+             ts=np.linspace(0, t_end, n_t), rtol=rtol, atol=atol, density_leaf=T(rho), g_mode="generic")
 
 
 def kagome_case(name, n1, n2, *, n_t, t_end, rtol, atol, seed=1):
@@ -260,6 +293,7 @@ CASES = {
     "static_pulse_4x4": lambda: static_pulse_case("static_pulse_4x4", 4, 4, n_t=3, rtol=1e-9, atol=1e-8),
     "tensile_linearized": lambda: tensile_case("tensile_linearized", 2, 1, n_t=4, t_end=60.),
     "tensile_ligament": lambda: tensile_case("tensile_ligament", 2, 0, n_t=4, t_end=60.),
+    "springs_4x3": lambda: spring_case("springs_4x3", 4, 3, n_t=4, t_end=0.02, rtol=1e-8, atol=1e-6),
 }
 
 if __name__ == "__main__":

@@ -80,6 +80,14 @@ def ligament_energy_linearized(nodal_DOFs, reference_vector, k_stretch=1., k_she
     return k_stretch * (axial * l0) ** 2 / 2 + k_shear * (shear * l0) ** 2 / 2 + k_rot * dRot ** 2 / 2
 
 
+# ------------------------------------------------------------------ energy.py:49-66
+def stretching_torsional_spring_energy(nodal_DOFs, k_stretch=1., k_rot=1.):
+    DOFs1, DOFs2 = nodal_DOFs
+    dU = DOFs2[:, :2] - DOFs1[:, :2]
+    dRot = DOFs2[:, 2] - DOFs1[:, 2]
+    return k_stretch * (dU * dU).sum(-1) / 2 + k_rot * dRot ** 2 / 2
+
+
 # ------------------------------------------------------------------ energy.py:179-197 (+ jax-md smap.bond)
 def strain_energy_bonds(node_displacements, bond_connectivity, bond_energy_fn, **bond_params):
     Ua = node_displacements[bond_connectivity[:, 0]]
@@ -126,7 +134,7 @@ class Problem:
     """Static description of one solver instance (what `setup_dynamic_solver` closes over).
 
     bond_connectivity (n_bonds,2) int64; free/constrained ids per geometry.py:163-178;
-    `bond_energy`: 'ligament' | 'linearized'; `use_contact`; `constrained_DOFs_fn(t, **cp)`
+    `bond_energy`: 'ligament' | 'linearized' | 'spring'; `use_contact`; `constrained_DOFs_fn(t, **cp)`
     torch callable returning scalar or (n_constrained,); `loading_fn(state, t, **lp)`;
     loaded ids / damped ids global DOF numbers.
     """
@@ -140,7 +148,9 @@ class Problem:
         mask = torch.ones(3 * n_blocks, dtype=torch.bool)
         mask[self.constrained] = False
         self.free = torch.nonzero(mask)[:, 0]
-        self.bond_energy_fn = {"ligament": ligament_energy, "linearized": ligament_energy_linearized}[bond_energy]
+        self.bond_energy_fn = {"ligament": ligament_energy, "linearized": ligament_energy_linearized,
+                               "spring": stretching_torsional_spring_energy}[bond_energy]
+        self.spring = bond_energy == "spring"
         self.use_contact = use_contact
         self.constrained_DOFs_fn = constrained_DOFs_fn or (lambda t, **kw: torch.zeros((), dtype=F64))
         self.loaded = None if loaded_DOF_ids is None else torch.as_tensor(loaded_DOF_ids, dtype=torch.int64)
@@ -165,9 +175,13 @@ class Problem:
     def energy(self, block_displacement, P):
         cnv = P["centroid_node_vectors"]
         node_disp = block_to_node_kinematics(block_displacement, cnv)
-        E = strain_energy_bonds(node_disp.reshape(-1, 3), self.bonds, self.bond_energy_fn,
-                                k_stretch=P["k_stretch"], k_shear=P["k_shear"], k_rot=P["k_rot"],
-                                reference_vector=P["reference_vector"])
+        if self.spring:  # StretchingTorsionalSpringParams: k_stretch, k_rot only (utils.py:80-91)
+            E = strain_energy_bonds(node_disp.reshape(-1, 3), self.bonds, self.bond_energy_fn,
+                                    k_stretch=P["k_stretch"], k_rot=P["k_rot"])
+        else:
+            E = strain_energy_bonds(node_disp.reshape(-1, 3), self.bonds, self.bond_energy_fn,
+                                    k_stretch=P["k_stretch"], k_shear=P["k_shear"], k_rot=P["k_rot"],
+                                    reference_vector=P["reference_vector"])
         if self.use_contact:
             current = P["block_centroids"][:, None] + cnv + node_disp[:, :, :2]
             E = E + contact_energy(void_angles(current, self.bonds), P["min_angle"], P["cutoff_angle"],

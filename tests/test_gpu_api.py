@@ -381,3 +381,57 @@ def test_angular_momentum_objective_gradient_matches_finite_differences():
     fd = ((Lp - Lm) / (2 * eps)).item()
     an = ((hs.grad * d_hs).sum() + (vs.grad * d_vs).sum()).item()
     assert abs(fd - an) <= 2e-5 * max(abs(fd), abs(an)), (fd, an)
+
+
+def test_zero_length_spring_energy_through_the_api():
+    """stretching_torsional_spring_energy + StretchingTorsionalSpringParams (reference energy.py:49-66,
+    utils.py:80-91) through setup_dynamic_solver, against the C++ oracle; gradient w.r.t. both stiffnesses"""
+    from difflexmm_b200 import _abi
+    from difflexmm_b200.dynamics import lower_params, setup_dynamic_solver
+    from difflexmm_b200.energy import build_strain_energy, stretching_torsional_spring_energy
+    from difflexmm_b200.geometry import QuadGeometry
+    from difflexmm_b200.loading import pulse_drive
+    from difflexmm_b200.utils import (ControlParams, GeometricalParams, LigamentParams, MechanicalParams,
+                                      StretchingTorsionalSpringParams)
+    from oracle import Oracle
+    geo = QuadGeometry(5, 4, spacing=15.0, bond_length=2.25)
+    bc, cnvf, bonds, refv = geo.get_parametrization()
+    hs, vs = geo.get_design_from_rotated_square(20 * math.pi / 180)
+    pairs = np.array([[10, 0], [10, 1], [10, 2], [0, 0], [0, 1], [0, 2], [4, 0], [4, 1], [4, 2]])
+    vec = np.zeros(len(pairs))
+    vec[0] = 1.0
+    solve = setup_dynamic_solver(geo, build_strain_energy(bonds(), stretching_torsional_spring_energy),
+                                 constrained_block_DOF_pairs=pairs, constrained_DOFs_fn=pulse_drive(vec),
+                                 damped_blocks=np.arange(geo.n_blocks), rtol=1e-8, atol=1e-6)
+    ks = torch.tensor(2.5, dtype=torch.float64, device="cuda", requires_grad=True)
+    kr = torch.tensor(1.5, dtype=torch.float64, device="cuda", requires_grad=True)
+
+    def params(bond_params):
+        return ControlParams(
+            geometrical_params=GeometricalParams(block_centroids=bc(hs, vs), centroid_node_vectors=cnvf(hs, vs)),
+            mechanical_params=MechanicalParams(bond_params=bond_params, density=6.18e-9, damping=2.0e-5),
+            constraint_params=dict(amplitude=3.0, loading_rate=40.0, input_delay=0.002))
+
+    cp = params(StretchingTorsionalSpringParams(k_stretch=ks, k_rot=kr))
+    ts = torch.linspace(0, 0.02, 5, dtype=torch.float64)
+    fields = solve(torch.zeros(2, geo.n_blocks, 3, dtype=torch.float64), ts, cp)
+    (fields[:, 1] ** 2).sum().backward()
+    s = solve.solver
+    assert s.spec.bond_energy == _abi.DFX_BOND_SPRING
+    leaves, pb, dpd, aug = lower_params(s.spec, s.drive, cp, None, "cpu")
+    assert aug == 4 * s.spec.n_free + 1 + (2 * geo.n_blocks + 8 * geo.n_blocks) + 2 + 1 + 1 + s.spec.n_free + 3  # no k_shear / reference_vector
+    orc = Oracle(s.spec)
+    lv = {k: v.detach().cpu().numpy() for k, v in leaves.items()}
+    ph = orc.params(1, lv, pb, dpd)
+    y0 = np.zeros(2 * s.spec.n_free)
+    ys_h, _ = orc.forward(ph, y0, ts.numpy(), 1e-8, 1e-6)
+    fields_h = orc.expand_fields(ph, ys_h, ts.numpy())
+    assert rel_l2(fields.detach().cpu().numpy(), fields_h[0]) <= 1e-6
+    g = np.zeros_like(ys_h)
+    g[:, :, s.spec.n_free:] = 2 * ys_h[:, :, s.spec.n_free:]
+    _, _, gr_h, _ = orc.adjoint(ph, ys_h, ts.numpy(), g, 1e-8, 1e-6, aug)
+    assert abs(ks.grad.item() - gr_h["k_stretch"][0]) <= 1e-5 * abs(gr_h["k_stretch"][0])
+    assert abs(kr.grad.item() - gr_h["k_rot"][0]) <= 1e-5 * abs(gr_h["k_rot"][0])
+    with pytest.raises(TypeError):  # ligament parameters with the spring energy
+        solve(torch.zeros(2, geo.n_blocks, 3, dtype=torch.float64), ts,
+              params(LigamentParams(k_stretch=1.0, k_shear=1.0, k_rot=1.0, reference_vector=refv())))

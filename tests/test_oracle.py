@@ -27,7 +27,8 @@ def test_oracle_matches_literal_golden(name):
     assert rel_l2(ys[0], c.ref["ys"]) < 1e-9
     y0b, tsb, gr, sb = orc.adjoint(ps, c.ref["ys"][None], c.ts, c.g[None], c.rtol, c.atol, aug_size=c.aug_size)
     assert sb["status"][0] == 0
-    assert abs(int(sb["steps"][0]) - int(c.ref["bwd_steps"])) <= 3
+    # borderline accept / reject decisions flip on round-off: the count is a diagnostic, the cotangents are the check
+    assert abs(int(sb["steps"][0]) - int(c.ref["bwd_steps"])) <= max(3, int(0.005 * c.ref["bwd_steps"]))
     assert rel_l2(y0b[0], c.ref["y0_bar"]) < 1e-7
     assert rel_l2(tsb[0], c.ref["ts_bar"]) < 1e-6
     for k, v in gr.items():

@@ -61,6 +61,7 @@ struct AdjArgs {
   double* scratch; long long scratch_per_design;
   // quadrature layout (entries)
   int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, nq;
+  int group;  // CL = 2: CTAs per design
 };
 
 struct QuadCtx {
@@ -111,7 +112,7 @@ struct ScalCtx {
 };
 constexpr int kRedDoublesDev = 40;  // reduction scratch at the start of shared memory (kRedDoubles of dfx_api.cu)
 constexpr int kScalDoubles = 2 * NSCAL + 5 * NSCAL * SCW;                 // Sq0, Sqnew + per-warp partials
-constexpr int kClusterReserve = 2 * kMaxCluster + 5 * NSCAL * kMaxCluster;  // cluster-sum partials + CTA totals
+constexpr int kClusterReserve = 8 + 2 * kMaxGroup + 5 * NSCAL * kMaxGroup;  // barrier counter, group-sum partials, CTA totals
 __device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, int which, double partial) {
   // most warps contribute nothing to the sparse scalars (contact, drive, t0): skip their shuffles
   const double v = __any_sync(0xffffffffu, partial != 0.0) ? warp_sum(partial) : 0.0;
@@ -139,25 +140,28 @@ __device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, 
   }
 }
 
-// CL = 0: one CTA per design.  CL = 1: one thread-block cluster per design (see forward_kernel).
+// CL = 0: one CTA per design.  CL = 1: one thread-block cluster per design.  CL = 2: a group of co-resident CTAs of a
+// cooperative launch per design (see forward_kernel).
 template <int CL>
 __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__ AdjArgs a) {
   extern __shared__ double smem[];
   const DevTopo& T = a.topo;
   const Tableau& tab = a.tab;
-  const int crank = CL ? (int)cluster_ctarank() : 0, ncta = CL ? (int)cluster_nctarank() : 1;
+  const int ncta = CL == 1 ? (int)cluster_nctarank() : (CL == 2 ? a.group : 1);
+  const int crank = CL == 1 ? (int)cluster_ctarank() : (CL == 2 ? (int)(blockIdx.x % ncta) : 0);
   const int design = blockIdx.x / ncta;
   const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
   const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, cnwarp = (blockDim.x + 31) >> 5;
-  int cpar = 0;
   const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;
   const int NQ = a.nq;
   double* red = smem;
   double* scratch = a.scratch ? a.scratch + (long long)design * a.scratch_per_design : nullptr;
-  double* cred = scratch;  // CL: cluster-sum partials at the start of the scratch ...
-  double* ctot = scratch + 2 * kMaxCluster;  // ... followed by the per-CTA totals of the scalar leaves [5][NSCAL][kMaxCluster]
-  auto SYNC = [&]() { if (CL) cluster_sync_all(); else __syncthreads(); };
-  auto SUM = [&](double v) { return CL ? cluster_sum(v, red, cred, crank, ncta, cpar) : block_sum(v, red); };
+  // CL: the scratch starts with the barrier counter, the group-sum partials and the per-CTA totals of the scalar
+  // leaves [5][NSCAL][kMaxGroup] (kClusterReserve doubles)
+  GroupCtx grp = {CL, crank, ncta, (unsigned long long*)scratch, 0ULL, scratch + 8, 0};
+  double* ctot = scratch + 8 + 2 * kMaxGroup;
+  auto SYNC = [&]() { if (CL) group_sync(grp); else __syncthreads(); };
+  auto SUM = [&](double v) { return CL ? group_sum(v, red, grp) : block_sum(v, red); };
   auto P = [&](int i) -> double* {
     const long long o = a.place.off[i];
     return o >= 0 ? smem + o : scratch + (-(o + 1));
@@ -388,14 +392,14 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
           if (!((mask >> k) & 1)) continue;
           double v = lane < cnwarp ? sc.wk1[(k * NSCAL + w) * SCW + lane] : 0.0;
           v = warp_sum(v);
-          if (lane == 0) ctot[(k * NSCAL + w) * kMaxCluster + crank] = v;
+          if (lane == 0) ctot[(k * NSCAL + w) * kMaxGroup + crank] = v;
         }
-      cluster_sync_all();
+      group_sync(grp);
     }
   };
   auto wtotal = [&](int k, int which) {  // whole warp
     double v;
-    if (CL) v = lane < ncta ? ctot[(k * NSCAL + which) * kMaxCluster + lane] : 0.0;
+    if (CL) { v = 0.0; for (int r = lane; r < ncta; r += 32) v += ctot[(k * NSCAL + which) * kMaxGroup + r]; }
     else v = lane < cnwarp ? sc.wk1[(k * NSCAL + which) * SCW + lane] : 0.0;
     return warp_sum(v);
   };

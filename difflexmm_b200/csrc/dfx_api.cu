@@ -35,6 +35,8 @@ int fail(int code, const char* fmt, ...) {
 constexpr size_t kSmemBytes = 232448;  // 227 KB: the opt-in maximum of one CTA on sm_100
 constexpr int kRedDoubles = 40;
 static_assert(kRedDoubles == kRedDoublesDev, "shared-memory reduction area");
+constexpr int kGroupMinBonds = 8192;  // lattices with at least this many bonds default to the cooperative group mode
+constexpr int kGroupDefault = 64;     // CTAs per design in that mode (measured on 100x100: 64, 100 and 148 CTAs take the same time)
 constexpr int kScratchSlots = 256;  // >= %nsmid of any sm_100 part: SM-indexed scratch of the fast adjoint kernel
 
 template <class T>
@@ -157,6 +159,37 @@ int pick_cluster(const DevTopo& T, int batch, int sm_count) {
   if (cl > kMaxCluster) cl = kMaxCluster;
   while (cl & (cl - 1)) cl &= cl - 1;  // power of two
   return cl;
+}
+
+// Multi-CTA plan of the generic kernels: mode 0 = one CTA per design, 1 = thread-block cluster, 2 = group of
+// co-resident CTAs with a software barrier (cooperative launch).  DFX_GROUP=<n> forces mode 2 with n CTAs per design.
+struct MultiCta { int mode, ncta; };
+MultiCta pick_multi_cta(const DevTopo& T, int batch, int sm_count) {
+  if (const char* e = std::getenv("DFX_GROUP")) {
+    int n = std::atoi(e);
+    if (n > kMaxGroup) n = kMaxGroup;
+    if ((long long)n * batch > sm_count) n = sm_count / batch;
+    if (n > 1) return {2, n};
+    return {0, 1};
+  }
+  if (!std::getenv("DFX_CLUSTER") && T.n_bonds >= kGroupMinBonds && 2LL * kMaxCluster * batch <= sm_count) {
+    // a lattice this large keeps more SMs busy than a cluster can span
+    int n = kGroupDefault;
+    if ((long long)n * batch > sm_count) n = sm_count / batch;
+    if (n > kMaxCluster) return {2, n};
+  }
+  const int cl = pick_cluster(T, batch, sm_count);
+  return {cl > 1 ? 1 : 0, cl};
+}
+
+template <class Kernel, class Args>
+cudaError_t launch_group(Kernel kernel, int batch, int ncta, size_t smem, cudaStream_t stream, Args& args, double* scratch,
+                         long long scratch_per_design) {
+  // zero every design's barrier counter (first 8 bytes of its scratch slice)
+  cudaError_t e = cudaMemset2DAsync(scratch, (size_t)scratch_per_design * sizeof(double), 0, sizeof(unsigned long long), batch, stream);
+  if (e != cudaSuccess) return e;
+  void* params[] = {(void*)&args};
+  return cudaLaunchCooperativeKernel((const void*)kernel, dim3((unsigned)batch * ncta), dim3(512), params, smem, stream);
 }
 
 template <class Kernel, class Args>
@@ -385,7 +418,7 @@ size_t dfx_forward_workspace_bytes(const DfxTopology* t, int batch) {
   size_t smem;
   FastFwdPlan f = plan_fast_forward(t->dev);
   forward_sizes(t->dev, sz);
-  plan(sz, off, &smem, &g, f.ok ? 1 : pick_cluster(t->dev, batch, t->sm_count));
+  plan(sz, off, &smem, &g, f.ok ? 1 : pick_multi_cta(t->dev, batch, t->sm_count).ncta);
   const long long fast = f.ok ? (long long)F_NSLOT * f.threads + 32 : 0;
   if (fast > g) g = fast;
   return (size_t)g * sizeof(double) * (size_t)batch;
@@ -402,7 +435,7 @@ size_t dfx_adjoint_workspace_bytes(const DfxTopology* t, int batch) {
   long long sz[AA_COUNT], off[AA_COUNT], g;
   size_t smem;
   FastPlan f = plan_fast_adjoint(t->dev);
-  const int cluster = f.ok ? 1 : pick_cluster(t->dev, batch, t->sm_count);
+  const int cluster = f.ok ? 1 : pick_multi_cta(t->dev, batch, t->sm_count).ncta;
   adjoint_sizes(t->dev, q, sz, cluster);
   plan(sz, off, &smem, &g, cluster);
   // worst case of the two kernels (the fast one assumes S_TOTAL slots with no TMEM)
@@ -425,7 +458,8 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
   long long sz[FA_COUNT], g;
   size_t smem;
   const FastFwdPlan fp = plan_fast_forward(t->dev);
-  const int cluster = fp.ok ? 1 : pick_cluster(t->dev, batch, t->sm_count);
+  const MultiCta mc = fp.ok ? MultiCta{0, 1} : pick_multi_cta(t->dev, batch, t->sm_count);
+  const int cluster = mc.ncta;
   forward_sizes(t->dev, sz);
   plan(sz, a.place.off, &smem, &g, cluster);
   a.y0 = y0; a.y0_bstride = y0_bstride; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t;
@@ -461,8 +495,10 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
   } else {
     const int threads = pick_threads(t->dev, opt ? opt->threads : 0);
     if (cluster > 1) {
-      cudaError_t le = launch_cluster(forward_kernel<1>, batch, cluster, 512, smem, stream, a);
-      if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "forward_kernel cluster launch (%d CTAs) failed: %s", cluster, cudaGetErrorString(le)); }
+      a.group = cluster;
+      cudaError_t le = mc.mode == 2 ? launch_group(forward_kernel<2>, batch, cluster, smem, stream, a, a.scratch, a.scratch_per_design)
+                                    : launch_cluster(forward_kernel<1>, batch, cluster, 512, smem, stream, a);
+      if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "forward_kernel multi-CTA launch (%d CTAs per design) failed: %s", cluster, cudaGetErrorString(le)); }
     } else {
       forward_kernel<0><<<batch, threads, smem, stream>>>(a);
     }
@@ -528,7 +564,8 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   long long sz[AA_COUNT], g;
   size_t smem;
   const FastPlan fp = plan_fast_adjoint(T);
-  const int cluster = fp.ok ? 1 : pick_cluster(T, batch, t->sm_count);
+  const MultiCta mc = fp.ok ? MultiCta{0, 1} : pick_multi_cta(T, batch, t->sm_count);
+  const int cluster = mc.ncta;
   adjoint_sizes(T, q, sz, cluster);
   plan(sz, a.place.off, &smem, &g, cluster);
   a.ys = ys; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t; a.g = g_;
@@ -589,10 +626,13 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
     }
     const int threads = pick_threads(T, opt ? opt->threads : 0);
     cudaError_t le = cudaSuccess;
-    if (cluster > 1) le = launch_cluster(adjoint_kernel<1>, batch, cluster, 512, (size_t)(kRedDoubles + kScalDoubles) * sizeof(double), stream, a);
+    a.group = cluster;
+    const size_t smem_multi = (size_t)(kRedDoubles + kScalDoubles) * sizeof(double);
+    if (mc.mode == 2) le = launch_group(adjoint_kernel<2>, batch, cluster, smem_multi, stream, a, a.scratch, a.scratch_per_design);
+    else if (cluster > 1) le = launch_cluster(adjoint_kernel<1>, batch, cluster, 512, smem_multi, stream, a);
     else adjoint_kernel<0><<<batch, threads, smem, stream>>>(a);
     if (gtmp) cudaFreeAsync(gtmp, stream);
-    if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "adjoint_kernel cluster launch (%d CTAs) failed: %s", cluster, cudaGetErrorString(le)); }
+    if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "adjoint_kernel multi-CTA launch (%d CTAs per design) failed: %s", cluster, cudaGetErrorString(le)); }
   }
   cudaError_t e = cudaGetLastError();
   if (own_ws) cudaFreeAsync(a.scratch, stream);

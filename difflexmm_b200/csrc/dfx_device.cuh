@@ -453,17 +453,46 @@ __device__ __forceinline__ unsigned cluster_nctarank() {
 __device__ __forceinline__ void cluster_sync_all() {
   asm volatile("barrier.cluster.arrive.release.aligned;\n\tbarrier.cluster.wait.acquire.aligned;" ::: "memory");
 }
-constexpr int kMaxCluster = 16;
-// Sum over every thread of the cluster; identical (bitwise) on all CTAs, so control flow stays uniform.
-// cred: [2][kMaxCluster] doubles in the design's global scratch; `parity` alternates between calls.
-__device__ __forceinline__ double cluster_sum(double v, double* red, double* cred, int rank, int ncta, int& parity) {
+constexpr int kMaxCluster = 16;   // CTAs of a thread-block cluster (non-portable maximum)
+constexpr int kMaxGroup = 160;    // CTAs cooperating on one design in either multi-CTA mode (>= SM count)
+
+// Multi-CTA mode of the generic kernels.  MODE 1: thread-block cluster (hardware barrier, <= 16 CTAs).
+// MODE 2: a group of co-resident CTAs of a cooperative launch with a software barrier (monotonic arrival counter in
+// global memory; thread 0 of every CTA arrives, spins and fences, the rest wait at the CTA barrier -- the structure of
+// cooperative_groups' grid sync, but per group of CTAs so that several designs can share the GPU).
+struct GroupCtx {
+  int mode, rank, ncta;
+  unsigned long long* counter;  // MODE 2: arrival counter of this group (zeroed before the launch)
+  unsigned long long epoch;     // number of barriers passed
+  double* cred;                 // [2][kMaxGroup] partial sums
+  int parity;
+};
+
+__device__ __forceinline__ void group_sync(GroupCtx& g) {
+  if (g.mode == 1) { cluster_sync_all(); return; }
+  __syncthreads();
+  if (threadIdx.x == 0) {
+    __threadfence();  // release: this CTA's writes are visible before its arrival
+    atomicAdd(g.counter, 1ULL);
+    const unsigned long long target = (g.epoch + 1) * (unsigned long long)g.ncta;
+    unsigned long long spins = 0;
+    while (*(volatile unsigned long long*)g.counter < target)
+      if (++spins > (1ULL << 28)) __trap();  // a CTA of the group never arrived: fail the launch instead of hanging
+    __threadfence();  // acquire (invalidates this SM's L1)
+  }
+  g.epoch++;
+  __syncthreads();
+}
+
+// Sum over every thread of the group; identical (bitwise) on all CTAs, so control flow stays uniform.
+__device__ __forceinline__ double group_sum(double v, double* red, GroupCtx& g) {
   const double part = block_sum(v, red);
-  if (threadIdx.x == 0) cred[parity * kMaxCluster + rank] = part;
-  cluster_sync_all();
+  if (threadIdx.x == 0) g.cred[g.parity * kMaxGroup + g.rank] = part;
+  group_sync(g);
   double s = 0.0;
-  for (int r = 0; r < ncta; ++r) s += cred[parity * kMaxCluster + r];
-  parity ^= 1;
-  return s;
+  for (int r = threadIdx.x & 31; r < g.ncta; r += 32) s += g.cred[g.parity * kMaxGroup + r];
+  g.parity ^= 1;
+  return warp_sum(s);
 }
 
 }  // namespace dfx

@@ -52,7 +52,9 @@ struct FwdArgs {
   int init_step_variant; long long max_steps;
   double* ys; DfxStats* stats;
   double* scratch; long long scratch_per_design;  // doubles
+  int group;  // CL = 2: CTAs per design
 };
+constexpr int kGroupReserveFwd = 8 + 2 * kMaxGroup;
 
 __device__ __forceinline__ double* placed(const Placement& pl, int i, double* smem, double* scratch) {
   long long o = pl.off[i];
@@ -102,21 +104,23 @@ __device__ inline void setup_design_constants(const DevTopo& T, const DfxParams&
 
 // CL = 0: one CTA per design.  CL = 1: one thread-block cluster per design -- the element loops are strided over
 // all threads of the cluster, every array lives in the design's global scratch (L2), CTA barriers become cluster
-// barriers and the norms are summed over the cluster (cfg5-sized lattices).
+// barriers and the norms are summed over the cluster (cfg5-sized lattices).  CL = 2: the same over a group
+// of `a.group` co-resident CTAs of a cooperative launch with a software barrier (more SMs than a cluster can span).
 template <int CL>
 __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__ FwdArgs a) {
   extern __shared__ double smem[];
   const DevTopo& T = a.topo;
-  const int crank = CL ? (int)cluster_ctarank() : 0, ncta = CL ? (int)cluster_nctarank() : 1;
+  const int ncta = CL == 1 ? (int)cluster_nctarank() : (CL == 2 ? a.group : 1);
+  const int crank = CL == 1 ? (int)cluster_ctarank() : (CL == 2 ? (int)(blockIdx.x % ncta) : 0);
   const int design = blockIdx.x / ncta;
   const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
-  int cpar = 0;
   const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb;
   double* red = smem;  // 40 doubles reserved at the start of shared memory
   double* scratch = a.scratch ? a.scratch + (long long)design * a.scratch_per_design : nullptr;
-  double* cred = scratch;  // CL: the first 2 * kMaxCluster doubles of the scratch hold the cluster-sum partials
-  auto SYNC = [&]() { if (CL) cluster_sync_all(); else __syncthreads(); };
-  auto SUM = [&](double v) { return CL ? cluster_sum(v, red, cred, crank, ncta, cpar) : block_sum(v, red); };
+  // CL: the scratch starts with the group's barrier counter and the partial sums (kGroupReserveFwd doubles)
+  GroupCtx grp = {CL, crank, ncta, (unsigned long long*)scratch, 0ULL, scratch + 8, 0};
+  auto SYNC = [&]() { if (CL) group_sync(grp); else __syncthreads(); };
+  auto SUM = [&](double v) { return CL ? group_sum(v, red, grp) : block_sum(v, red); };
   double* Us = placed(a.place, FA_US, smem, scratch);      // [5][NB]  x, y, theta, sin, cos
   double* Vs = placed(a.place, FA_VS, smem, scratch);      // [3][NB]  stage velocity
   double* Fs = placed(a.place, FA_FS, smem, scratch);      // [3][NN]  node force slots

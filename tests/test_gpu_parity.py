@@ -34,7 +34,11 @@ def _significant(ref, key):
 
 def _kernel_mode(monkeypatch, var, mode):
     monkeypatch.setenv("DFX_CLUSTER", "1")
-    if mode == "fast_tmem":
+    monkeypatch.delenv("DFX_GROUP", raising=False)
+    if mode.startswith("group"):
+        monkeypatch.setenv(var, "generic")
+        monkeypatch.setenv("DFX_GROUP", mode[len("group"):])
+    elif mode == "fast_tmem":
         monkeypatch.delenv(var, raising=False)
     elif mode.startswith("cluster"):
         monkeypatch.setenv(var, "generic")
@@ -44,10 +48,11 @@ def _kernel_mode(monkeypatch, var, mode):
     return mode
 
 
-@pytest.fixture(params=["fast_tmem", "notmem", "generic", "cluster4", "cluster16"])
+@pytest.fixture(params=["fast_tmem", "notmem", "generic", "cluster4", "cluster16", "group40"])
 def forward_kernel_mode(request, monkeypatch):
     """the forward code paths of libdfx: fast kernel with TMEM-resident stage history, fast kernel without TMEM,
-    generic kernel for any lattice size, generic kernel spread over a thread-block cluster (4 and 16 CTAs per design)"""
+    generic kernel for any lattice size, generic kernel spread over a thread-block cluster (4 and 16 CTAs per design)
+    or over a cooperative group of 40 CTAs with the software barrier"""
     return _kernel_mode(monkeypatch, "DFX_FORWARD_KERNEL", request.param)
 
 
@@ -65,7 +70,7 @@ def test_forward_matches_golden(name, forward_kernel_mode):
     assert abs(int(st["steps"]) - int(c.ref["fwd_steps"])) <= max(2, int(0.01 * c.ref["fwd_steps"]))
 
 
-@pytest.fixture(params=["fast_tmem", "notmem", "generic", "cluster4", "cluster16"])
+@pytest.fixture(params=["fast_tmem", "notmem", "generic", "cluster4", "cluster16", "group40"])
 def adjoint_kernel_mode(request, monkeypatch):
     """the adjoint code paths of libdfx: fast kernel with TMEM-resident stage history (default), fast kernel
     without TMEM, generic kernel (any lattice size), generic kernel over a thread-block cluster"""

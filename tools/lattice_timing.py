@@ -15,7 +15,8 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 def main():
     n = int(sys.argv[1]) if len(sys.argv) > 1 else 100
     periods = float(sys.argv[2]) if len(sys.argv) > 2 else 0.25
-    clusters = [int(c) for c in sys.argv[3].split(",")] if len(sys.argv) > 3 else [1, 2, 4, 8, 16]
+    # "16" = thread-block cluster of 16 CTAs (DFX_CLUSTER), "g64" = cooperative group of 64 CTAs (DFX_GROUP)
+    clusters = sys.argv[3].split(",") if len(sys.argv) > 3 else ["1", "2", "4", "8", "16"]
     from difflexmm_b200 import _abi
     from difflexmm_b200.problems import QuadsFocusing
     P = QuadsFocusing(n1_blocks=n, n2_blocks=n, simulation_time=periods / 30.0, n_timepoints=8, target_shift=(2, 2),
@@ -26,7 +27,12 @@ def main():
     nf = P.spec.n_free
     ref = None
     for cl in clusters:
-        os.environ["DFX_CLUSTER"] = str(cl)
+        os.environ.pop("DFX_GROUP", None)
+        os.environ.pop("DFX_CLUSTER", None)
+        if str(cl).startswith("g"):
+            os.environ["DFX_GROUP"] = str(cl)[1:]
+        else:
+            os.environ["DFX_CLUSTER"] = str(cl)
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)]
         s.lib_forward(ps, y0, ts)  # warm-up
         torch.cuda.synchronize()

@@ -147,3 +147,37 @@ def test_adjoint_gradient_matches_finite_differences():
         an = float((gr[name][0] * d).sum())
         tol = 2e-4 if name == "drive" else 2e-5  # the pulse delay has a large second derivative: FD truncation
         assert abs(fd - an) <= tol * max(abs(fd), abs(an)), name
+
+
+def test_forward_converges_to_an_independent_scipy_integration():
+    """the restated Dormand-Prince stepper (controller, FSAL, dense output) against scipy's DOP853
+    with its own step control at rtol = atol = 1e-12 -- an independent integrator on the same RHS; trajectories must
+    agree far below the production tolerance.  Also the augmented (adjoint) system: its cotangents against scipy
+    integrating the same augmented RHS backwards over every output interval."""
+    from scipy.integrate import solve_ivp
+    P, spec, lv, pb, dpd, aug, y0, ts = _small_quads((-15 * math.pi / 180, -10 * math.pi / 180))
+    orc = Oracle(spec)
+    ps = orc.params(1, lv, pb, dpd)
+    ys, st = orc.forward(ps, y0, ts, 1e-11, 1e-12)
+    sol = solve_ivp(lambda t, y: orc.rhs(ps, y, t), (ts[0], ts[-1]), y0, method="DOP853", t_eval=ts, rtol=1e-12, atol=1e-12)
+    assert sol.success
+    assert rel_l2(ys[0], sol.y.T) < 1e-8
+    # adjoint: z = (y, y_bar, t0_bar, args_bar) in negated time, restarted at every output (jax _odeint_rev)
+    nf = spec.n_free
+    w = np.linspace(0.5, 1.5, len(ts) * 2 * nf).reshape(len(ts), 2 * nf)
+    g = w * np.cos(ys[0])
+    y0b, tsb, gr, sb = orc.adjoint(ps, ys, ts, g[None], 1e-11, 1e-12)
+    n_aug = orc.aug_size(ps)
+    y_bar = g[-1].copy()
+    tail = np.zeros(n_aug - 4 * nf)  # t0_bar followed by the parameter cotangents
+    for i in range(len(ts) - 1, 0, -1):
+        tail[0] -= float(orc.rhs(ps, ys[0, i], ts[i]) @ g[i])
+        z0 = np.concatenate([ys[0, i], y_bar, tail])
+        s = solve_ivp(lambda s_, z: orc.aug_rhs(ps, z, s_), (-ts[i], -ts[i - 1]), z0, method="DOP853", rtol=1e-12, atol=1e-14)
+        assert s.success
+        z1 = s.y[:, -1]
+        y_bar = z1[2 * nf:4 * nf] + g[i - 1]
+        tail = z1[4 * nf:]
+    assert rel_l2(y0b[0], y_bar) < 1e-7
+    flat = np.concatenate([np.asarray(gr[k][0]).reshape(-1) for k in gr])
+    assert np.isfinite(tail).all() and abs(np.linalg.norm(tail[1:]) - np.linalg.norm(flat)) < 1e-6 * np.linalg.norm(flat)

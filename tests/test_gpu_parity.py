@@ -103,8 +103,26 @@ def test_adjoint_matches_golden(name, adjoint_kernel_mode):
             assert np.abs(got - c.ref[key]).max() <= 1e-9, k
 
 
+@pytest.fixture(params=["default", "cluster4", "group40"])
+def batched_kernel_mode(request, monkeypatch):
+    """default kernel choice, and the multi-CTA modes of the generic kernels with several designs per launch
+    (design index = CTA index / CTAs per design; per-design scratch slices, barrier counters and partial sums)"""
+    for var in ("DFX_FORWARD_KERNEL", "DFX_ADJOINT_KERNEL"):
+        if request.param == "default":
+            monkeypatch.delenv(var, raising=False)
+        else:
+            monkeypatch.setenv(var, "generic")
+    monkeypatch.delenv("DFX_GROUP", raising=False)
+    monkeypatch.delenv("DFX_CLUSTER", raising=False)
+    if request.param.startswith("cluster"):
+        monkeypatch.setenv("DFX_CLUSTER", request.param[len("cluster"):])
+    if request.param.startswith("group"):
+        monkeypatch.setenv("DFX_GROUP", request.param[len("group"):])
+    return request.param
+
+
 @pytest.mark.parametrize("name", golden_names())
-def test_cuda_matches_cpp_oracle_batched(name):
+def test_cuda_matches_cpp_oracle_batched(name, batched_kernel_mode):
     """a batch of 3 perturbed designs: CUDA vs the C++ oracle on identical inputs"""
     from oracle import Oracle
     c = load_golden(name)

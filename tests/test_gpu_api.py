@@ -435,3 +435,43 @@ def test_zero_length_spring_energy_through_the_api():
     with pytest.raises(TypeError):  # ligament parameters with the spring energy
         solve(torch.zeros(2, geo.n_blocks, 3, dtype=torch.float64), ts,
               params(LigamentParams(k_stretch=1.0, k_shear=1.0, k_rot=1.0, reference_vector=refv())))
+
+
+def test_c_abi_error_behaviour_on_the_device():
+    """return codes + dfx_last_error instead of crashes or silent fallbacks: undersized workspace, NULL pointers,
+    bad sizes, inputs of the wrong length at the Python mirror"""
+    import ctypes as C
+    from difflexmm_b200 import _abi, _lib
+    P = _problem()
+    s = P.setup()
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(P.initial_design(), device="cuda")
+    ps = _abi.ParamSet(P.spec, 1, {k: v.contiguous() for k, v in leaves.items()}, pb, dpd)
+    p = ps.to_struct()
+    N, n_t = 2 * P.spec.n_free, ts.shape[0]
+    ys = torch.empty((1, n_t, N), dtype=torch.float64, device="cuda")
+    stats = torch.zeros((1, _abi.STATS_DTYPE.itemsize), dtype=torch.uint8, device="cuda")
+    lib, h = _lib.lib, s.handle._h
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    need = lib.dfx_forward_workspace_bytes(h, 1)
+    assert need > 8 and lib.dfx_adjoint_workspace_bytes(h, 1) > need
+    ws = torch.empty((need,), dtype=torch.uint8, device="cuda")
+
+    def fwd(y0_ptr, n_t_, ws_bytes, batch=1):
+        return lib.dfx_forward(h, C.byref(p), batch, C.c_void_p(y0_ptr), C.c_int64(0), C.c_void_p(ts.data_ptr()), C.c_int64(0), n_t_,
+                               C.c_double(1e-8), C.c_double(1e-4), None, C.c_void_p(ys.data_ptr()), C.c_void_p(stats.data_ptr()),
+                               C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes), stream)
+
+    assert fwd(y0.data_ptr(), n_t, need) == 0
+    assert fwd(y0.data_ptr(), n_t, 8) != 0 and b"workspace too small" in lib.dfx_last_error()
+    assert fwd(None, n_t, need) != 0 and b"NULL" in lib.dfx_last_error()
+    assert fwd(y0.data_ptr(), 0, need) != 0
+    assert fwd(y0.data_ptr(), n_t, need, batch=0) != 0
+    assert lib.dfx_adjoint_kinetic(h, C.byref(p), 1, C.c_void_p(ys.data_ptr()), C.c_void_p(ts.data_ptr()), C.c_int64(0), n_t, None,
+                                   C.c_double(1e-8), C.c_double(1e-4), C.c_int64(0), None, None, None, None, None, None,
+                                   C.c_size_t(0), stream) != 0
+    torch.cuda.synchronize()
+    with pytest.raises(ValueError):  # state0 of the wrong size
+        s.lib_forward(ps, y0[:-2], ts)
+    with pytest.raises(RuntimeError):  # CUDA-only: there is no CPU path
+        from difflexmm_b200.dynamics import DynamicSolver
+        DynamicSolver(P.spec, P.drive, device="cpu")

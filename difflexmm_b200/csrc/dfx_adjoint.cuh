@@ -162,6 +162,14 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   double* ctot = scratch + 8 + 2 * kMaxGroup;
   auto SYNC = [&]() { if (CL) group_sync(grp); else __syncthreads(); };
   auto SUM = [&](double v) { return CL ? group_sum(v, red, grp) : block_sum(v, red); };
+  // Work distribution: CTA `crank` owns a contiguous slice of the blocks (all three DOF rows of it) and of the bonds,
+  // so that every CTA of a cluster / group gets the same share of each phase.  One CTA: e = i, b = i.
+  const int perB = (T.n_blocks + ncta - 1) / ncta;
+  const int blk0 = min(T.n_blocks, crank * perB), cntB = min(T.n_blocks, blk0 + perB) - blk0;
+  const int perL = (T.n_bonds + ncta - 1) / ncta;
+  const int bond0 = min(T.n_bonds, crank * perL), bond1 = min(T.n_bonds, bond0 + perL);
+#define FOR_E(e) for (int _i = threadIdx.x, e = 0; _i < 3 * cntB && ((e = (_i / cntB) * T.n_blocks + blk0 + _i % cntB), true); _i += blockDim.x)
+#define FOR_B(b) for (int b = bond0 + threadIdx.x; b < bond1; b += blockDim.x)
   auto P = [&](int i) -> double* {
     const long long o = a.place.off[i];
     return o >= 0 ? smem + o : scratch + (-(o + 1));
@@ -219,7 +227,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   double cmin = 0, ccut = 0, ckc = 0;
   if (T.contact) { cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
   // y_bar = g[-1]
-  for (int e = tid; e < ND; e += nthr) {
+  FOR_E(e) {
     const int j = e / NB, blk = e - j * NB;
     const int f = T.free_of_dof[3 * blk + j];
     lu0[e] = f >= 0 ? gg[(long long)(a.n_t - 1) * 2 * nf + f] : 0.0;
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     const bool want_q = qc.mode != 1;
     SYNC();
     double p_ks = 0, p_ksh = 0, p_kr = 0, p_c0 = 0, p_c1 = 0, p_c2 = 0, probe = 0;
-    for (int b = tid; b < NBONDS; b += nthr) {
+    FOR_B(b) {
       const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
       BlockState<Dual> s1, s2;
       make_block(Us[bl.x], Us[NB + bl.x], Us[2 * NB + bl.x], Us[3 * NB + bl.x], Us[4 * NB + bl.x], Ws[bl.x], Ws[NB + bl.x], Ws[2 * NB + bl.x], s1);
@@ -281,7 +289,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     double ls = 0.0, lsd = 0.0;
     if (T.load_kind != DFX_LOAD_NONE) load_eval(T.load_kind, time, T.load_consts, ls, lsd);
     double p_t0 = 0, p_damp = 0, p_dr[DFX_MAX_DRIVE_PARAMS] = {0, 0, 0, 0, 0};
-    for (int e = tid; e < ND; e += nthr) {
+    FOR_E(e) {
       const int j = e / NB, blk = e - j * NB, dof = 3 * blk + j;
       double F = 0.0, HW = 0.0;
       {
@@ -415,7 +423,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     const double s0 = -ts[i], s_target = -ts[i - 1];
     const double* yi = ys + (long long)i * 2 * nf;
     const double* gi = gg + (long long)i * 2 * nf;
-    for (int e = tid; e < ND; e += nthr) {
+    FOR_E(e) {
       const int j = e / NB, blk = e - j * NB;
       const int f = T.free_of_dof[3 * blk + j];
       u0[e] = f >= 0 ? yi[f] : 0.0;
@@ -427,7 +435,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     n_rhs++;
     // t_bar = func(ys[i], ts[i]) . g[i];  func = (v, acc) = (v0, -kv[0])
     double pt = 0.0;
-    for (int e = tid; e < ND; e += nthr) {
+    FOR_E(e) {
       if (invm[e] == 0.0) continue;
       const int j = e / NB, blk = e - j * NB;
       const int f = T.free_of_dof[3 * blk + j];
@@ -442,7 +450,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     // ---- initial_step_size over the whole augmented vector ---------------------------------------
     {
       double sd0 = 0, sd1 = 0;
-      for (int e = tid; e < ND; e += nthr) {
+      FOR_E(e) {
         if (invm[e] == 0.0) continue;
         const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
         const double slu = atol + fabs(lu0[e]) * rtol, slv = atol + fabs(lv0[e]) * rtol;
@@ -467,12 +475,12 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       const double d0 = sqrt(SUM(sd0));
       const double d1 = sqrt(SUM(sd1));
       const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-      for (int e = tid; e < ND; e += nthr)
+      FOR_E(e)
         put_stage(e, u0[e] - h0 * v0[e], v0[e] + h0 * kv[e], lu0[e] + h0 * klu[e], lv0[e] + h0 * klv[e], -(s0 + h0));
       qc.mode = 7;
       double sd2 = aug_BC(-(s0 + h0), kv + ND, klu + ND, klv + ND);
       n_rhs++;
-      for (int e = tid; e < ND; e += nthr) {
+      FOR_E(e) {
         if (invm[e] == 0.0) continue;
         const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
         const double slu = atol + fabs(lu0[e]) * rtol, slv = atol + fabs(lv0[e]) * rtol;
@@ -510,7 +518,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
 #pragma unroll 1
       for (int st = 0; st < 6; ++st) {
         const double ha = h * tab.alpha[st], h2 = h * h, s_stage = s_cur + ha;
-        for (int e = tid; e < ND; e += nthr) {
+        FOR_E(e) {
           double au = 0.0, av = 0.0, alu = 0.0, alv = 0.0;
           for (int l = 0; l <= st; ++l) {
             const double b = tab.beta[st][l];
@@ -530,7 +538,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       }
       n_rhs += 6;
       // error of the dynamic entries
-      for (int e = tid; e < ND; e += nthr) {
+      FOR_E(e) {
         if (invm[e] == 0.0) continue;
         double eu = 0.0, ev = 0.0, elu = 0.0, elv = 0.0;
 #pragma unroll
@@ -569,7 +577,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
         if (qc.crossing) {
           // interval finished: keep the interpolated cotangents at s_target, add g[i-1]
           const double* gp = gg + (long long)(i - 1) * 2 * nf;
-          for (int e = tid; e < ND; e += nthr) {
+          FOR_E(e) {
             if (invm[e] == 0.0) continue;
             const int j = e / NB, blk = e - j * NB;
             const int f = T.free_of_dof[3 * blk + j];
@@ -586,7 +594,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
           }
           done = true;
         } else {
-          for (int e = tid; e < ND; e += nthr) {
+          FOR_E(e) {
             u0[e] = Us[e]; v0[e] = Vs[e]; lu0[e] = Lus[e]; lv0[e] = Lvs[e];
             kv[e] = kv[6 * ND + e]; klu[e] = klu[6 * ND + e]; klv[e] = klv[6 * ND + e];
           }
@@ -608,7 +616,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   SYNC();
   const double nanv = nan("");
   const bool bad = status != 0;
-  for (int e = tid; e < ND; e += nthr) {
+  FOR_E(e) {
     const int j = e / NB, blk = e - j * NB, dof = 3 * blk + j;
     const int f = T.free_of_dof[dof];
     if (a.grads.damping && has_damp && damp_pd) {
@@ -629,7 +637,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       a.grads.centroid_node_vectors[((long long)design * NN + n) * 2 + 1] = bad ? nanv : qc.q0[a.qo_cnv + NN + n];
     }
   if (a.grads.reference_vector)
-    for (int b = tid; b < NBONDS; b += nthr) {
+    FOR_B(b) {
       a.grads.reference_vector[((long long)design * NBONDS + b) * 2] = bad ? nanv : qc.q0[a.qo_ref + b];
       a.grads.reference_vector[((long long)design * NBONDS + b) * 2 + 1] = bad ? nanv : qc.q0[a.qo_ref + NBONDS + b];
     }
@@ -639,7 +647,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     const int qo[3] = {a.qo_ks, a.qo_ksh, a.qo_kr};
     for (int k = 0; k < 3; ++k) {
       if (!outs[k]) continue;
-      if (pb[k]) { for (int b = tid; b < NBONDS; b += nthr) outs[k][(long long)design * NBONDS + b] = bad ? nanv : qc.q0[qo[k] + b]; }
+      if (pb[k]) { FOR_B(b) outs[k][(long long)design * NBONDS + b] = bad ? nanv : qc.q0[qo[k] + b]; }
       else if (tid == 0) outs[k][design] = bad ? nanv : Sq0[SC_KS + k];
     }
   }
@@ -655,5 +663,8 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     }
   }
 }
+
+#undef FOR_E
+#undef FOR_B
 
 }  // namespace dfx

@@ -36,7 +36,7 @@ constexpr size_t kSmemBytes = 232448;  // 227 KB: the opt-in maximum of one CTA 
 constexpr int kRedDoubles = 40;
 static_assert(kRedDoubles == kRedDoublesDev, "shared-memory reduction area");
 constexpr int kGroupMinBonds = 8192;  // lattices with at least this many bonds default to the cooperative group mode
-constexpr int kGroupDefault = 64;     // CTAs per design in that mode (measured on 100x100: 64, 100 and 148 CTAs take the same time)
+constexpr int kGroupDefault = kMaxGroup;  // CTAs per design in that mode: as many as fit (100x100: 64 CTAs 127 ms, 148 CTAs 110 ms adjoint)
 constexpr int kScratchSlots = 256;  // >= %nsmid of any sm_100 part: SM-indexed scratch of the fast adjoint kernel
 
 template <class T>

@@ -121,6 +121,14 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
   GroupCtx grp = {CL, crank, ncta, (unsigned long long*)scratch, 0ULL, scratch + 8, 0};
   auto SYNC = [&]() { if (CL) group_sync(grp); else __syncthreads(); };
   auto SUM = [&](double v) { return CL ? group_sum(v, red, grp) : block_sum(v, red); };
+  // Work distribution: CTA `crank` owns a contiguous slice of the blocks (all three DOF rows of it) and of the bonds,
+  // so that every CTA of a cluster / group gets the same share of each phase.  One CTA: e = i, b = i.
+  const int perB = (T.n_blocks + ncta - 1) / ncta;
+  const int blk0 = min(T.n_blocks, crank * perB), cntB = min(T.n_blocks, blk0 + perB) - blk0;
+  const int perL = (T.n_bonds + ncta - 1) / ncta;
+  const int bond0 = min(T.n_bonds, crank * perL), bond1 = min(T.n_bonds, bond0 + perL);
+#define FOR_E(e) for (int _i = threadIdx.x, e = 0; _i < 3 * cntB && ((e = (_i / cntB) * T.n_blocks + blk0 + _i % cntB), true); _i += blockDim.x)
+#define FOR_B(b) for (int b = bond0 + threadIdx.x; b < bond1; b += blockDim.x)
   double* Us = placed(a.place, FA_US, smem, scratch);      // [5][NB]  x, y, theta, sin, cos
   double* Vs = placed(a.place, FA_VS, smem, scratch);      // [3][NB]  stage velocity
   double* Fs = placed(a.place, FA_FS, smem, scratch);      // [3][NN]  node force slots
@@ -147,7 +155,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
 
   setup_design_constants(T, a.p, design, bondc, cnv, alpha, invm, cd, tid, nthr);
   for (int i = tid; i < 3 * NN; i += nthr) Fs[i] = 0.0;
-  for (int e = tid; e < ND; e += nthr) {
+  FOR_E(e) {
     const int j = e / NB, blk = e - j * NB;
     const int f = T.free_of_dof[3 * blk + j];
     u0[e] = f >= 0 ? y0g[f] : 0.0;
@@ -161,7 +169,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
   // ---- RHS phases B and C (phase A is written by the caller into Us / Vs) ---------------------
   auto rhs_BC = [&](double tstage, double* kout) {
     SYNC();
-    for (int b = tid; b < NBONDS; b += nthr) {
+    FOR_B(b) {
       const int2 nd = T.bond_nodes[b], bl = T.bond_blocks[b];
       BlockState<double> s1, s2;
       make_block(Us[bl.x], Us[NB + bl.x], Us[2 * NB + bl.x], Us[3 * NB + bl.x], Us[4 * NB + bl.x], s1);
@@ -186,7 +194,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
     SYNC();
     double ls = 0.0, lsd;
     if (T.load_kind != DFX_LOAD_NONE) load_eval(T.load_kind, tstage, T.load_consts, ls, lsd);
-    for (int e = tid; e < ND; e += nthr) {
+    FOR_E(e) {
       const int j = e / NB, blk = e - j * NB;
       double F = 0.0;
       const double* slot = Fs + (long long)j * NN + blk * npb;
@@ -224,7 +232,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
   double t = ts[0];
 
   // f0 = rhs(y0, t0)
-  for (int e = tid; e < ND; e += nthr) put_stage(e, u0[e], v0[e], t);
+  FOR_E(e) put_stage(e, u0[e], v0[e], t);
   rhs_BC(t, kv);
   n_rhs++;
 
@@ -232,7 +240,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
   double dt;
   {
     double sd0 = 0, sd1 = 0;
-    for (int e = tid; e < ND; e += nthr) {
+    FOR_E(e) {
       if (invm[e] == 0.0) continue;
       const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
       const double a0 = u0[e] / su, a1 = v0[e] / sv, b0 = v0[e] / su, b1 = kv[e] / sv;
@@ -242,11 +250,11 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
     const double d0 = sqrt(SUM(sd0));
     const double d1 = sqrt(SUM(sd1));
     const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-    for (int e = tid; e < ND; e += nthr) put_stage(e, u0[e] + h0 * v0[e], v0[e] + h0 * kv[e], t + h0);
+    FOR_E(e) put_stage(e, u0[e] + h0 * v0[e], v0[e] + h0 * kv[e], t + h0);
     rhs_BC(t + h0, kv + ND);
     n_rhs++;
     double sd2 = 0;
-    for (int e = tid; e < ND; e += nthr) {
+    FOR_E(e) {
       if (invm[e] == 0.0) continue;
       const double su = atol + fabs(u0[e]) * rtol, sv = atol + fabs(v0[e]) * rtol;
       const double b0 = (Vs[e] - v0[e]) / su, b1 = (kv[ND + e] - kv[e]) / sv;
@@ -273,7 +281,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
 #pragma unroll 1
       for (int s = 0; s < 6; ++s) {
         const double ha = dt * tab.alpha[s], h2 = dt * dt, tstage = t + ha;
-        for (int e = tid; e < ND; e += nthr) {
+        FOR_E(e) {
           double au = 0.0, av = 0.0;
           for (int l = 0; l <= s; ++l) {
             const double k = kv[l * ND + e];
@@ -287,7 +295,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
       n_rhs += 6;
       // error ratio: sqrt(mean((err / (atol + rtol*max(|y0|,|y1|)))^2))
       double se = 0.0;
-      for (int e = tid; e < ND; e += nthr) {
+      FOR_E(e) {
         if (invm[e] == 0.0) continue;
         double eu = 0.0, ev = 0.0;
 #pragma unroll
@@ -312,7 +320,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
         while (it < a.n_t && !(t_new < ts[it])) {
           const double x = (ts[it] - t) / (t_new - t);
           double* out = ys + (long long)it * 2 * nf;
-          for (int e = tid; e < ND; e += nthr) {
+          FOR_E(e) {
             if (invm[e] == 0.0) continue;
             const int j = e / NB, blk = e - j * NB;
             const int f = T.free_of_dof[3 * blk + j];
@@ -343,7 +351,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
           ++it;
           crossed = true;
         }
-        for (int e = tid; e < ND; e += nthr) {
+        FOR_E(e) {
           u0[e] = Us[e];
           v0[e] = Vs[e];
           kv[e] = kv[6 * ND + e];
@@ -366,5 +374,8 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
     a.stats[design] = st;
   }
 }
+
+#undef FOR_E
+#undef FOR_B
 
 }  // namespace dfx

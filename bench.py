@@ -290,7 +290,7 @@ def main():
         te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B / te.item(), "unit": UNIT, "h2d_bytes_per_step": h2d, "d2h_bytes_per_step": d2h}
+        e2e = {"value": world * B / te.item(), "unit": UNIT, "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h}
 
     if rank != 0:
         if world > 1:

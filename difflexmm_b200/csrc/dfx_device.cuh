@@ -472,13 +472,15 @@ __device__ __forceinline__ void group_sync(GroupCtx& g) {
   if (g.mode == 1) { cluster_sync_all(); return; }
   __syncthreads();
   if (threadIdx.x == 0) {
-    __threadfence();  // release: this CTA's writes are visible before its arrival
-    atomicAdd(g.counter, 1ULL);
+    // arrive with release semantics (the CTA's writes, ordered before this by the CTA barrier, become visible first),
+    // then poll with acquire loads (which also drop this SM's stale L1 lines for the threads released below)
     const unsigned long long target = (g.epoch + 1) * (unsigned long long)g.ncta;
-    unsigned long long spins = 0;
-    while (*(volatile unsigned long long*)g.counter < target)
+    asm volatile("red.release.gpu.global.add.u64 [%0], %1;" ::"l"(g.counter), "l"(1ULL) : "memory");
+    unsigned long long seen, spins = 0;
+    do {
+      asm volatile("ld.acquire.gpu.global.u64 %0, [%1];" : "=l"(seen) : "l"(g.counter) : "memory");
       if (++spins > (1ULL << 28)) __trap();  // a CTA of the group never arrived: fail the launch instead of hanging
-    __threadfence();  // acquire (invalidates this SM's L1)
+    } while (seen < target);
   }
   g.epoch++;
   __syncthreads();

@@ -102,7 +102,7 @@ def main():
         P.setup()
         design = P.initial_design()
         ms, J, sf, sb, st = gpu_value_and_grad(P, design, reps=1)
-        print(json.dumps({"config": f"cfg5 quads 100x100 contact active, {periods} drive periods, one lattice over a cooperative group of 64 CTAs (software barrier), value_and_grad",
+        print(json.dumps({"config": f"cfg5 quads 100x100 contact active, {periods} drive periods, one lattice over all SMs (cooperative group, software barrier), value_and_grad",
                           "gpu_ms": ms, "objective": J, "fwd_steps": sf, "bwd_steps": sb, "status": st,
                           "us_per_step_fwd_plus_bwd": 1e3 * ms / max(1, sf + sb)}), flush=True)
 

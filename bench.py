@@ -216,10 +216,10 @@ def main():
         if timed:
             ev[1].record()
         # objective on the device; the adjoint kernel forms its cotangent dJ/dys = m v itself (no g tensor)
-        J, ibar = lib.kinetic_energy(solver.handle, ps, ys, tidx32)
+        J, ibar, _ = lib.objective_value(solver.handle, ps, ys, tidx32)
         if timed:
             ev[2].record()
-        y0_bar, ts_bar, grads, st_b = lib.adjoint_kinetic(solver.handle, ps, ys, ts, tidx32, ones_w, prob.rtol, prob.atol,
+        y0_bar, ts_bar, grads, st_b = lib.adjoint_objective(solver.handle, ps, ys, ts, tidx32, ones_w, prob.rtol, prob.atol,
                                                           aug, solver.options)
         if timed:
             ev[3].record()

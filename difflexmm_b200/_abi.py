@@ -74,8 +74,12 @@ class DfxGeometryDesc(C.Structure):
                 ("base_nodes", C.c_void_p), ("node_design", C.c_void_p)]
 
 
-class DfxKineticObjective(C.Structure):
-    _fields_ = [("target_free_ids", C.c_void_p), ("n_target", C.c_int32), ("weights", C.c_void_p)]
+DFX_OBJ_KINETIC, DFX_OBJ_ANGULAR = 0, 1
+
+
+class DfxObjective(C.Structure):
+    _fields_ = [("kind", C.c_int32), ("n_target", C.c_int32), ("target_free_ids", C.c_void_p), ("weights", C.c_void_p),
+                ("arm", C.c_void_p), ("arm_bstride", C.c_int64)]
 
 
 class DfxStats(C.Structure):

@@ -46,7 +46,7 @@ lib.dfx_fp64_peak.restype = C.c_double
 
 EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free", "dfx_drive_n_params",
            "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
-           "dfx_expand_fields", "dfx_kinetic_energy", "dfx_adjoint_kinetic",
+           "dfx_expand_fields", "dfx_objective", "dfx_adjoint_objective",
            "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp", "dfx_fp64_peak", "dfx_math_selftest", "dfx_last_error", "dfx_version")
 
 
@@ -178,27 +178,44 @@ def adjoint(topo: Topology, ps: _abi.ParamSet, ys, ts, g, rtol, atol, aug_size, 
     return y0_bar, ts_bar, grads, _Stats(stats)
 
 
-def kinetic_energy(topo: Topology, ps: _abi.ParamSet, ys, target_free_ids, want_inertia_bar=True):
-    """-> J (B,) = sum_t sum_{f in target} 1/2 m_f v_f^2, and dJ/d(inertia) (B, n_free) or None."""
+def _objective_struct(kind, ids, weights, arm, B):
+    """-> (DfxObjective, tensors to keep alive)"""
+    keep = [ids]
+    obj = _abi.DfxObjective()
+    obj.kind, obj.n_target, obj.target_free_ids = int(kind), ids.numel(), ids.data_ptr()
+    if weights is not None:
+        keep.append(weights)
+        obj.weights = weights.data_ptr()
+    if arm is not None:
+        keep.append(arm)
+        obj.arm, obj.arm_bstride = arm.data_ptr(), (arm[0].numel() if arm.dim() == 3 else 0)
+    return obj, keep
+
+
+def objective_value(topo: Topology, ps: _abi.ParamSet, ys, target_free_ids, kind=_abi.DFX_OBJ_KINETIC, arm=None):
+    """-> J (B,), dJ/d(inertia) (B, n_free), dJ/d(arm) (B, n_target/3, 2) or None.
+    kinetic: J = sum_t sum_target 1/2 m v^2; angular: sum_t sum_blocks (arm + u) x (m v) + I omega (include/dfx.h)."""
     spec, B = topo.spec, ps.batch
     dev = ys.device
     n_t = ys.shape[1]
     ys = ys.contiguous()
     ids = target_free_ids.to(device=dev, dtype=torch.int32).contiguous()
+    arm = None if arm is None else arm.to(device=dev, dtype=torch.float64).contiguous()
     value = torch.empty((B,), dtype=torch.float64, device=dev)
-    ibar = torch.empty((B, spec.n_free), dtype=torch.float64, device=dev) if want_inertia_bar else None
-    obj = _abi.DfxKineticObjective(ids.data_ptr(), ids.numel(), None)
+    ibar = torch.empty((B, spec.n_free), dtype=torch.float64, device=dev)
+    abar = torch.empty((B, ids.numel() // 3, 2), dtype=torch.float64, device=dev) if kind == _abi.DFX_OBJ_ANGULAR else None
+    obj, keep = _objective_struct(kind, ids, None, arm, B)
     p = ps.to_struct()
     with torch.cuda.device(dev):
-        _check(lib.dfx_kinetic_energy(topo._h, C.byref(p), B, C.c_void_p(ys.data_ptr()), n_t, C.byref(obj),
-                                      C.c_void_p(value.data_ptr()), C.c_void_p(ibar.data_ptr() if ibar is not None else None),
-                                      _stream_ptr(dev)), "dfx_kinetic_energy")
-    return value, ibar
+        _check(lib.dfx_objective(topo._h, C.byref(p), B, C.c_void_p(ys.data_ptr()), n_t, C.byref(obj),
+                                 C.c_void_p(value.data_ptr()), C.c_void_p(ibar.data_ptr()),
+                                 C.c_void_p(abar.data_ptr() if abar is not None else None), _stream_ptr(dev)), "dfx_objective")
+    return value, ibar, abar
 
 
-def adjoint_kinetic(topo: Topology, ps: _abi.ParamSet, ys, ts, target_free_ids, weights, rtol, atol, aug_size,
-                    options: _abi.DfxOptions):
-    """`adjoint` with the cotangent of the kinetic objective generated in the kernel (weights[b] = dL/dJ_b)."""
+def adjoint_objective(topo: Topology, ps: _abi.ParamSet, ys, ts, target_free_ids, weights, rtol, atol, aug_size,
+                      options: _abi.DfxOptions, kind=_abi.DFX_OBJ_KINETIC, arm=None):
+    """`adjoint` with the cotangent of the device objective generated in the kernel (weights[b] = dL/dJ_b)."""
     spec, B = topo.spec, ps.batch
     N = 2 * spec.n_free
     dev = ys.device
@@ -206,6 +223,7 @@ def adjoint_kinetic(topo: Topology, ps: _abi.ParamSet, ys, ts, target_free_ids, 
     ys, ts = ys.contiguous(), ts.contiguous()
     ids = target_free_ids.to(device=dev, dtype=torch.int32).contiguous()
     w = weights.to(device=dev, dtype=torch.float64).expand(B).contiguous()
+    arm = None if arm is None else arm.to(device=dev, dtype=torch.float64).contiguous()
     y0_bar = torch.zeros((B, N), dtype=torch.float64, device=dev)
     ts_bar = torch.zeros((B, n_t), dtype=torch.float64, device=dev)
     grads = {n: torch.zeros((B,) + ps.base_shapes[n], dtype=torch.float64, device=dev) for n in ps.leaves}
@@ -213,17 +231,17 @@ def adjoint_kinetic(topo: Topology, ps: _abi.ParamSet, ys, ts, target_free_ids, 
     for n, t in grads.items():
         setattr(gs, n, t.data_ptr())
     stats = torch.zeros((B, _abi.STATS_DTYPE.itemsize), dtype=torch.uint8, device=dev)
-    obj = _abi.DfxKineticObjective(ids.data_ptr(), ids.numel(), w.data_ptr())
+    obj, keep = _objective_struct(kind, ids, w, arm, B)
     p = ps.to_struct()
     with torch.cuda.device(dev):
         ws_bytes = lib.dfx_adjoint_workspace_bytes(topo._h, B)
         ws = torch.empty((max(ws_bytes, 8),), dtype=torch.uint8, device=dev)
-        _check(lib.dfx_adjoint_kinetic(topo._h, C.byref(p), B, C.c_void_p(ys.data_ptr()), C.c_void_p(ts.data_ptr()),
-                                       C.c_int64(n_t if ts.dim() == 2 else 0), n_t, C.byref(obj),
-                                       C.c_double(rtol), C.c_double(atol), C.c_int64(int(aug_size)), C.byref(options),
-                                       C.c_void_p(y0_bar.data_ptr()), C.c_void_p(ts_bar.data_ptr()), C.byref(gs),
-                                       C.c_void_p(stats.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes),
-                                       _stream_ptr(dev)), "dfx_adjoint_kinetic")
+        _check(lib.dfx_adjoint_objective(topo._h, C.byref(p), B, C.c_void_p(ys.data_ptr()), C.c_void_p(ts.data_ptr()),
+                                         C.c_int64(n_t if ts.dim() == 2 else 0), n_t, C.byref(obj),
+                                         C.c_double(rtol), C.c_double(atol), C.c_int64(int(aug_size)), C.byref(options),
+                                         C.c_void_p(y0_bar.data_ptr()), C.c_void_p(ts_bar.data_ptr()), C.byref(gs),
+                                         C.c_void_p(stats.data_ptr()), C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes),
+                                         _stream_ptr(dev)), "dfx_adjoint_objective")
     return y0_bar, ts_bar, grads, _Stats(stats)
 
 

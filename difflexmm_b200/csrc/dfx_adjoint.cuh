@@ -51,7 +51,8 @@ struct AdjArgs {
   PlacementA place;
   const double* ys; const double* ts; long long ts_bstride; int n_t;
   const double* g;            // cotangent of ys, or NULL when the kinetic objective generates it in the kernel
-  const int* obj_ids; int obj_n; const double* obj_w;  // kinetic objective (fast kernel only)
+  // objective whose cotangent is formed in the kernel (g == NULL): see objective_cotangent()
+  int obj_kind; const int* obj_ids; int obj_n; const double* obj_w; const double* obj_arm; long long obj_arm_bstride;
   double rtol, atol;
   long long aug_size;
   int init_step_variant; long long max_steps;
@@ -63,6 +64,28 @@ struct AdjArgs {
   int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, nq;
   int group;  // CL = 2: CTAs per design
 };
+
+// Cotangent dJ/d ys[design][i][(is_v ? n_free : 0) + f] of the device objectives (include/dfx.h), w = weights[design]:
+//   kinetic:  dJ/dv_f = w m_f v_f on the target DOFs
+//   angular:  J = sum (arm + u) x (m v) + I omega  ->  dJ/du_x = w m_y v_y, dJ/du_y = -w m_x v_x,
+//             dJ/dv_x = -w (arm_y + u_y) m_x, dJ/dv_y = w (arm_x + u_x) m_y, dJ/domega = w I
+__device__ inline double objective_cotangent(const AdjArgs& a, int design, int i, int f, bool is_v) {
+  int k = -1;
+  for (int q = 0; q < a.obj_n; ++q) if (a.obj_ids[q] == f) k = q;
+  if (k < 0) return 0.0;
+  const int nf = a.topo.n_free;
+  const double w = a.obj_w ? a.obj_w[design] : 1.0;
+  const double* m = a.p.inertia.ptr + (long long)design * a.p.inertia.bstride;
+  const double* y = a.ys + ((long long)design * a.n_t + i) * 2 * nf;
+  if (a.obj_kind == DFX_OBJ_KINETIC) return is_v ? w * m[f] * y[nf + f] : 0.0;
+  const int kb = k / 3, c = k - 3 * kb;
+  const int fx = a.obj_ids[3 * kb], fy = a.obj_ids[3 * kb + 1];
+  const double* arm = a.obj_arm + (long long)design * a.obj_arm_bstride + 2 * kb;
+  if (!is_v) return c == 0 ? w * m[fy] * y[nf + fy] : (c == 1 ? -w * m[fx] * y[nf + fx] : 0.0);
+  if (c == 0) return -w * (arm[1] + y[fy]) * m[fx];
+  if (c == 1) return w * (arm[0] + y[fx]) * m[fy];
+  return w * m[f];
+}
 
 struct QuadCtx {
   double *q0, *qnew, *k1, *k7, *ks[4];  // ks: stage values k3..k6

@@ -146,19 +146,12 @@ struct Adj2Args {
   int tmem_cols_per_warp;    // columns of TMEM owned by one warp
 };
 
-// Cotangent of ys[design][i][(is_v ? n_free : 0) + f].  Either read from the caller's tensor `g`, or (g == NULL) formed
-// here for the kinetic objective J = w * sum 1/2 m v^2 over the target DOFs: dJ/dv_f = w m_f v_f, dJ/du = 0.
-// Called once per output time and DOF (cold); kept out of line so that it costs the integration loop no registers.
+// Cotangent of ys[design][i][(is_v ? n_free : 0) + f]: read from the caller's tensor `g`, or (g == NULL) formed here
+// for the device objective.  Called once per output time and DOF (cold); kept out of line so that it costs the
+// integration loop no registers.
 __device__ __noinline__ double cotangent_nl(const AdjArgs& a, int design, int i, int f, bool is_v) {
-  const int nf = a.topo.n_free;
-  const long long at = ((long long)design * a.n_t + i) * 2 * nf + (is_v ? nf : 0) + f;
-  if (a.g) return __ldcs(&a.g[at]);
-  if (!is_v) return 0.0;
-  bool target = false;
-  for (int k = 0; k < a.obj_n; ++k) target |= a.obj_ids[k] == f;
-  if (!target) return 0.0;
-  const double w = a.obj_w ? a.obj_w[design] : 1.0;
-  return w * a.p.inertia.ptr[(long long)design * a.p.inertia.bstride + f] * __ldcs(&a.ys[at]);
+  if (a.g) return __ldcs(&a.g[((long long)design * a.n_t + i) * 2 * a.topo.n_free + (is_v ? a.topo.n_free : 0) + f]);
+  return objective_cotangent(a, design, i, f, is_v);
 }
 
 template <int NT, int NS, int TT>

@@ -512,45 +512,77 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
 }  // extern "C"
 
 namespace {
-__global__ void kinetic_cotangent_kernel(DevTopo T, DfxLeaf inertia, const double* ys, int n_t, const int* ids, int n_ids,
-                                         const double* w, double* g) {
-  // g[b][i][:] = 0 except g[b][i][n_free + f] = w_b * m_f * v_f for the target DOFs (generic-kernel route)
-  const int b = blockIdx.y, i = blockIdx.x, nf = T.n_free;
-  double* gi = g + ((long long)b * n_t + i) * 2 * nf;
-  const double* yi = ys + ((long long)b * n_t + i) * 2 * nf;
+__global__ void objective_cotangent_kernel(AdjArgs a, double* g) {
+  // materialised cotangent of the device objective for the generic adjoint kernels: g[b][i][:]
+  const int b = blockIdx.y, i = blockIdx.x, nf = a.topo.n_free;
+  double* gi = g + ((long long)b * a.n_t + i) * 2 * nf;
   for (int k = threadIdx.x; k < 2 * nf; k += blockDim.x) gi[k] = 0.0;
   __syncthreads();
-  const double* m = inertia.ptr + (long long)b * inertia.bstride;
-  const double wb = w ? w[b] : 1.0;
-  for (int k = threadIdx.x; k < n_ids; k += blockDim.x) gi[nf + ids[k]] = wb * m[ids[k]] * yi[nf + ids[k]];
+  for (int k = threadIdx.x; k < 2 * a.obj_n; k += blockDim.x) {
+    const bool is_v = k >= a.obj_n;
+    const int f = a.obj_ids[is_v ? k - a.obj_n : k];
+    gi[(is_v ? nf : 0) + f] = objective_cotangent(a, b, i, f, is_v);
+  }
 }
 
-__global__ void kinetic_energy_kernel(DevTopo T, DfxLeaf inertia, const double* ys, int n_t, const int* ids, int n_ids,
-                                      double* value, double* inertia_bar) {
-  // one CTA per design: J = sum_t sum_f 1/2 m v^2 ; dJ/dm_f = sum_t 1/2 v^2
+__global__ void objective_kernel(DevTopo T, DfxLeaf inertia, const double* ys, int n_t, DfxObjective obj, double* value,
+                                 double* inertia_bar, double* arm_bar) {
+  // one CTA per design: J (weights not applied) and its explicit derivatives w.r.t. the inertia and the arms
   __shared__ double red[40];
   const int b = blockIdx.x, nf = T.n_free;
   const double* m = inertia.ptr + (long long)b * inertia.bstride;
+  const int* ids = obj.target_free_ids;
   if (inertia_bar) for (int k = threadIdx.x; k < nf; k += blockDim.x) inertia_bar[(long long)b * nf + k] = 0.0;
   __syncthreads();
   double acc = 0.0;
-  for (int k = threadIdx.x; k < n_ids; k += blockDim.x) {
-    const int f = ids[k];
-    double s2 = 0.0;
-    for (int i = 0; i < n_t; ++i) { const double v = ys[((long long)b * n_t + i) * 2 * nf + nf + f]; s2 = fma(v, v, s2); }
-    acc += 0.5 * m[f] * s2;
-    if (inertia_bar) inertia_bar[(long long)b * nf + f] = 0.5 * s2;
+  if (obj.kind == DFX_OBJ_KINETIC) {
+    for (int k = threadIdx.x; k < obj.n_target; k += blockDim.x) {
+      const int f = ids[k];
+      double s2 = 0.0;
+      for (int i = 0; i < n_t; ++i) { const double v = ys[((long long)b * n_t + i) * 2 * nf + nf + f]; s2 = fma(v, v, s2); }
+      acc += 0.5 * m[f] * s2;
+      if (inertia_bar) inertia_bar[(long long)b * nf + f] = 0.5 * s2;
+    }
+  } else {
+    for (int kb = threadIdx.x; kb < obj.n_target / 3; kb += blockDim.x) {
+      const int fx = ids[3 * kb], fy = ids[3 * kb + 1], ft = ids[3 * kb + 2];
+      const double* arm = obj.arm + (long long)b * obj.arm_bstride + 2 * kb;
+      double s_pxvy = 0.0, s_pyvx = 0.0, s_vy = 0.0, s_vx = 0.0, s_w = 0.0;
+      for (int i = 0; i < n_t; ++i) {
+        const double* y = ys + ((long long)b * n_t + i) * 2 * nf;
+        const double px = arm[0] + y[fx], py = arm[1] + y[fy], vx = y[nf + fx], vy = y[nf + fy];
+        s_pxvy = fma(px, vy, s_pxvy); s_pyvx = fma(py, vx, s_pyvx); s_vx += vx; s_vy += vy; s_w += y[nf + ft];
+      }
+      acc += m[fy] * s_pxvy - m[fx] * s_pyvx + m[ft] * s_w;
+      if (inertia_bar) {
+        inertia_bar[(long long)b * nf + fx] = -s_pyvx;
+        inertia_bar[(long long)b * nf + fy] = s_pxvy;
+        inertia_bar[(long long)b * nf + ft] = s_w;
+      }
+      if (arm_bar) {
+        arm_bar[((long long)b * (obj.n_target / 3) + kb) * 2] = m[fy] * s_vy;
+        arm_bar[((long long)b * (obj.n_target / 3) + kb) * 2 + 1] = -m[fx] * s_vx;
+      }
+    }
   }
   acc = block_sum(acc, red);
   if (threadIdx.x == 0) value[b] = acc;
 }
 
+int check_objective(const DfxObjective* obj) {
+  if (obj->kind != DFX_OBJ_KINETIC && obj->kind != DFX_OBJ_ANGULAR) return fail(DFX_ERR_UNSUPPORTED, "unknown objective kind %d", obj->kind);
+  if (obj->n_target < 0 || (obj->n_target > 0 && !obj->target_free_ids)) return fail(DFX_ERR_INVALID, "bad objective");
+  if (obj->kind == DFX_OBJ_ANGULAR && (obj->n_target % 3 != 0 || !obj->arm))
+    return fail(DFX_ERR_INVALID, "the angular-momentum objective needs (x, y, theta) triples of target DOFs and the arms");
+  return DFX_OK;
+}
+
 int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
-                 int64_t ts_bstride, int n_t, const double* g_, const DfxKineticObjective* obj, double rtol, double atol,
+                 int64_t ts_bstride, int n_t, const double* g_, const DfxObjective* obj, double rtol, double atol,
                  int64_t aug_size, const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads,
                  DfxStats* stats, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!t || !ys || !ts || (!g_ && !obj)) return fail(DFX_ERR_INVALID, "NULL argument");
-  if (obj && (obj->n_target < 0 || (obj->n_target > 0 && !obj->target_free_ids))) return fail(DFX_ERR_INVALID, "bad objective");
+  if (obj) { if (int rc = check_objective(obj)) return rc; }
   if (batch <= 0 || n_t < 1) return fail(DFX_ERR_INVALID, "batch and n_t must be positive");
   if (int rc = check_params(t->dev, params)) return rc;
   cudaStream_t stream = (cudaStream_t)stream_;
@@ -569,7 +601,10 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   adjoint_sizes(T, q, sz, cluster);
   plan(sz, a.place.off, &smem, &g, cluster);
   a.ys = ys; a.ts = ts; a.ts_bstride = ts_bstride; a.n_t = n_t; a.g = g_;
-  if (obj) { a.obj_ids = obj->target_free_ids; a.obj_n = obj->n_target; a.obj_w = obj->weights; }
+  if (obj) {
+    a.obj_kind = obj->kind; a.obj_ids = obj->target_free_ids; a.obj_n = obj->n_target; a.obj_w = obj->weights;
+    a.obj_arm = obj->arm; a.obj_arm_bstride = obj->arm_bstride;
+  }
   a.rtol = rtol; a.atol = atol;
   if (aug_size <= 0) {
     // count the leaves listed in DfxParams: y, y_bar, t0_bar, then every leaf
@@ -620,8 +655,7 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
     double* gtmp = nullptr;
     if (!g_) {
       CUDA_TRY(cudaMallocAsync((void**)&gtmp, (size_t)batch * n_t * 2 * T.n_free * sizeof(double), stream));
-      kinetic_cotangent_kernel<<<dim3(n_t, batch), 256, 0, stream>>>(T, params->inertia, ys, n_t, obj->target_free_ids,
-                                                                    obj->n_target, obj->weights, gtmp);
+      objective_cotangent_kernel<<<dim3(n_t, batch), 256, 0, stream>>>(a, gtmp);
       a.g = gtmp;
     }
     const int threads = pick_threads(T, opt ? opt->threads : 0);
@@ -652,25 +686,24 @@ int dfx_adjoint(const DfxTopology* t, const DfxParams* params, int batch, const 
                       stats, workspace, workspace_bytes, stream_);
 }
 
-int dfx_adjoint_kinetic(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
-                        int64_t ts_bstride, int n_t, const DfxKineticObjective* obj, double rtol, double atol,
-                        int64_t aug_size, const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads,
-                        DfxStats* stats, void* workspace, size_t workspace_bytes, void* stream_) {
+int dfx_adjoint_objective(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, const double* ts,
+                          int64_t ts_bstride, int n_t, const DfxObjective* obj, double rtol, double atol,
+                          int64_t aug_size, const DfxOptions* opt, double* y0_bar, double* ts_bar, const DfxParamGrads* grads,
+                          DfxStats* stats, void* workspace, size_t workspace_bytes, void* stream_) {
   if (!obj) return fail(DFX_ERR_INVALID, "NULL argument");
   return adjoint_impl(t, params, batch, ys, ts, ts_bstride, n_t, nullptr, obj, rtol, atol, aug_size, opt, y0_bar, ts_bar, grads,
                       stats, workspace, workspace_bytes, stream_);
 }
 
-int dfx_kinetic_energy(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, int n_t,
-                       const DfxKineticObjective* obj, double* value, double* inertia_bar, void* stream_) {
+int dfx_objective(const DfxTopology* t, const DfxParams* params, int batch, const double* ys, int n_t, const DfxObjective* obj,
+                  double* value, double* inertia_bar, double* arm_bar, void* stream_) {
   if (!t || !params || !ys || !obj || !value || !params->inertia.ptr) return fail(DFX_ERR_INVALID, "NULL argument");
-  kinetic_energy_kernel<<<batch, 128, 0, (cudaStream_t)stream_>>>(t->dev, params->inertia, ys, n_t, obj->target_free_ids,
-                                                                 obj->n_target, value, inertia_bar);
+  if (int rc = check_objective(obj)) return rc;
+  objective_kernel<<<batch, 128, 0, (cudaStream_t)stream_>>>(t->dev, params->inertia, ys, n_t, *obj, value, inertia_bar, arm_bar);
   cudaError_t e = cudaGetLastError();
-  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "kinetic_energy launch failed: %s", cudaGetErrorString(e));
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "objective launch failed: %s", cudaGetErrorString(e));
   return DFX_OK;
 }
-
 
 }  // extern "C"
 

@@ -224,31 +224,40 @@ class _OdeSolve(torch.autograd.Function):
         return (None, None, y0_bar, ts_bar, *out)
 
 
-class _KineticObjective(torch.autograd.Function):
-    """J[b] = kinetic energy of the target DOFs summed over the output times, evaluated on the device
-    (dfx_forward + dfx_kinetic_energy); backward = dfx_adjoint_kinetic, whose kernel forms the cotangent
-    dJ/dys = m v itself, plus the explicit dJ/d(inertia).  The trajectory never leaves libdfx buffers."""
+class _DeviceObjective(torch.autograd.Function):
+    """J[b] evaluated on the device (dfx_forward + dfx_objective): the kinetic energy of the target DOFs or their
+    angular momentum about a spin centre, summed over the output times; backward = dfx_adjoint_objective, whose
+    kernel forms the cotangent dJ/dys itself, plus the explicit dJ/d(inertia) and dJ/d(arm).  The trajectory never
+    leaves libdfx buffers."""
 
     @staticmethod
-    def forward(ctx, solver, meta, target_ids, y0, ts, *leaf_tensors):
+    def forward(ctx, solver, meta, target_ids, arm, y0, ts, *leaf_tensors):
         names = meta["names"]
         leaves = dict(zip(names, leaf_tensors))
         ps = _abi.ParamSet(solver.spec, meta["batch"], leaves, meta["per_bond"], meta["damping_per_dof"])
         ys, stats = solver.lib_forward(ps, y0, ts)
         solver.last_forward_stats = stats
-        value, ibar = solver._lib.kinetic_energy(solver.handle, ps, ys, target_ids, want_inertia_bar=True)
-        ctx.solver, ctx.meta, ctx.ps, ctx.target_ids = solver, meta, ps, target_ids
-        ctx.save_for_backward(ys, ts, y0, ibar)
+        arm_c = None if arm is None else arm.contiguous()
+        value, ibar, abar = solver._lib.objective_value(solver.handle, ps, ys, target_ids, meta["kind"], arm_c)
+        ctx.solver, ctx.meta, ctx.ps, ctx.target_ids, ctx.arm = solver, meta, ps, target_ids, arm_c
+        ctx.arm_batched = arm is not None and arm.dim() == 3
+        ctx.save_for_backward(ys, ts, y0, ibar, abar if abar is not None else ibar)
         return value
 
     @staticmethod
     def backward(ctx, gJ):
         solver, meta, ps = ctx.solver, ctx.meta, ctx.ps
-        ys, ts, y0, ibar = ctx.saved_tensors
-        y0_bar, ts_bar, grads, stats = solver._lib.adjoint_kinetic(
-            solver.handle, ps, ys, ts, ctx.target_ids, gJ, solver.rtol, solver.atol, meta["aug_size"], solver.options)
+        ys, ts, y0, ibar, abar = ctx.saved_tensors
+        y0_bar, ts_bar, grads, stats = solver._lib.adjoint_objective(
+            solver.handle, ps, ys, ts, ctx.target_ids, gJ, solver.rtol, solver.atol, meta["aug_size"], solver.options,
+            meta["kind"], ctx.arm)
         solver.last_adjoint_stats = stats
         grads["inertia"] = grads["inertia"] + gJ[:, None] * ibar  # explicit dependence of J on the masses
+        arm_bar = None
+        if ctx.arm is not None:
+            arm_bar = gJ[:, None, None] * abar
+            if not ctx.arm_batched:
+                arm_bar = arm_bar.sum(0)
         out = []
         for n in meta["names"]:
             gl = grads[n]
@@ -257,7 +266,7 @@ class _KineticObjective(torch.autograd.Function):
             y0_bar = y0_bar.sum(0)
         if ts.dim() == 1:
             ts_bar = ts_bar.sum(0)
-        return (None, None, None, y0_bar, ts_bar, *out)
+        return (None, None, None, arm_bar, y0_bar, ts_bar, *out)
 
 
 class DynamicSolver:
@@ -293,14 +302,19 @@ class DynamicSolver:
                     aug_size=int(aug_size))
         return _OdeSolve.apply(self, meta, y0.contiguous(), ts.contiguous(), *[leaves[n].contiguous() for n in names])
 
-    def odeint_kinetic(self, y0, ts, leaves, target_free_ids, batch, per_bond=(), damping_per_dof=False, aug_size=0):
-        """J[B] = sum_t sum_{f in target_free_ids} 1/2 m_f v_f(t)^2 of the solution of `odeint`; differentiable
-        (forward + objective + adjoint inside libdfx, see `_KineticObjective`)."""
+    def odeint_objective(self, y0, ts, leaves, target_free_ids, batch, per_bond=(), damping_per_dof=False, aug_size=0,
+                         kind=_abi.DFX_OBJ_KINETIC, arm=None):
+        """J[B] of the solution of `odeint` (forward + objective + adjoint inside libdfx, see `_DeviceObjective`);
+        differentiable.  kind DFX_OBJ_KINETIC: sum_t sum_{f in target_free_ids} 1/2 m_f v_f(t)^2;
+        DFX_OBJ_ANGULAR: angular momentum of the target blocks with `arm` = reference centroid - spin centre."""
         names = [n for n in _abi.LEAF_NAMES if n in leaves]
         meta = dict(names=names, batch=batch, per_bond=tuple(per_bond), damping_per_dof=damping_per_dof,
-                    aug_size=int(aug_size))
-        return _KineticObjective.apply(self, meta, target_free_ids, y0.contiguous(), ts.contiguous(),
-                                       *[leaves[n].contiguous() for n in names])
+                    aug_size=int(aug_size), kind=int(kind))
+        return _DeviceObjective.apply(self, meta, target_free_ids, arm, y0.contiguous(), ts.contiguous(),
+                                      *[leaves[n].contiguous() for n in names])
+
+    def odeint_kinetic(self, y0, ts, leaves, target_free_ids, batch, per_bond=(), damping_per_dof=False, aug_size=0):
+        return self.odeint_objective(y0, ts, leaves, target_free_ids, batch, per_bond, damping_per_dof, aug_size)
 
     # -- reference-level solve ---------------------------------------------------------------
     def solve(self, state0, timepoints, control_params: ControlParams, batch: Optional[int] = None, per_bond=()):
@@ -324,19 +338,40 @@ class DynamicSolver:
             raise ValueError("target blocks of the on-device kinetic objective must not have constrained DOFs")
         return torch.as_tensor(pos.astype(np.int32), device=self.device)
 
+    def angular_momentum_objective(self, state0, timepoints, control_params: ControlParams, target_blocks, spin_center,
+                                   batch: Optional[int] = None, per_bond=(), inertia_full=None):
+        """Fused objective of the reference's spin problem (`problems/quads_spin.py:395-428`, `energy.py:502-519`):
+        angular momentum of `target_blocks` about `spin_center` ((2,) or (B, 2)), summed over blocks and output times."""
+        return self._fused_objective(_abi.DFX_OBJ_ANGULAR, state0, timepoints, control_params, target_blocks, batch,
+                                     per_bond, inertia_full, spin_center)
+
     def kinetic_objective(self, state0, timepoints, control_params: ControlParams, target_blocks,
                           batch: Optional[int] = None, per_bond=(), inertia_full=None):
         """Fused objective of the reference's focusing problems (`problems/quads_focusing.py:453-467`):
         sum over output times of the kinetic energy of `target_blocks`.  -> (B,) tensor (scalar without batch),
         differentiable w.r.t. control_params; forward, objective and adjoint all run inside libdfx."""
+        return self._fused_objective(_abi.DFX_OBJ_KINETIC, state0, timepoints, control_params, target_blocks, batch,
+                                     per_bond, inertia_full, None)
+
+    def _fused_objective(self, kind, state0, timepoints, control_params, target_blocks, batch, per_bond, inertia_full,
+                         spin_center):
         spec, dev = self.spec, self.device
         leaves, pb, dpd, aug_size = lower_params(spec, self.drive, control_params, batch, dev, per_bond, inertia_full)
         free = torch.as_tensor(spec.free_dofs, device=dev)
         state0 = _as_t(state0, dev)
         y0 = state0.reshape(*state0.shape[:-3], 2, spec.n_blocks * 3)[..., free]
         y0 = y0.reshape(*y0.shape[:-2], 2 * spec.n_free)
-        J = self.odeint_kinetic(y0, _as_t(timepoints, dev), leaves, self.target_free_ids(target_blocks),
-                                1 if batch is None else batch, pb, dpd, aug_size)
+        arm = None
+        if kind == _abi.DFX_OBJ_ANGULAR:
+            # arm = reference centroid of the target blocks - spin centre (differentiable w.r.t. both)
+            tb = torch.as_tensor(np.asarray(target_blocks, dtype=np.int64), device=dev)
+            cen = _as_t(control_params.geometrical_params.block_centroids, dev)
+            center = _as_t(spin_center, dev)
+            arm = cen.index_select(-2, tb) - (center[..., None, :] if center.dim() == 2 else center)
+            if batch is not None and arm.dim() == 2:
+                arm = arm[None].expand(batch, -1, -1)
+        J = self.odeint_objective(y0, _as_t(timepoints, dev), leaves, self.target_free_ids(target_blocks),
+                                  1 if batch is None else batch, pb, dpd, aug_size, kind, arm)
         return J[0] if batch is None else J
 
     def expand_fields(self, ys, ts, control_params):

@@ -123,11 +123,20 @@ class _ProblemBase:
             return kinetic_energy(v, m)
         return (m[:, None] * v ** 2 / 2).sum(dim=(1, 2, 3))
 
-    def target_angular_momentum(self, design, spin_center="center"):
+    def target_angular_momentum(self, design, spin_center="center", batch=None, fused=False):
         """objective of the reference's spin problem (`problems/quads_spin.py:395-428`): angular momentum of the target
         blocks about `spin_center`, summed over blocks and output times.  "center" = mean reference centroid of the
         target blocks for THIS design, held fixed (not differentiated), as in the reference where it is evaluated
-        once from the forward input."""
+        once from the forward input.  `fused=True` (and batches) evaluate it inside libdfx
+        (`DynamicSolver.angular_momentum_objective`)."""
+        if fused or batch is not None:
+            s = self.solver
+            cnv, cen, inertia = self.device_geometry()(design, self.density)
+            tb = torch.as_tensor(self.target_blocks(), device=s.device)
+            center = cen.index_select(-2, tb).mean(-2).detach() if isinstance(spin_center, str) else spin_center
+            cp = self.control_params(design, s.device, geom=(cnv, cen))
+            return s.angular_momentum_objective(self.state0(s.device), self.timepoints(s.device), cp, self.target_blocks(),
+                                                center, batch=batch, inertia_full=inertia)
         sol = self.solve(design)
         dev = sol.fields.device
         tb = torch.as_tensor(self.target_blocks(), device=dev)

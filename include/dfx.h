@@ -184,28 +184,36 @@ int dfx_adjoint(const DfxTopology* topo, const DfxParams* params, int batch,
                 double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
                 void* workspace, size_t workspace_bytes, void* stream);
 
-/* ---- objective on the device: the reference's target kinetic energy
- *   J_b = w_b * sum_t sum_{f in target} 1/2 m_f v_f(t)^2     (problems/quads_focusing.py:453-467, energy.py:494-499)
- * `target_free_ids` are indices into the free-DOF vector (the three DOFs of every target block; they must be free).
- * dfx_kinetic_energy evaluates J (w = 1) and, optionally, its explicit derivative w.r.t. the reduced inertia;
- * dfx_adjoint_kinetic is dfx_adjoint with the cotangent g = dJ/dys generated inside the kernel (g is never
- * materialised: no 3.5 MB per design of cotangent traffic), weights[b] = dL/dJ_b. */
-typedef struct DfxKineticObjective {
+/* ---- objectives on the device ------------------------------------------------------------------
+ * DFX_OBJ_KINETIC   J_b = w_b sum_t sum_{f in target} 1/2 m_f v_f(t)^2
+ *                   (target kinetic energy: problems/quads_focusing.py:453-467, energy.py:494-499)
+ * DFX_OBJ_ANGULAR   J_b = w_b sum_t sum_{k in target blocks} (arm_k + u_k(t)) x (m v_k(t))_xy + I_k omega_k(t)
+ *                   (angular momentum about a spin centre: problems/quads_spin.py:395-428, energy.py:502-519;
+ *                    arm_k = reference centroid of block k minus the spin centre)
+ * `target_free_ids` are indices into the free-DOF vector: the three DOFs (x, y, theta) of every target block, block
+ * after block; they must be free.  dfx_objective evaluates J (w = 1) and, optionally, its explicit derivatives w.r.t.
+ * the reduced inertia and the arms; dfx_adjoint_objective is dfx_adjoint with the cotangent g = dJ/dys generated
+ * inside the kernel (g is never materialised: no 3.5 MB per design of cotangent traffic), weights[b] = dL/dJ_b. */
+enum { DFX_OBJ_KINETIC = 0, DFX_OBJ_ANGULAR = 1 };
+typedef struct DfxObjective {
+  int32_t kind;
+  int32_t n_target;               /* number of target DOFs (3 per target block) */
   const int32_t* target_free_ids; /* device, [n_target] */
-  int32_t n_target;
   const double* weights;          /* device, [B], or NULL (= 1) */
-} DfxKineticObjective;
+  const double* arm;              /* device, [B or 1][n_target / 3][2]; DFX_OBJ_ANGULAR only */
+  int64_t arm_bstride;            /* doubles between designs (0 = shared) */
+} DfxObjective;
 
-int dfx_kinetic_energy(const DfxTopology* topo, const DfxParams* params, int batch, const double* ys, int n_t,
-                       const DfxKineticObjective* obj, double* value /*[B]*/, double* inertia_bar /*[B][n_free] or NULL*/,
-                       void* stream);
+int dfx_objective(const DfxTopology* topo, const DfxParams* params, int batch, const double* ys, int n_t,
+                  const DfxObjective* obj, double* value /*[B]*/, double* inertia_bar /*[B][n_free] or NULL*/,
+                  double* arm_bar /*[B][n_target / 3][2] or NULL*/, void* stream);
 
-int dfx_adjoint_kinetic(const DfxTopology* topo, const DfxParams* params, int batch,
-                        const double* ys, const double* ts, int64_t ts_bstride, int n_t,
-                        const DfxKineticObjective* obj, double rtol, double atol, int64_t aug_size,
-                        const DfxOptions* opt,
-                        double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
-                        void* workspace, size_t workspace_bytes, void* stream);
+int dfx_adjoint_objective(const DfxTopology* topo, const DfxParams* params, int batch,
+                          const double* ys, const double* ts, int64_t ts_bstride, int n_t,
+                          const DfxObjective* obj, double rtol, double atol, int64_t aug_size,
+                          const DfxOptions* opt,
+                          double* y0_bar, double* ts_bar, const DfxParamGrads* grads, DfxStats* stats,
+                          void* workspace, size_t workspace_bytes, void* stream);
 
 /* ---- design -> solver parameters on the device ------------------------------------------------
  * Replaces the reference's design maps and their JAX-derived VJPs for lattices whose every polygon vertex is

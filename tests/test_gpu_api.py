@@ -267,7 +267,7 @@ def test_status_flags_and_per_design_inputs():
 
 @pytest.mark.parametrize("kernel", ["fast", "generic"])
 def test_fused_kinetic_objective_equals_the_unfused_path(kernel, monkeypatch):
-    """dfx_forward + dfx_kinetic_energy + dfx_adjoint_kinetic (cotangent formed inside the adjoint kernel)
+    """dfx_forward + dfx_objective + dfx_adjoint_objective (cotangent formed inside the adjoint kernel)
     against the torch objective on the expanded fields + dfx_adjoint with a materialised cotangent; batch of designs
     with non-uniform upstream weights; the generic adjoint kernel takes the cotangent-materialising route."""
     if kernel == "generic":
@@ -466,7 +466,7 @@ def test_c_abi_error_behaviour_on_the_device():
     assert fwd(None, n_t, need) != 0 and b"NULL" in lib.dfx_last_error()
     assert fwd(y0.data_ptr(), 0, need) != 0
     assert fwd(y0.data_ptr(), n_t, need, batch=0) != 0
-    assert lib.dfx_adjoint_kinetic(h, C.byref(p), 1, C.c_void_p(ys.data_ptr()), C.c_void_p(ts.data_ptr()), C.c_int64(0), n_t, None,
+    assert lib.dfx_adjoint_objective(h, C.byref(p), 1, C.c_void_p(ys.data_ptr()), C.c_void_p(ts.data_ptr()), C.c_int64(0), n_t, None,
                                    C.c_double(1e-8), C.c_double(1e-4), C.c_int64(0), None, None, None, None, None, None,
                                    C.c_size_t(0), stream) != 0
     torch.cuda.synchronize()
@@ -475,3 +475,37 @@ def test_c_abi_error_behaviour_on_the_device():
     with pytest.raises(RuntimeError):  # CUDA-only: there is no CPU path
         from difflexmm_b200.dynamics import DynamicSolver
         DynamicSolver(P.spec, P.drive, device="cpu")
+
+
+@pytest.mark.parametrize("kernel", ["fast", "generic"])
+def test_fused_angular_momentum_objective_equals_the_unfused_path(kernel, monkeypatch):
+    """DFX_OBJ_ANGULAR: value, explicit inertia / arm derivatives and the in-kernel cotangent (displacement AND
+    velocity parts) against the torch objective on the expanded fields + dfx_adjoint"""
+    if kernel == "generic":
+        monkeypatch.setenv("DFX_ADJOINT_KERNEL", "generic")
+        monkeypatch.setenv("DFX_FORWARD_KERNEL", "generic")
+    P = _problem()
+    P.setup()
+    hs0, vs0 = P.initial_design()
+    center = P.geometry.block_centroids(hs0, vs0)[P.target_blocks()].mean(0) + torch.tensor([3.0, -2.0], dtype=torch.float64)
+    res = []
+    for fused in (False, True):
+        hs, vs = hs0.clone().requires_grad_(True), vs0.clone().requires_grad_(True)
+        L = P.target_angular_momentum((hs, vs), spin_center=center, fused=fused)
+        assert L.dim() == 0
+        L.backward()
+        res.append((L.item(), hs.grad.clone(), vs.grad.clone()))
+    (L0, gh0, gv0), (L1, gh1, gv1) = res
+    assert abs(L0 - L1) <= 1e-11 * abs(L0)
+    assert rel_l2(gh1.numpy(), gh0.numpy()) <= 1e-9 and rel_l2(gv1.numpy(), gv0.numpy()) <= 1e-9
+    # a batch with per-design weights
+    B = 2
+    hsb, vsb = P.random_ensemble(B, noise=0.03)
+    hsb, vsb = hsb.cuda().requires_grad_(True), vsb.cuda().requires_grad_(True)
+    Lb = P.target_angular_momentum((hsb, vsb), spin_center=center, batch=B)
+    (Lb * torch.tensor([1.0, -2.0], dtype=torch.float64, device="cuda")).sum().backward()
+    hs1, vs1 = hsb[1].detach().cpu().requires_grad_(True), vsb[1].detach().cpu().requires_grad_(True)
+    L1s = P.target_angular_momentum((hs1, vs1), spin_center=center)
+    (-2.0 * L1s).backward()
+    assert abs(Lb[1].item() - L1s.item()) <= 1e-10 * abs(L1s.item())
+    assert rel_l2(hsb.grad[1].cpu().numpy(), hs1.grad.numpy()) <= 1e-8

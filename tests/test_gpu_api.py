@@ -509,3 +509,23 @@ def test_fused_angular_momentum_objective_equals_the_unfused_path(kernel, monkey
     (-2.0 * L1s).backward()
     assert abs(Lb[1].item() - L1s.item()) <= 1e-10 * abs(L1s.item())
     assert rel_l2(hsb.grad[1].cpu().numpy(), hs1.grad.numpy()) <= 1e-8
+
+
+def test_fused_objective_on_the_kagome_lattice():
+    """the fused design-to-gradient path (device geometry with three shift arrays, triangles) on a kagome lattice
+    against the unfused torch path"""
+    from difflexmm_b200.problems import KagomeFocusing
+    P = KagomeFocusing(n1_cells=8, n2_cells=6, simulation_time=0.01, n_timepoints=6, target_shift=(1, 1))
+    P.setup()
+    rng = np.random.default_rng(2)
+    base = [d + 0.2 * torch.from_numpy(rng.standard_normal(d.shape)) for d in P.initial_design()]
+    res = []
+    for fused in (False, True):
+        d = [x.clone().requires_grad_(True) for x in base]
+        J = P.target_kinetic_energy(d, fused=fused)
+        J.backward()
+        res.append((J.item(), [x.grad.clone() for x in d]))
+    (J0, g0), (J1, g1) = res
+    assert abs(J0 - J1) <= 1e-11 * abs(J0)
+    for a, b in zip(g1, g0):
+        assert rel_l2(a.numpy(), b.numpy()) <= 1e-8

@@ -10,14 +10,38 @@ from typing import Sequence
 import numpy as np
 import torch
 
-from . import _lib
-
 _F64 = torch.float64
+
+
+def design_vertex_table(geometry):
+    """-> (base (n_blocks, n_npb, 2), node_design (n_blocks, n_npb) int64 with -1 = none, shapes, sizes): every polygon
+    vertex of the lattice is `base + design_flat[node_design]`, design_flat = the design arrays concatenated.  Read off
+    the torch map `reference_node_vectors` by probing it once (host only, no GPU needed)."""
+    if not hasattr(geometry, "reference_node_vectors"):
+        geometry.compute_geometry()
+    if not hasattr(geometry, "reference_node_vectors"):
+        raise TypeError(f"{type(geometry).__name__} has no per-vertex design shifts (use its torch maps)")
+    shapes = [tuple(s) for s in geometry.design_shapes]
+    sizes = [int(np.prod(s[:-1])) for s in shapes]
+    base = geometry.reference_node_vectors(*[torch.zeros(s, dtype=_F64) for s in shapes])
+    # probe: design 2-vector k = (k + 1, -(k + 1)) -> the vertex offset identifies k
+    probe, k0 = [], 0
+    for s, n in zip(shapes, sizes):
+        k = torch.arange(k0 + 1, k0 + n + 1, dtype=_F64).reshape(s[:-1])
+        probe.append(torch.stack([k, -k], -1))
+        k0 += n
+    off = geometry.reference_node_vectors(*probe) - base
+    idx = torch.round(off[..., 0]).to(torch.int64)
+    tol = 1e-9 * max(1.0, float(base.abs().max()))
+    if (off[..., 0] - idx).abs().max() > tol or (off[..., 1] + idx).abs().max() > tol or idx.min() < 0:
+        raise ValueError("reference_node_vectors is not `base + one design vector per vertex`")
+    return base, idx - 1, shapes, sizes
 
 
 class _DesignToParams(torch.autograd.Function):
     @staticmethod
     def forward(ctx, dg, design, density):
+        from . import _lib
         cnv, cen, inertia = _lib.geometry_forward(dg.handle, design, density)
         ctx.dg = dg
         ctx.save_for_backward(design, density)
@@ -27,6 +51,7 @@ class _DesignToParams(torch.autograd.Function):
     def backward(ctx, cnv_bar, cen_bar, inertia_bar):
         design, density = ctx.saved_tensors
         want_rho = ctx.needs_input_grad[2]
+        from . import _lib
         design_bar, rho_bar = _lib.geometry_vjp(ctx.dg.handle, design, density, cnv_bar, cen_bar, inertia_bar, want_rho)
         if want_rho and density.dim() == 0:
             rho_bar = rho_bar.sum()
@@ -37,30 +62,13 @@ class DeviceGeometry:
     """Device-side design map of one lattice geometry (`QuadGeometry` or `KagomeGeometry` of `difflexmm_b200.geometry`)."""
 
     def __init__(self, geometry, device="cuda"):
-        if not hasattr(geometry, "reference_node_vectors"):
-            geometry.compute_geometry()
-        if not hasattr(geometry, "reference_node_vectors"):
-            raise TypeError(f"{type(geometry).__name__} has no per-vertex design shifts (use its torch maps)")
+        from . import _lib  # raises if the CUDA library is missing
+        base, node_design, self.shapes, self.sizes = design_vertex_table(geometry)
         self.geometry = geometry
         self.device = torch.device(device)
-        self.shapes = [tuple(s) for s in geometry.design_shapes]
-        self.sizes = [int(np.prod(s[:-1])) for s in self.shapes]
         self.n_design = sum(self.sizes)
-        zeros = [torch.zeros(s, dtype=_F64) for s in self.shapes]
-        base = geometry.reference_node_vectors(*zeros)
-        # probe: design 2-vector k = (k + 1, -(k + 1)) -> vertex offset identifies k
-        probe, k0 = [], 0
-        for s, n in zip(self.shapes, self.sizes):
-            k = torch.arange(k0 + 1, k0 + n + 1, dtype=_F64).reshape(s[:-1])
-            probe.append(torch.stack([k, -k], -1))
-            k0 += n
-        off = geometry.reference_node_vectors(*probe) - base
-        idx = torch.round(off[..., 0]).to(torch.int64)
-        tol = 1e-9 * max(1.0, float(base.abs().max()))
-        if (off[..., 0] - idx).abs().max() > tol or (off[..., 1] + idx).abs().max() > tol or idx.min() < 0:
-            raise ValueError("reference_node_vectors is not `base + one design vector per vertex`")
         self.n_blocks, self.n_npb = base.shape[0], base.shape[1]
-        self.handle = _lib.GeometryHandle(self.n_blocks, self.n_npb, self.n_design, base.numpy(), (idx - 1).numpy(),
+        self.handle = _lib.GeometryHandle(self.n_blocks, self.n_npb, self.n_design, base.numpy(), node_design.numpy(),
                                           self.device.index if self.device.index is not None else torch.cuda.current_device())
         self.reference_points = geometry.reference_points.to(self.device)
 

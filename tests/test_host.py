@@ -286,3 +286,30 @@ def test_save_load_data_is_pickle_compatible_with_the_reference(tmp_path):
     finally:
         del sys.modules["difflexmm"], sys.modules["difflexmm.utils"]
     assert isinstance(load_data(ref_file), SolutionData)
+
+
+def test_design_vertex_table_of_the_device_geometry():
+    """the vertex -> design-variable table handed to dfx_geometry_create, against the reference's indexing
+    (geometry.py:866-883 quads: vertex 0..3 <- hs[a+1,b], vs[a,b+1], hs[a,b], vs[a,b]; kagome :690-720)"""
+    import torch
+    from difflexmm_b200.geometry import KagomeGeometry, QuadGeometry, RotatedSquareGeometry
+    from difflexmm_b200.geometry_device import design_vertex_table
+    n1, n2 = 5, 4
+    geo = QuadGeometry(n1, n2, spacing=15.0, bond_length=2.25)
+    geo.compute_geometry()
+    base, nd, shapes, sizes = design_vertex_table(geo)
+    assert shapes == [(n1 + 1, n2, 2), (n1, n2 + 1, 2)] and sizes == [(n1 + 1) * n2, n1 * (n2 + 1)]
+    n_hs = sizes[0]
+    for blk in range(n1 * n2):
+        a, b = blk % n1, blk // n1  # row-major over n2 then n1 (geometry._grid_row_major)
+        want = [(a + 1) * n2 + b, n_hs + a * (n2 + 1) + b + 1, a * n2 + b, n_hs + a * (n2 + 1) + b]
+        assert nd[blk].tolist() == want
+    assert torch.allclose(base, geo.reference_node_vectors(*[torch.zeros(s, dtype=torch.float64) for s in shapes]))
+    kag = KagomeGeometry(4, 3)
+    kag.compute_geometry()
+    base, nd, shapes, sizes = design_vertex_table(kag)
+    assert nd.shape == (24, 3) and nd.min() >= 0 and nd.max() == sum(sizes) - 1
+    counts = np.bincount(nd.numpy().ravel(), minlength=sum(sizes))
+    assert counts.min() == 1 and counts.max() == 2  # boundary shifts feed one vertex, interior ones two
+    with pytest.raises(TypeError):
+        design_vertex_table(RotatedSquareGeometry(2, 2))

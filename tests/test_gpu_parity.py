@@ -3,6 +3,8 @@ the literal restatement of the reference and against the C++ oracle on the same 
 
 Tolerances are the north star's: trajectories rel-L2 <= 1e-6, parameter gradients rel-L2 <= 1e-5."""
 
+import math
+
 import numpy as np
 import pytest
 import torch
@@ -236,3 +238,50 @@ def test_device_math():
     assert _lib.lib.dfx_math_selftest(C.c_void_p(xa.data_ptr()), C.c_void_p(ys_.data_ptr()), C.c_void_p(o1.data_ptr()),
                                       C.c_void_p(o4.data_ptr()), C.c_void_p(o3.data_ptr()), n, stream) == 0
     assert np.max(np.abs(o4.cpu().numpy() - np.arctan2(vy, vx))) < 2e-15
+
+
+@pytest.mark.parametrize("kernel", ["fast", "generic"])
+def test_null_leaves_free_lattice(kernel, monkeypatch):
+    """edge case of the boundary: nothing constrained, nothing damped, no contact, no drive, no load (NULL damping /
+    contact / drive leaves), all three stiffnesses per bond, non-zero initial state, two output times only --
+    forward and adjoint against the C++ oracle"""
+    from difflexmm_b200.geometry import QuadGeometry, compute_inertia
+    from oracle import Oracle
+    if kernel == "generic":
+        monkeypatch.setenv("DFX_ADJOINT_KERNEL", "generic")
+        monkeypatch.setenv("DFX_FORWARD_KERNEL", "generic")
+    geo = QuadGeometry(4, 3, spacing=15.0, bond_length=2.25)
+    bc, cnvf, bonds, refv = geo.get_parametrization()
+    hs, vs = geo.get_design_from_rotated_square(25 * math.pi / 180)
+    cnv = cnvf(hs, vs)
+    spec = _abi.TopologySpec(geo.n_blocks, 4, bonds())
+    assert spec.n_free == 3 * geo.n_blocks and spec.n_drive_params == 0
+    rng = np.random.default_rng(7)
+    nb = spec.n_bonds
+    leaves = dict(centroid_node_vectors=cnv.numpy(), reference_vector=refv().numpy(),
+                  k_stretch=120.0 * (1 + 0.1 * rng.random(nb)), k_shear=1.19 * (1 + 0.1 * rng.random(nb)),
+                  k_rot=1.5 * (1 + 0.1 * rng.random(nb)), inertia=compute_inertia(cnv, 6.18e-9).reshape(-1).numpy())
+    pb = ("k_stretch", "k_shear", "k_rot")
+    nf = spec.n_free
+    y0 = np.concatenate([0.05 * rng.standard_normal(nf), 20.0 * rng.standard_normal(nf)])
+    ts = np.array([0.0, 0.004])
+    rtol, atol = 1e-8, 1e-6
+    orc = Oracle(spec)
+    ph = orc.params(1, leaves, pb, False)
+    ys_h, st_h = orc.forward(ph, y0, ts, rtol, atol)
+    g = np.cos(ys_h) + 0.2
+    y0b_h, tsb_h, gr_h, sb_h = orc.adjoint(ph, ys_h, ts, g, rtol, atol)
+    lib, topo = _solver(spec)
+    dl = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64, device="cuda").contiguous() for k, v in leaves.items()}
+    ps = _abi.ParamSet(spec, 1, dl, pb, False)
+    ys, st = lib.forward(topo, ps, torch.as_tensor(y0, device="cuda"), torch.as_tensor(ts, device="cuda"), rtol, atol,
+                         _abi.DfxOptions(0, 0, 0))
+    assert st.numpy()["status"][0] == 0 and int(st.numpy()["steps"][0]) == int(st_h["steps"][0])
+    assert rel_l2(ys[0].cpu().numpy(), ys_h[0]) <= TRAJ_TOL
+    y0b, tsb, gr, sb = lib.adjoint(topo, ps, torch.as_tensor(ys_h, device="cuda"), torch.as_tensor(ts, device="cuda"),
+                                   torch.as_tensor(g, device="cuda"), rtol, atol, 0, _abi.DfxOptions(0, 0, 0))
+    assert sb.numpy()["status"][0] == 0
+    assert rel_l2(y0b[0].cpu().numpy(), y0b_h[0]) <= GRAD_TOL and rel_l2(tsb[0].cpu().numpy(), tsb_h[0]) <= GRAD_TOL
+    assert set(gr) == set(gr_h) and "damping" not in gr and "contact" not in gr and "drive" not in gr
+    for k in gr_h:
+        assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= GRAD_TOL, k

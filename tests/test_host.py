@@ -2,6 +2,7 @@
 setup_dynamic_solver's arguments and of ControlParams (no GPU needed)."""
 
 import math
+import os
 
 import numpy as np
 import pytest
@@ -313,3 +314,21 @@ def test_design_vertex_table_of_the_device_geometry():
     assert counts.min() == 1 and counts.max() == 2  # boundary shifts feed one vertex, interior ones two
     with pytest.raises(TypeError):
         design_vertex_table(RotatedSquareGeometry(2, 2))
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU port timed through the bench harness) prints one JSON line with the keys the
+    driver reads; shortened horizon and two designs so that it takes a second"""
+    import json
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1", "--warmup", "0",
+                          "--cpu-designs", "2", "--horizon-scale", "0.05"], capture_output=True, text=True, timeout=300, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    line = json.loads(out.stdout.strip().splitlines()[-1])
+    assert line["impl"] == "reference" and line["unit"] == "designs/s" and line["higher_is_better"] is True
+    assert line["value"] > 0 and line["steps"] == 1 and line["dtype"] == "f64" and line["scaling"] == "weak"
+    assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"] == {"value": line["value"], "unit": "designs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
+    assert "workload" in line["config"]

@@ -529,3 +529,25 @@ def test_fused_objective_on_the_kagome_lattice():
     assert abs(J0 - J1) <= 1e-11 * abs(J0)
     for a, b in zip(g1, g0):
         assert rel_l2(a.numpy(), b.numpy()) <= 1e-8
+
+
+def test_bench_prints_the_contract_line():
+    """bench.py end to end on a tiny ensemble (shortened horizon: not a measurement): every key the driver reads"""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    out = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--designs", "8", "--steps", "2", "--warmup", "1",
+                          "--cpu-designs", "2", "--horizon-scale", "0.05"], capture_output=True, text=True, timeout=600, cwd=root)
+    assert out.returncode == 0, out.stderr[-2000:]
+    d = json.loads(out.stdout.strip().splitlines()[-1])
+    for key in ("metric", "value", "unit", "n_gpus", "steps", "warmup", "ms_per_step", "higher_is_better", "scaling",
+                "vs_baseline", "dtype", "data", "config", "clocks", "e2e", "gpu_launches", "roofline", "cpu_baseline"):
+        assert key in d, key
+    assert d["n_gpus"] == 1 and d["steps"] == 2 and d["gpu_launches"] == 6 and d["failed_designs"] == 0
+    assert d["value"] > 0 and d["e2e"]["value"] > 0 and d["e2e"]["h2d_bytes_per_step"] > 0 and d["e2e"]["d2h_bytes_per_step"] > 0
+    r = d["roofline"]
+    assert r["achieved"] > 0 and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["unit"] == "TFLOP/s"
+    assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
+    assert "PROFILING_ONLY_horizon_scale" in d["config"] and "workload" in d["config"]

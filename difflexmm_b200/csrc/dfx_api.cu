@@ -220,6 +220,7 @@ FastPlan plan_fast_adjoint(const DevTopo& T) {
   if (T.bond_energy == DFX_BOND_SPRING) return f;  // generic kernels only
   int t = T.n_blocks > (T.n_bonds + 1) / 2 ? T.n_blocks : (T.n_bonds + 1) / 2;
   t = t <= 384 ? 384 : 512;  // the CTA size is a compile-time constant of the kernel (addresses become immediates)
+  if (const char* e = getenv("DFX_ADJOINT_THREADS")) { if (atoi(e) == 512) t = 512; }  // experiment: 16 warps at <= 128 registers
   if (T.n_npb > 4 || T.n_blocks > t || T.n_bonds > 2 * t) return f;
   const int nwarp = t / 32, groups = (nwarp + 3) / 4;
   f.cols_per_warp = (512 / groups) & ~1;

@@ -272,8 +272,15 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
   int it = 1;
   while (it < a.n_t) {
     const double target = ts[it];
+    if (!(t < target)) {
+      // output time not after the current time (repeated or decreasing `ts`, which jax's odeint does not allow): its
+      // interpolation is 0/0 at the start -- emit NaN and move on instead of waiting for a step that never comes
+      for (int f = tid; f < 2 * nf; f += nthr) ys[(long long)it * 2 * nf + f] = nan("");
+      ++it;
+      continue;
+    }
     long long istep = 0;
-    bool crossed = !(t < target);
+    bool crossed = false;
     while (!crossed) {
       if (!(dt > 0.0)) { status |= DFX_STATUS_DT_UNDERFLOW; break; }
       if (istep >= a.max_steps) { status |= DFX_STATUS_MAX_STEPS; break; }

@@ -285,3 +285,37 @@ def test_null_leaves_free_lattice(kernel, monkeypatch):
     assert set(gr) == set(gr_h) and "damping" not in gr and "contact" not in gr and "drive" not in gr
     for k in gr_h:
         assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= GRAD_TOL, k
+
+
+@pytest.mark.parametrize("mode", ["fast", "generic", "cluster4"])
+def test_single_output_time(mode, monkeypatch):
+    """ragged end of the time axis: n_t = 1 (odeint returns y0 only; the reference's backward scan is empty, so
+    y0_bar = g[0] and every parameter cotangent is zero) and n_t = 2 with a zero-length interval"""
+    for var in ("DFX_FORWARD_KERNEL", "DFX_ADJOINT_KERNEL"):
+        if mode != "fast":
+            monkeypatch.setenv(var, "generic")
+    monkeypatch.setenv("DFX_CLUSTER", "4" if mode == "cluster4" else "1")
+    c = load_golden("quads_4x3_contact_active")
+    lib, topo = _solver(c.spec)
+    ps = _dev_params(c)
+    nf = c.spec.n_free
+    rng = np.random.default_rng(11)
+    y0 = torch.as_tensor(0.01 * rng.standard_normal(2 * nf), device="cuda")
+    ts = torch.as_tensor(c.ts[:1].copy(), device="cuda")
+    ys, st = lib.forward(topo, ps, y0, ts, c.rtol, c.atol, _abi.DfxOptions(0, 0, 0))
+    assert ys.shape == (1, 1, 2 * nf) and torch.equal(ys[0, 0], y0) and st.numpy()["status"][0] == 0
+    g = torch.as_tensor(rng.standard_normal((1, 1, 2 * nf)), device="cuda")
+    y0b, tsb, gr, sb = lib.adjoint(topo, ps, ys, ts, g, c.rtol, c.atol, c.aug_size, _abi.DfxOptions(0, 0, 0))
+    assert sb.numpy()["status"][0] == 0 and int(sb.numpy()["steps"][0]) == 0
+    assert torch.equal(y0b[0], g[0, 0]) and float(tsb.abs().max()) == 0.0
+    assert all(float(v.abs().max()) == 0.0 for v in gr.values())
+    # a repeated first output time violates odeint's "strictly increasing" precondition: jax's interpolation is 0/0
+    # there; libdfx returns NaN for that output as well (it must not hang) and carries on with the later ones
+    from oracle import Oracle
+    ts3 = np.array([c.ts[0], c.ts[0], c.ts[1]])
+    ys3, st3 = lib.forward(topo, ps, y0, torch.as_tensor(ts3, device="cuda"), c.rtol, c.atol, _abi.DfxOptions(0, 0, 0))
+    orc = Oracle(c.spec)
+    ys_h, st_h = orc.forward(orc.params(1, c.leaves, c.per_bond, c.damping_per_dof), y0.cpu().numpy(), ts3, c.rtol, c.atol)
+    assert st3.numpy()["status"][0] == 0 and torch.equal(ys3[0, 0], y0)
+    assert torch.isnan(ys3[0, 1]).all() and np.isnan(ys_h[0, 1]).all()
+    assert rel_l2(ys3[0, 2].cpu().numpy(), ys_h[0, 2]) <= TRAJ_TOL

@@ -319,3 +319,37 @@ def test_single_output_time(mode, monkeypatch):
     assert st3.numpy()["status"][0] == 0 and torch.equal(ys3[0, 0], y0)
     assert torch.isnan(ys3[0, 1]).all() and np.isnan(ys_h[0, 1]).all()
     assert rel_l2(ys3[0, 2].cpu().numpy(), ys_h[0, 2]) <= TRAJ_TOL
+
+
+@pytest.mark.timeout(120)
+@pytest.mark.parametrize("scenario", ["max_steps", "nan_parameter", "zero_tolerance"])
+@pytest.mark.parametrize("mode", ["fast", "generic", "cluster4", "group40"])
+def test_failing_integrations_stop_with_a_status(mode, scenario, monkeypatch):
+    """integrations that cannot finish (step cap, NaN inertia, zero tolerances) must come back with a status flag and
+    NaN outputs in every kernel mode -- in particular the multi-CTA modes must leave their barriers together"""
+    _kernel_mode(monkeypatch, "DFX_FORWARD_KERNEL", {"fast": "fast_tmem"}.get(mode, mode))
+    _kernel_mode(monkeypatch, "DFX_ADJOINT_KERNEL", {"fast": "fast_tmem"}.get(mode, mode))
+    c = load_golden("quads_4x3_contact_active")
+    lib, topo = _solver(c.spec)
+    leaves = {k: np.array(v, dtype=np.float64, copy=True) for k, v in c.leaves.items()}
+    rtol, atol, opts = c.rtol, c.atol, _abi.DfxOptions(0, 0, 0)
+    if scenario == "max_steps":
+        opts = _abi.DfxOptions(0, 0, 2)
+    elif scenario == "nan_parameter":
+        leaves["inertia"][3] = np.nan
+    else:
+        rtol = atol = 0.0
+    dl = {k: torch.as_tensor(v, dtype=torch.float64, device="cuda").contiguous() for k, v in leaves.items()}
+    ps = _abi.ParamSet(c.spec, 1, dl, c.per_bond, c.damping_per_dof)
+    ys, st = lib.forward(topo, ps, torch.as_tensor(c.y0, device="cuda"), torch.as_tensor(c.ts, device="cuda"), rtol, atol, opts)
+    torch.cuda.synchronize()
+    s = st.numpy()[0]
+    want = {"max_steps": _abi.DFX_STATUS_MAX_STEPS, "nan_parameter": _abi.DFX_STATUS_NONFINITE}.get(scenario)
+    assert s["status"] != 0 and (want is None or s["status"] & want)
+    assert torch.isnan(ys[0, -1]).all()
+    # adjoint on the (valid) golden trajectory with the same failing setting
+    y0b, tsb, gr, sb = lib.adjoint(topo, ps, torch.as_tensor(c.ref["ys"][None], device="cuda"), torch.as_tensor(c.ts, device="cuda"),
+                                   torch.as_tensor(c.g[None], device="cuda"), rtol, atol, c.aug_size, opts)
+    torch.cuda.synchronize()
+    assert sb.numpy()[0]["status"] != 0 and torch.isnan(y0b).all()
+    assert all(torch.isnan(v).all() for v in gr.values())

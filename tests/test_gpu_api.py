@@ -551,3 +551,32 @@ def test_bench_prints_the_contract_line():
     assert r["achieved"] > 0 and r["peak"] > 0 and abs(r["frac"] - r["achieved"] / r["peak"]) < 1e-12 and r["unit"] == "TFLOP/s"
     assert d["cpu_baseline"]["kind"] == "port" and d["cpu_baseline"]["value"] > 0
     assert "PROFILING_ONLY_horizon_scale" in d["config"] and "workload" in d["config"]
+
+
+def test_cfg4_lattice_size_uses_the_512_thread_kernels():
+    """quads 24 x 18 (432 units, 822 bonds: the 512-thread instances of both fast kernels, static ramp + delayed pulse
+    drive with 150 constrained DOFs) against the C++ oracle, short dynamic window"""
+    from difflexmm_b200 import _abi
+    from difflexmm_b200.problems import QuadsStaticTuning
+    from oracle import Oracle
+    P = QuadsStaticTuning(simulation_time_dynamic=0.004, n_timepoints=4, compressive_strain=0.02, compressive_strain_rate=25.0)
+    s = P.setup()
+    assert P.spec.n_blocks == 432 and P.spec.n_bonds == 822
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(P.initial_design(), device="cuda")
+    ps = _abi.ParamSet(P.spec, 1, {k: v.contiguous() for k, v in leaves.items()}, pb, dpd)
+    ys, st = s.lib_forward(ps, y0, ts)
+    assert st.numpy()["status"][0] == 0
+    orc = Oracle(P.spec)
+    ph = orc.params(1, {k: v.cpu().numpy() for k, v in leaves.items()}, pb, dpd)
+    ys_h, st_h = orc.forward(ph, y0.cpu().numpy(), ts.cpu().numpy(), P.rtol, P.atol)
+    assert abs(int(st.numpy()["steps"][0]) - int(st_h["steps"][0])) <= 2
+    assert rel_l2(ys[0].cpu().numpy(), ys_h[0]) <= 1e-6
+    nf = P.spec.n_free
+    g = np.zeros_like(ys_h)
+    g[:, :, nf:] = ys_h[:, :, nf:] * leaves["inertia"].cpu().numpy()
+    y0b_h, tsb_h, gr_h, sb_h = orc.adjoint(ph, ys_h, ts.cpu().numpy(), g, P.rtol, P.atol, aug)
+    y0b, tsb, gr, sb = s.lib_adjoint(ps, torch.as_tensor(ys_h, device="cuda"), ts, torch.as_tensor(g, device="cuda"), aug)
+    assert sb.numpy()["status"][0] == 0
+    for k in gr_h:
+        if np.abs(gr_h[k]).max() > 1e-9:
+            assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= 1e-5, k

@@ -353,3 +353,36 @@ def test_failing_integrations_stop_with_a_status(mode, scenario, monkeypatch):
     torch.cuda.synchronize()
     assert sb.numpy()[0]["status"] != 0 and torch.isnan(y0b).all()
     assert all(torch.isnan(v).all() for v in gr.values())
+
+
+def test_large_batch_reuses_the_sm_indexed_scratch_correctly():
+    """more designs than scratch slots (300 > 256): the fast adjoint indexes its L2 scratch by SM id and re-uses a slot for
+    one design after another; every design must come out exactly as when it is solved in a small batch with its own
+    scratch slice"""
+    c = load_golden("quads_4x3_contact_active")
+    lib, topo = _solver(c.spec)
+    rng = np.random.default_rng(5)
+    B = 300
+    leaves = dict(c.leaves)
+    cnv0 = leaves["centroid_node_vectors"]
+    leaves["centroid_node_vectors"] = np.stack([cnv0 * (1 + 0.02 * rng.standard_normal(cnv0.shape)) for _ in range(B)])
+    dl = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64, device="cuda").contiguous() for k, v in leaves.items()}
+    y0, ts = torch.as_tensor(c.y0, device="cuda"), torch.as_tensor(c.ts, device="cuda")
+    opts = _abi.DfxOptions(0, 0, 0)
+    ps = _abi.ParamSet(c.spec, B, dl, c.per_bond, c.damping_per_dof)
+    ys, st = lib.forward(topo, ps, y0, ts, c.rtol, c.atol, opts)
+    g = torch.cos(ys) + 0.3
+    y0b, tsb, gr, sb = lib.adjoint(topo, ps, ys, ts, g, c.rtol, c.atol, c.aug_size, opts)
+    assert (st.numpy()["status"] == 0).all() and (sb.numpy()["status"] == 0).all()
+    for lo in (0, 147, 296):  # first wave, a later wave, the tail
+        sl = slice(lo, lo + 4)
+        d4 = dict(dl)
+        d4["centroid_node_vectors"] = dl["centroid_node_vectors"][sl].contiguous()
+        p4 = _abi.ParamSet(c.spec, 4, d4, c.per_bond, c.damping_per_dof)
+        ys4, _ = lib.forward(topo, p4, y0, ts, c.rtol, c.atol, opts)
+        assert torch.equal(ys4, ys[sl])
+        y0b4, tsb4, gr4, sb4 = lib.adjoint(topo, p4, ys4, ts, g[sl].contiguous(), c.rtol, c.atol, c.aug_size, opts)
+        assert torch.equal(y0b4, y0b[sl]) and torch.equal(tsb4, tsb[sl])
+        assert (sb4.numpy()["steps"] == sb.numpy()["steps"][sl]).all()
+        for k in gr:
+            assert torch.equal(gr4[k], gr[k][sl]), k

@@ -386,3 +386,28 @@ def test_large_batch_reuses_the_sm_indexed_scratch_correctly():
         assert (sb4.numpy()["steps"] == sb.numpy()["steps"][sl]).all()
         for k in gr:
             assert torch.equal(gr4[k], gr[k][sl]), k
+
+
+def test_concurrent_streams_share_one_topology_handle():
+    """INTEGRATION.md stream contract: calls on different streams with one immutable topology handle run concurrently
+    (each brings its own workspace) and give the results of the sequential calls"""
+    c = load_golden("kagome_3x2_perbond")
+    lib, topo = _solver(c.spec)
+    ps = _dev_params(c)
+    y0, ts = torch.as_tensor(c.y0, device="cuda"), torch.as_tensor(c.ts, device="cuda")
+    g = torch.as_tensor(c.g[None], device="cuda")
+    opts = _abi.DfxOptions(0, 0, 0)
+    ys_ref, _ = lib.forward(topo, ps, y0, ts, c.rtol, c.atol, opts)
+    ref = lib.adjoint(topo, ps, ys_ref, ts, g, c.rtol, c.atol, c.aug_size, opts)
+    torch.cuda.synchronize()
+    streams = [torch.cuda.Stream() for _ in range(3)]
+    outs = []
+    for s in streams:
+        s.wait_stream(torch.cuda.current_stream())
+        with torch.cuda.stream(s):
+            ys, _ = lib.forward(topo, ps, y0, ts, c.rtol, c.atol, opts)
+            outs.append((ys, lib.adjoint(topo, ps, ys, ts, g, c.rtol, c.atol, c.aug_size, opts)))
+    torch.cuda.synchronize()
+    for ys, (y0b, tsb, gr, sb) in outs:
+        assert torch.equal(ys, ys_ref) and torch.equal(y0b, ref[0]) and torch.equal(tsb, ref[1])
+        assert all(torch.equal(gr[k], ref[2][k]) for k in gr)

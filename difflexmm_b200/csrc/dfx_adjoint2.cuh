@@ -581,11 +581,20 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
             Q(QA_ERR, c0 + k) = fma(qc.ce, qv[c0 + k], ac.fe * e_in[k]);
           }
         }
-        if (qc.crossing) {  // midpoint sums: one step in ~25, not prefetched
+        if (qc.crossing) {  // midpoint sums (one step in ~20): loads of a group in flight together, then the stores
 #pragma unroll
-          for (int k = 0; k < E_REF; ++k) Q(ac.a_k7, k) = fma(qc.cm, qv[k], ac.fm * Q(ac.a_m, k));
+          for (int c0 = 0; c0 < E_REF; c0 += 7) {
+            double m_in[7];
 #pragma unroll
-          for (int k = 0; k < NEB; ++k) if (E_REF + k < ne_used) Q(ac.a_k7, E_REF + k) = fma(qc.cm, qb[k], ac.fm * Q(ac.a_m, E_REF + k));
+            for (int k = 0; k < 7; ++k) m_in[k] = Q(ac.a_m, c0 + k);
+#pragma unroll
+            for (int k = 0; k < 7; ++k) Q(ac.a_k7, c0 + k) = fma(qc.cm, qv[c0 + k], ac.fm * m_in[k]);
+          }
+          double mb_in[NEB];
+#pragma unroll
+          for (int k = 0; k < NEB; ++k) mb_in[k] = E_REF + k < ne_used ? Q(ac.a_m, E_REF + k) : 0.0;
+#pragma unroll
+          for (int k = 0; k < NEB; ++k) if (E_REF + k < ne_used) Q(ac.a_k7, E_REF + k) = fma(qc.cm, qb[k], ac.fm * mb_in[k]);
         }
       } else {
 #pragma unroll

@@ -15,6 +15,8 @@ from . import _abi
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libdfx.so")
+if os.environ.get("DFX_LIB"):  # experiments: load another build of the same ABI
+    _SO = os.environ["DFX_LIB"]
 _SRC = os.path.join(_HERE, "csrc")
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
               "-Xcompiler", "-fPIC", "-shared"]

@@ -108,32 +108,40 @@ struct TP {
   __device__ __forceinline__ void fence_st() const { if (NT > 0) tmem_st_wait(); }
 };
 
-// scalar-leaf update kept out of line (not on the critical path): up to three consecutive scalar leaves per call,
-// their warp reductions interleaved
-__device__ __noinline__ void scal_update3_nl(int mode, double cs, double ce, double cm, double cs0, double ce0, double cm0,
-                                             double* wbase, int which, int n, double p0, double p1, double p2) {
+// Scalar-leaf update, kept out of line: the call (register save / restore around it at 168 live registers) costs more
+// than the work, so ONE call handles two groups of up to three consecutive leaves each (nB may be 0); the six warp
+// reductions are interleaved.
+__device__ __noinline__ void scal_update6_nl(int mode, double cs, double ce, double cm, double cs0, double ce0, double cm0,
+                                             double* wbase, int whichA, int nA, double a0, double a1, double a2,
+                                             int whichB, int nB, double b0, double b1, double b2) {
 #pragma unroll
   for (int o = 16; o > 0; o >>= 1) {
-    p0 += __shfl_xor_sync(0xffffffffu, p0, o);
-    p1 += __shfl_xor_sync(0xffffffffu, p1, o);
-    p2 += __shfl_xor_sync(0xffffffffu, p2, o);
+    a0 += __shfl_xor_sync(0xffffffffu, a0, o);
+    a1 += __shfl_xor_sync(0xffffffffu, a1, o);
+    a2 += __shfl_xor_sync(0xffffffffu, a2, o);
+    b0 += __shfl_xor_sync(0xffffffffu, b0, o);
+    b1 += __shfl_xor_sync(0xffffffffu, b1, o);
+    b2 += __shfl_xor_sync(0xffffffffu, b2, o);
   }
-  if ((threadIdx.x & 31) != 0) return;
+  // every lane holds the six totals (butterfly): lane k updates leaf k, so the per-warp partials of the (up to) six
+  // leaves are updated side by side instead of one after the other by lane 0
+  const int k = threadIdx.x & 31;
+  if (k >= nA + nB) return;
   double* wk1 = wbase; double* wk7 = wk1 + NSCAL * SCW; double* wsol = wk7 + NSCAL * SCW;
   double* werr = wsol + NSCAL * SCW; double* wmid = werr + NSCAL * SCW;
-  for (int k = 0; k < n; ++k) {
-    const double v = k == 0 ? p0 : (k == 1 ? p1 : p2);
-    const int idx = (which + k) * SCW + (threadIdx.x >> 5);
-    switch (mode) {
-      case 0: wk1[idx] = v; break;
-      case 7: wk7[idx] = v; break;
-      case 2: {
-        const double k1 = wk1[idx];
-        wsol[idx] = cs0 * k1 + cs * v; werr[idx] = ce0 * k1 + ce * v; wmid[idx] = cm0 * k1 + cm * v;
-      } break;
-      case 6: werr[idx] += ce * v; wmid[idx] += cm * v; wk7[idx] = v; break;
-      default: wsol[idx] += cs * v; werr[idx] += ce * v; wmid[idx] += cm * v; break;
-    }
+  const bool inA = k < nA;
+  const int kk = inA ? k : k - nA;
+  const double v = inA ? (kk == 0 ? a0 : (kk == 1 ? a1 : a2)) : (kk == 0 ? b0 : (kk == 1 ? b1 : b2));
+  const int idx = ((inA ? whichA : whichB) + kk) * SCW + (threadIdx.x >> 5);
+  switch (mode) {
+    case 0: wk1[idx] = v; break;
+    case 7: wk7[idx] = v; break;
+    case 2: {
+      const double k1 = wk1[idx];
+      wsol[idx] = cs0 * k1 + cs * v; werr[idx] = ce0 * k1 + ce * v; wmid[idx] = cm0 * k1 + cm * v;
+    } break;
+    case 6: werr[idx] += ce * v; wmid[idx] += cm * v; wk7[idx] = v; break;
+    default: wsol[idx] += cs * v; werr[idx] += ce * v; wmid[idx] += cm * v; break;
   }
 }
 
@@ -312,7 +320,8 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
   sc.wk1 = SC + 2 * NSCAL; sc.wk7 = sc.wk1 + NSCAL * SCW; sc.wsol = sc.wk7 + NSCAL * SCW;
   sc.werr = sc.wsol + NSCAL * SCW; sc.wmid = sc.werr + NSCAL * SCW;
 
-#define SCAL3(which, n, p0, p1, p2) scal_update3_nl(qc.mode, qc.cs, qc.ce, qc.cm, qc.cs0, qc.ce0, qc.cm0, sc.wk1, which, n, p0, p1, p2)
+#define SCAL6(wA, nA, a0, a1, a2, wB, nB, b0, b1, b2) \
+  scal_update6_nl(qc.mode, qc.cs, qc.ce, qc.cm, qc.cs0, qc.ce0, qc.cm0, sc.wk1, wA, nA, a0, a1, a2, wB, nB, b0, b1, b2)
   QuadCtx qc;  // pointer fields unused here
   qc.atol = atol; qc.rtol = rtol; qc.crossing = false; qc.x = 0; qc.h = 0; qc.mode = 0;
   qc.cs = qc.ce = qc.cm = qc.cs0 = qc.ce0 = qc.cm0 = 0;
@@ -391,13 +400,22 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
   // ---- one augmented RHS evaluation: phases B and C.  The stage v, lambda_u and w of this thread's unit
   // are parked in the thread-private store by publish(); derivative stage `kidx` is written there too.
   // `time_next`: real time of the next evaluation when it is already known (drive channels are prepared for it).
+#ifdef DFX_PHASE_TIMERS
+  // A | wait A->B | B bond math + slots | wait B->C | C rest | step logic | B bond quadrature | B scalars | C gather | C k + store | C unit quadrature
+  long long pt_acc[12] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt_mark = 0;
+#define PT_MARK(k) do { const long long now_ = clock64(); pt_acc[k] += now_ - pt_mark; pt_mark = now_; } while (0)
+#else
+#define PT_MARK(k) do { } while (0)
+#endif
   auto aug_BC = [&](double time, int kidx, double time_next) -> double {
     const bool want_q = qc.mode != 1;
     constexpr int NEB = NE - E_REF;  // bond-owned entries: reference vector (+ per-bond stiffnesses)
     double qb[NEB];                  // integrands of the bond-owned entries (live from phase B to the end of phase C)
 #pragma unroll
     for (int e = 0; e < NEB; ++e) qb[e] = 0.0;
+    PT_MARK(0);
     __syncthreads();
+    PT_MARK(1);
     // ============ phase B: bonds ============
     double p_ks = 0, p_ksh = 0, p_kr = 0, p_c0 = 0, p_c1 = 0, p_c2 = 0;
     const AccCoef ac = acc_coef();
@@ -456,6 +474,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
         if (kr_pb) { if (i == 0) qb[KP + 2] = -o.gkr.d; else qb[KP + 5] = -o.gkr.d; } else p_kr -= o.gkr.d;
       }
     }
+    PT_MARK(2);
     if (ac.on && want_q) {
       // bond-owned entries: all loads first, then the updates
       double bs_in[NEB], be_in[NEB];
@@ -467,15 +486,17 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
         Q(QA_ERR, E_REF + k) = fma(qc.ce, qb[k], ac.fe * be_in[k]);
       }
     }
+    PT_MARK(6);
     if (want_q) {
-      if (!ks_pb || !ksh_pb || !kr_pb) SCAL3(SC_KS, 3, ks_pb ? 0.0 : p_ks, ksh_pb ? 0.0 : p_ksh, kr_pb ? 0.0 : p_kr);
-      if (contact) {
-        // a warp takes part in the contact scalars from the first time one of its bonds touches (sticky)
-        warp_contact = warp_contact || __any_sync(0xffffffffu, p_c0 != 0.0 || p_c1 != 0.0 || p_c2 != 0.0);
-        if (warp_contact) SCAL3(SC_CONTACT, 3, p_c0, p_c1, p_c2);
-      }
+      // a warp takes part in the contact scalars from the first time one of its bonds touches (sticky)
+      if (contact) warp_contact = warp_contact || __any_sync(0xffffffffu, p_c0 != 0.0 || p_c1 != 0.0 || p_c2 != 0.0);
+      const int n_k = (!ks_pb || !ksh_pb || !kr_pb) ? 3 : 0, n_c = (contact && warp_contact) ? 3 : 0;
+      if (n_k + n_c > 0)
+        SCAL6(SC_KS, n_k, ks_pb ? 0.0 : p_ks, ksh_pb ? 0.0 : p_ksh, kr_pb ? 0.0 : p_kr, SC_CONTACT, n_c, p_c0, p_c1, p_c2);
     }
+    PT_MARK(7);
     __syncthreads();
+    PT_MARK(3);
     // ============ phase C: this thread's unit ============
     double qv[NE];  // unit-owned integrands in [0, E_REF); the bond-owned ones are appended only for the rare modes
 #pragma unroll
@@ -501,6 +522,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
         }
       }
     }
+    PT_MARK(8);
     double ls = 0.0, lsd = 0.0;
     if (T.load_kind != DFX_LOAD_NONE) load_eval(T.load_kind, time, T.load_consts, ls, lsd);
     double p_t0 = 0, p_damp = 0, p_dr0 = 0, p_dr1 = 0, p_dr2 = 0, p_dr3 = 0, p_dr4 = 0;
@@ -540,6 +562,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
         }
       }
     }
+    PT_MARK(9);
     double probe = 0.0;
     if (want_q) {
       if (contact) {
@@ -568,6 +591,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
           }
         }
       }
+      PT_MARK(10);
       if (ac.on) {
         // unit-owned entries in two groups: all loads of a group are in flight before the first dependent use
 #pragma unroll
@@ -601,13 +625,13 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
         for (int k = 0; k < NEB; ++k) qv[E_REF + k] = qb[k];
         probe = quad_apply(qv);
       }
+      PT_MARK(11);
       // t0_bar and the drive parameters only receive contributions from constrained or loaded DOFs
       if (warp_t0) {
-        SCAL3(SC_T0, 1, p_t0, 0.0, 0.0);
-        if (ndp > 0) SCAL3(SC_DRIVE, ndp < 3 ? ndp : 3, p_dr0, p_dr1, p_dr2);
-        if (ndp > 3) SCAL3(SC_DRIVE + 3, ndp - 3, p_dr3, p_dr4, 0.0);
+        SCAL6(SC_T0, 1, p_t0, 0.0, 0.0, SC_DRIVE, ndp < 3 ? ndp : 3, p_dr0, p_dr1, p_dr2);
+        if (ndp > 3) SCAL6(SC_DRIVE + 3, ndp - 3, p_dr3, p_dr4, 0.0, SC_DAMP, 0, 0.0, 0.0, 0.0);
       }
-      if (has_damp && !damp_pd) SCAL3(SC_DAMP, 1, p_damp, 0.0, 0.0);
+      if (has_damp && !damp_pd) SCAL6(SC_DAMP, 1, p_damp, 0.0, 0.0, SC_DAMP, 0, 0.0, 0.0, 0.0);
     }
     tp.fence_st();
     return probe;
@@ -705,7 +729,11 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
     return true;
   };
 
+#ifdef DFX_PHASE_TIMERS
+  pt_mark = clock64();
+#endif
   while (running) {
+    PT_MARK(5);
     double us[3], vs[3], lus[3], lvs[3], time;
     int kidx;
     // ---------------- stage state ----------------
@@ -746,6 +774,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
     // real time of the next evaluation when it is already determined (stages 0..4 of a step)
     const double time_next = ev < 5 ? -(s_cur + h * tab.alpha[ev + 1]) : nan("");
     const double probe = aug_BC(time, kidx, time_next);
+    PT_MARK(4);
     n_rhs++;
     // ---------------- what follows the evaluation ----------------
     if (ev == EV_INIT) {
@@ -918,6 +947,12 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
     }
   }
 
+#ifdef DFX_PHASE_TIMERS
+  if (design == 0 && (tid == 0 || tid == 352))
+    printf("phase timers design 0 thread %d [cycles]: A %lld | wait A->B %lld | B bond math+slots %lld | B bond quadrature %lld | B scalars %lld | wait B->C %lld | "
+           "C gather %lld | C k+store %lld | C contact chain %lld | C unit quadrature %lld | C scalars+rest %lld | step logic %lld | evaluations %lld\n",
+           tid, pt_acc[0], pt_acc[1], pt_acc[2], pt_acc[6], pt_acc[7], pt_acc[3], pt_acc[8], pt_acc[9], pt_acc[10], pt_acc[11], pt_acc[4], pt_acc[5], n_rhs);
+#endif
   // ---- outputs ----------------------------------------------------------------------------------------------
   __syncthreads();
   const double nanv = nan("");

@@ -284,15 +284,20 @@ def main():
         for _ in range(max(1, min(args.warmup, 1))):
             e2e_step()
         barrier()
-        t0 = time.perf_counter()
         n_e2e = max(1, min(args.steps, 3))
-        for _ in range(n_e2e):
-            e2e_step()
-        barrier()
-        te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
+        e2e_step_ms = []
+        with ClockSampler(local_rank) as e2e_clocks:
+            t0 = time.perf_counter()
+            for _ in range(n_e2e):
+                t1 = time.perf_counter()
+                e2e_step()
+                e2e_step_ms.append(1e3 * (time.perf_counter() - t1))
+            barrier()
+            te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B / te.item(), "unit": UNIT, "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h}
+        e2e = {"value": world * B / te.item(), "unit": UNIT, "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
+               "step_ms": e2e_step_ms, "clocks": e2e_clocks.summary()}
 
     if rank != 0:
         if world > 1:

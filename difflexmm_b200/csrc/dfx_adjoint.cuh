@@ -163,6 +163,50 @@ __device__ __forceinline__ void scal_update(const QuadCtx& c, const ScalCtx& s, 
   }
 }
 
+// Several scalar leaves at once: the N warp reductions are interleaved and lane k updates the per-warp partial of leaf
+// which[k] (which[k] < 0: skipped), instead of N separate reductions each finished by lane 0.
+template <int N>
+__device__ __forceinline__ void scal_update_many(const QuadCtx& c, const ScalCtx& s, const int (&which)[N], double (&v)[N]) {
+  bool any = false;
+#pragma unroll
+  for (int k = 0; k < N; ++k) any = any || (which[k] >= 0 && v[k] != 0.0);
+  // warps that contribute nothing to these leaves still have to write their (zero) partial in the modes that assign
+  const bool assign = c.mode == 0 || c.mode == 7 || c.mode == 2 || c.mode == 6;
+  if (!__any_sync(0xffffffffu, any) && !assign) return;
+#pragma unroll
+  for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+    for (int k = 0; k < N; ++k) v[k] += __shfl_xor_sync(0xffffffffu, v[k], o);
+  }
+  const int lane = threadIdx.x & 31;
+  double mine = 0.0;
+  int w = -1;
+#pragma unroll
+  for (int k = 0; k < N; ++k) if (lane == k) { mine = v[k]; w = which[k]; }
+  if (w < 0) return;
+  const int idx = w * SCW + (threadIdx.x >> 5);
+  switch (c.mode) {
+    case 0: s.wk1[idx] = mine; break;
+    case 7: s.wk7[idx] = mine; break;
+    case 2: {
+      const double k1 = s.wk1[idx];
+      s.wsol[idx] = c.cs0 * k1 + c.cs * mine;
+      s.werr[idx] = c.ce0 * k1 + c.ce * mine;
+      s.wmid[idx] = c.cm0 * k1 + c.cm * mine;
+    } break;
+    case 6:
+      s.werr[idx] += c.ce * mine;
+      s.wmid[idx] += c.cm * mine;
+      s.wk7[idx] = mine;
+      break;
+    default:
+      s.wsol[idx] += c.cs * mine;
+      s.werr[idx] += c.ce * mine;
+      s.wmid[idx] += c.cm * mine;
+      break;
+  }
+}
+
 // CL = 0: one CTA per design.  CL = 1: one thread-block cluster per design.  CL = 2: a group of co-resident CTAs of a
 // cooperative launch per design (see forward_kernel).
 template <int CL>
@@ -303,10 +347,10 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       }
     }
     if (want_q) {
-      if (!ks_pb) scal_update(qc, sc, SC_KS, p_ks);
-      if (!ksh_pb) scal_update(qc, sc, SC_KSH, p_ksh);
-      if (!kr_pb) scal_update(qc, sc, SC_KR, p_kr);
-      if (T.contact) { scal_update(qc, sc, SC_CONTACT, p_c0); scal_update(qc, sc, SC_CONTACT + 1, p_c1); scal_update(qc, sc, SC_CONTACT + 2, p_c2); }
+      const int wb[6] = {ks_pb ? -1 : SC_KS, ksh_pb ? -1 : SC_KSH, kr_pb ? -1 : SC_KR,
+                         T.contact ? SC_CONTACT : -1, T.contact ? SC_CONTACT + 1 : -1, T.contact ? SC_CONTACT + 2 : -1};
+      double vb[6] = {p_ks, p_ksh, p_kr, p_c0, p_c1, p_c2};
+      scal_update_many<6>(qc, sc, wb, vb);
     }
     SYNC();
     double ls = 0.0, lsd = 0.0;
@@ -383,9 +427,10 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       }
     }
     if (want_q) {
-      scal_update(qc, sc, SC_T0, p_t0);
-      if (has_damp && !damp_pd) scal_update(qc, sc, SC_DAMP, p_damp);
-      for (int q = 0; q < ndp; ++q) scal_update(qc, sc, SC_DRIVE + q, p_dr[q]);
+      const int wc[7] = {SC_T0, (has_damp && !damp_pd) ? SC_DAMP : -1, ndp > 0 ? SC_DRIVE : -1, ndp > 1 ? SC_DRIVE + 1 : -1,
+                         ndp > 2 ? SC_DRIVE + 2 : -1, ndp > 3 ? SC_DRIVE + 3 : -1, ndp > 4 ? SC_DRIVE + 4 : -1};
+      double vc[7] = {p_t0, p_damp, p_dr[0], p_dr[1], p_dr[2], p_dr[3], p_dr[4]};
+      scal_update_many<7>(qc, sc, wc, vc);
     }
     return probe;
   };

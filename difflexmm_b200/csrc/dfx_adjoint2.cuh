@@ -90,6 +90,24 @@ struct TP {
     if (NT > 0 && slot < NT) tmem_st(taddr + 2 * slot, v);
     else stc(slot, v);
   }
+  // slot known to lie in the derivative history [0, 63): with NT >= 63 it is in TMEM whatever its run-time value
+  __device__ __forceinline__ void st_hist(int slot, double v) const {
+    if (NT >= 63) tmem_st(taddr + 2 * slot, v);
+    else st(slot, v);
+  }
+  template <int N>
+  __device__ __forceinline__ void ldn_hist(int slot0, int stride, double (&out)[N]) const {
+    if (NT >= 63) {
+      uint32_t lo[N], hi[N];
+#pragma unroll
+      for (int i = 0; i < N; ++i) tmem_ld_issue(taddr + 2 * (slot0 + i * stride), lo[i], hi[i]);
+      tmem_ld_wait();
+#pragma unroll
+      for (int i = 0; i < N; ++i) { tmem_pin(lo[i], hi[i]); out[i] = __hiloint2double(hi[i], lo[i]); }
+    } else {
+      ldn<N>(slot0, stride, out);
+    }
+  }
   // N strided loads with a single TMEM wait: out[i] = slot0 + i*stride
   template <int N>
   __device__ __forceinline__ void ldn(int slot0, int stride, double (&out)[N]) const {
@@ -544,9 +562,9 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
         if (has_damp && dslot[j] >= 0) { if (damp_pd) qv[E_DAMP + j] = -wst[j] * vst[j]; else p_damp -= wst[j] * vst[j]; }
         p_t0 += wst[j] * lm * lsd;
       }
-      tp.st(S_KV + kidx * 3 + j, kvv);
-      tp.st(S_KLU + kidx * 3 + j, kluv);
-      tp.st(S_KLV + kidx * 3 + j, klvv);
+      tp.st_hist(S_KV + kidx * 3 + j, kvv);
+      tp.st_hist(S_KLU + kidx * 3 + j, kluv);
+      tp.st_hist(S_KLV + kidx * 3 + j, klvv);
     }
     if (has_cons && want_q && T.drive_kind != DFX_DRIVE_ZERO) {
 #pragma unroll
@@ -683,9 +701,9 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
     for (int l = 0; l <= st; ++l) {
       const double b = tab.beta[st][l], b2 = tab.a2[st][l];
       double kv[3], klu[3], klv[3];
-      tp.template ldn<3>(S_KV + 3 * l, 1, kv);
-      tp.template ldn<3>(S_KLU + 3 * l, 1, klu);
-      tp.template ldn<3>(S_KLV + 3 * l, 1, klv);
+      tp.template ldn_hist<3>(S_KV + 3 * l, 1, kv);
+      tp.template ldn_hist<3>(S_KLU + 3 * l, 1, klu);
+      tp.template ldn_hist<3>(S_KLV + 3 * l, 1, klv);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         au[j] = fma(b2, kv[j], au[j]);

@@ -90,14 +90,16 @@ struct TP {
     if (NT > 0 && slot < NT) tmem_st(taddr + 2 * slot, v);
     else stc(slot, v);
   }
-  // slot known to lie in the derivative history [0, 63): with NT >= 63 it is in TMEM whatever its run-time value
-  __device__ __forceinline__ void st_hist(int slot, double v) const {
-    if (NT >= 63) tmem_st(taddr + 2 * slot, v);
+  // slot known to lie in [0, LIM) (the derivative history): with NT >= LIM it is in TMEM whatever its run-time value,
+  // so the tier test and the code of the other tiers disappear
+  template <int LIM>
+  __device__ __forceinline__ void st_below(int slot, double v) const {
+    if (NT >= LIM) tmem_st(taddr + 2 * slot, v);
     else st(slot, v);
   }
-  template <int N>
-  __device__ __forceinline__ void ldn_hist(int slot0, int stride, double (&out)[N]) const {
-    if (NT >= 63) {
+  template <int LIM, int N>
+  __device__ __forceinline__ void ldn_below(int slot0, int stride, double (&out)[N]) const {
+    if (NT >= LIM) {
       uint32_t lo[N], hi[N];
 #pragma unroll
       for (int i = 0; i < N; ++i) tmem_ld_issue(taddr + 2 * (slot0 + i * stride), lo[i], hi[i]);
@@ -562,9 +564,9 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
         if (has_damp && dslot[j] >= 0) { if (damp_pd) qv[E_DAMP + j] = -wst[j] * vst[j]; else p_damp -= wst[j] * vst[j]; }
         p_t0 += wst[j] * lm * lsd;
       }
-      tp.st_hist(S_KV + kidx * 3 + j, kvv);
-      tp.st_hist(S_KLU + kidx * 3 + j, kluv);
-      tp.st_hist(S_KLV + kidx * 3 + j, klvv);
+      tp.template st_below<63>(S_KV + kidx * 3 + j, kvv);
+      tp.template st_below<63>(S_KLU + kidx * 3 + j, kluv);
+      tp.template st_below<63>(S_KLV + kidx * 3 + j, klvv);
     }
     if (has_cons && want_q && T.drive_kind != DFX_DRIVE_ZERO) {
 #pragma unroll
@@ -701,9 +703,9 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
     for (int l = 0; l <= st; ++l) {
       const double b = tab.beta[st][l], b2 = tab.a2[st][l];
       double kv[3], klu[3], klv[3];
-      tp.template ldn_hist<3>(S_KV + 3 * l, 1, kv);
-      tp.template ldn_hist<3>(S_KLU + 3 * l, 1, klu);
-      tp.template ldn_hist<3>(S_KLV + 3 * l, 1, klv);
+      tp.template ldn_below<63, 3>(S_KV + 3 * l, 1, kv);
+      tp.template ldn_below<63, 3>(S_KLU + 3 * l, 1, klu);
+      tp.template ldn_below<63, 3>(S_KLV + 3 * l, 1, klv);
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         au[j] = fma(b2, kv[j], au[j]);

@@ -203,7 +203,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
     for (int j = 0; j < 3; ++j) {
       double Fj = F[j];
       if (T.load_kind != DFX_LOAD_NONE && is_free[j]) Fj += T.load_mul[3 * blk + j] * ls;
-      tp.st(F_KV + kidx * 3 + j, is_free[j] ? (Fj - cdv[j] * vst[j]) * im[j] : 0.0);
+      tp.template st_below<21>(F_KV + kidx * 3 + j, is_free[j] ? (Fj - cdv[j] * vst[j]) * im[j] : 0.0);
     }
     tp.fence_st();
   };
@@ -267,7 +267,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
       for (int l = 0; l <= ev; ++l) {
         const double b = tab.beta[ev][l], b2 = tab.a2[ev][l];
         double kv[3];
-        tp.template ldn<3>(F_KV + 3 * l, 1, kv);
+        tp.template ldn_below<21, 3>(F_KV + 3 * l, 1, kv);
 #pragma unroll
         for (int j = 0; j < 3; ++j) { au[j] = fma(b2, kv[j], au[j]); av[j] = fma(b, kv[j], av[j]); }
       }

@@ -290,6 +290,9 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
 
   // ---- constants into the thread-private store -------------------------------------------------------------
   for (int i = tid; i < NN; i += nthr) nodeb[i] = A.node_bond[i];
+  int nbq[4];  // bond * 2 + side attached to each vertex of this thread's unit (-1: none), kept in registers
+#pragma unroll
+  for (int l = 0; l < 4; ++l) nbq[l] = (has_blk && l < npb) ? A.node_bond[blk * npb + l] : -1;
   for (int i = tid; i < 2 * NSCAL + 5 * NSCAL * SCW; i += nthr) SC[i] = 0.0;
   for (int i = tid; i < 14 * NDS; i += nthr) SL[i] = 0.0;
   for (int i = tid; i < 32; i += nthr) drv[i] = 0.0;
@@ -525,7 +528,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
 #pragma unroll
     for (int l = 0; l < 4; ++l) {
       if (l < npb) {
-        const int nb_ = nodeb[blk * npb + l];
+        const int nb_ = nbq[l];
         if (nb_ >= 0) {
           const int b = nb_ >> 1;
           const bool second = nb_ & 1;

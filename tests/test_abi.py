@@ -54,3 +54,19 @@ def test_topology_create_reports_errors_instead_of_crashing():
     h = C.c_void_p()
     rc = _lib.lib.dfx_topology_create(C.byref(desc), 0, C.byref(h))
     assert rc != 0 and b"more than one bond" in _lib.lib.dfx_last_error()
+
+
+def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
+    """include/dfx.h must compile as C99 (the boundary is a C ABI, no C++ types) and the ctypes mirrors in
+    difflexmm_b200/_abi.py must have the sizes the C compiler gives the structs"""
+    import subprocess
+    from difflexmm_b200 import _abi
+    names = ["DfxTopologyDesc", "DfxLeaf", "DfxParams", "DfxParamGrads", "DfxOptions", "DfxStats", "DfxObjective", "DfxGeometryDesc"]
+    src = tmp_path / "sizes.c"
+    src.write_text('#include <stdio.h>\n#include "dfx.h"\nint main(void) {\n' +
+                   "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")
+    exe = tmp_path / "sizes"
+    subprocess.check_call(["gcc", "-std=c99", "-Wall", "-Werror", "-I", os.path.join(ROOT, "include"), "-o", str(exe), str(src)])
+    sizes = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
+    for n in names:
+        assert int(sizes[n]) == C.sizeof(getattr(_abi, n)), n

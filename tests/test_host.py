@@ -332,3 +332,16 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "designs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]
+
+
+def test_every_python_file_compiles():
+    """bench.py, __graft_entry__.py, tools/ and the package byte-compile (no GPU needed to catch a syntax error)"""
+    import py_compile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    files = [os.path.join(root, f) for f in ("bench.py", "__graft_entry__.py")]
+    for sub in ("tools", "difflexmm_b200", "oracle", "tests"):
+        for dp, _, fs in os.walk(os.path.join(root, sub)):
+            files += [os.path.join(dp, f) for f in fs if f.endswith(".py")]
+    assert len(files) > 20
+    for f in files:
+        py_compile.compile(f, doraise=True)

@@ -345,3 +345,28 @@ def test_every_python_file_compiles():
     assert len(files) > 20
     for f in files:
         py_compile.compile(f, doraise=True)
+
+
+def test_optimization_problem_flatten_unflatten_roundtrip():
+    """design tuple <-> flat vector (the reference uses jax.flatten_util.ravel_pytree, quads_focusing.py:562-563),
+    single designs and batches"""
+    import torch
+    from difflexmm_b200.optimization import OptimizationProblem
+    from difflexmm_b200.problems import KagomeFocusing, QuadsFocusing
+    for P in (QuadsFocusing(n1_blocks=8, n2_blocks=7), KagomeFocusing(n1_cells=8, n2_cells=6)):
+        P.lower()
+        opt = OptimizationProblem(P)
+        rng = np.random.default_rng(0)
+        shapes = [tuple(s) for s in P.geometry.design_shapes]
+        single = [torch.from_numpy(rng.standard_normal(s)) for s in shapes]
+        x = opt.flatten(single)
+        assert x.shape == (1, sum(int(np.prod(s)) for s in shapes))
+        back = opt.unflatten(x)
+        assert all(torch.equal(b[0], a) for a, b in zip(single, back))
+        batch = [torch.from_numpy(rng.standard_normal((3,) + s)) for s in shapes]
+        xb = opt.flatten(batch)
+        assert xb.shape[0] == 3 and all(torch.equal(b, a) for a, b in zip(batch, opt.unflatten(xb)))
+        # ravel order: first design array first, C order (as ravel_pytree)
+        assert torch.equal(xb[1, :int(np.prod(shapes[0]))], batch[0][1].reshape(-1))
+    with pytest.raises(ImportError):
+        OptimizationProblem(P).run_optimization_nlopt(None, 1)

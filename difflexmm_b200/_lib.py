@@ -6,7 +6,6 @@ Device buffers come from torch (allocation, streams); the library itself never s
 
 import ctypes as C
 import os
-import subprocess
 
 import numpy as np
 import torch
@@ -17,21 +16,12 @@ _HERE = os.path.dirname(os.path.abspath(__file__))
 _SO = os.path.join(_HERE, "libdfx.so")
 if os.environ.get("DFX_LIB"):  # experiments: load another build of the same ABI
     _SO = os.environ["DFX_LIB"]
-_SRC = os.path.join(_HERE, "csrc")
-NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-lineinfo", "-O3", "-std=c++17",
-              "-Xcompiler", "-fPIC", "-shared"]
 
 
 def build(force=False, verbose=False):
-    """Compile csrc/dfx_api.cu -> libdfx.so for sm_100a (nvcc cross-compiles without a GPU)."""
-    srcs = [os.path.join(_SRC, f) for f in os.listdir(_SRC)] + [os.path.join(_HERE, "..", "include", "dfx.h")]
-    if not force and os.path.exists(_SO) and os.path.getmtime(_SO) >= max(os.path.getmtime(s) for s in srcs):
-        return _SO
-    cmd = ["nvcc", *NVCC_FLAGS, "-o", _SO, os.path.join(_SRC, "dfx_api.cu")]
-    if verbose:
-        cmd.insert(1, "-Xptxas=-v")
-    subprocess.check_call(cmd)
-    return _SO
+    """Compile csrc/*.cu -> libdfx.so for sm_100a (nvcc cross-compiles without a GPU); see build_native.py."""
+    from . import build_native
+    return build_native.build(force=force, extra_flags=("-Xptxas=-v",) if verbose else ())
 
 
 if not os.path.exists(_SO):

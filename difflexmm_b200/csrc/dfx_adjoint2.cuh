@@ -131,7 +131,7 @@ struct TP {
 // Scalar-leaf update, kept out of line: the call (register save / restore around it at 168 live registers) costs more
 // than the work, so ONE call handles two groups of up to three consecutive leaves each (nB may be 0); the six warp
 // reductions are interleaved.
-__device__ __noinline__ void scal_update6_nl(int mode, double cs, double ce, double cm, double cs0, double ce0, double cm0,
+static __device__ __noinline__ void scal_update6_nl(int mode, double cs, double ce, double cm, double cs0, double ce0, double cm0,
                                              double* wbase, int whichA, int nA, double a0, double a1, double a2,
                                              int whichB, int nB, double b0, double b1, double b2) {
 #pragma unroll
@@ -177,7 +177,7 @@ struct Adj2Args {
 // Cotangent of ys[design][i][(is_v ? n_free : 0) + f]: read from the caller's tensor `g`, or (g == NULL) formed here
 // for the device objective.  Called once per output time and DOF (cold); kept out of line so that it costs the
 // integration loop no registers.
-__device__ __noinline__ double cotangent_nl(const AdjArgs& a, int design, int i, int f, bool is_v) {
+static __device__ __noinline__ double cotangent_nl(const AdjArgs& a, int design, int i, int f, bool is_v) {
   if (a.g) return __ldcs(&a.g[((long long)design * a.n_t + i) * 2 * a.topo.n_free + (is_v ? a.topo.n_free : 0) + f]);
   return objective_cotangent(a, design, i, f, is_v);
 }

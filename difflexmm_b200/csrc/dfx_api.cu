@@ -11,6 +11,14 @@
 
 #include "dfx_forward2.cuh"
 #include "dfx_geometry.cuh"
+#include "dfx_adjoint3.cuh"
+
+namespace dfx {  // dfx_adjoint3.cu
+size_t adjoint3_smem_bytes(bool contact);
+long long adjoint3_scratch_doubles();
+bool adjoint3_supported(int npb, bool contact, int damp);
+cudaError_t launch_adjoint3(const Adj3Args& A, int npb, bool contact, int damp, int batch, cudaStream_t stream);
+}
 
 using namespace dfx;
 
@@ -249,6 +257,24 @@ FastPlan plan_fast_adjoint(const DevTopo& T) {
   return f;
 }
 
+// The 24-warp adjoint kernel (dfx_adjoint3.cuh) serves lattices of the cfg1 / cfg3 size with the common vocabulary;
+// DFX_ADJOINT_KERNEL=v2 keeps them on dfx_adjoint2.cuh (A/B comparisons).
+struct Fast3Plan { bool ok; int npb, damp; bool contact; };
+
+Fast3Plan plan_adjoint3(const DevTopo& T, const DfxParams& p) {
+  Fast3Plan f = {};
+  const char* mode = getenv("DFX_ADJOINT_KERNEL");
+  if (mode && (!strcmp(mode, "generic") || !strcmp(mode, "notmem") || !strcmp(mode, "v2"))) return f;
+  if (getenv("DFX_ADJOINT_THREADS")) return f;
+  if (T.bond_energy != DFX_BOND_LIGAMENT || T.load_kind != DFX_LOAD_NONE) return f;
+  if (p.k_per_bond[0] || p.k_per_bond[1] || p.k_per_bond[2]) return f;
+  if (T.n_blocks > k3::TU || T.n_bonds > k3::TT || T.n_blocks < 1 || T.n_bonds < 1) return f;
+  const bool has_damp = T.n_damped > 0 && p.damping.ptr != nullptr;
+  f.npb = T.n_npb; f.contact = T.contact != 0; f.damp = !has_damp ? 0 : (p.damping_per_dof ? 2 : 1);
+  f.ok = adjoint3_supported(f.npb, f.contact, f.damp);
+  return f;
+}
+
 // launch plan of the fast forward kernel (dfx_forward2.cuh)
 struct FastFwdPlan { bool ok; int threads, nt, ns, cols_per_warp, cols_alloc, ctas; size_t smem; long long scratch; };
 
@@ -442,6 +468,7 @@ size_t dfx_adjoint_workspace_bytes(const DfxTopology* t, int batch) {
   // worst case of the two kernels (the fast one assumes S_TOTAL slots with no TMEM)
   long long fast = f.ok ? (long long)(S_NCONST - f.ns + (NQA + 1) * NE) * f.threads + 32 : 0;
   if (fast > g) g = fast;
+  if (f.ok && adjoint3_scratch_doubles() > g) g = adjoint3_scratch_doubles();
   const int units = f.ok && batch < kScratchSlots ? kScratchSlots : batch;  // the fast kernel indexes scratch by SM id
   return (size_t)g * sizeof(double) * (size_t)units;
 }
@@ -597,6 +624,7 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   long long sz[AA_COUNT], g;
   size_t smem;
   const FastPlan fp = plan_fast_adjoint(T);
+  const Fast3Plan f3 = fp.ok ? plan_adjoint3(T, *params) : Fast3Plan{};
   const MultiCta mc = fp.ok ? MultiCta{0, 1} : pick_multi_cta(T, batch, t->sm_count);
   const int cluster = mc.ncta;
   adjoint_sizes(T, q, sz, cluster);
@@ -624,10 +652,11 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   if (grads) a.grads = *grads;
   a.stats = stats;
   if (fp.ok) g = fp.scratch;
+  if (f3.ok) g = adjoint3_scratch_doubles();
   a.scratch_per_design = g;
   bool own_ws = false;
-  // fast kernel: scratch indexed by SM id when that is smaller than one slice per design
-  const int scratch_slots = (fp.ok && batch > kScratchSlots) ? kScratchSlots : 0;
+  // fast kernels: scratch indexed by SM id when that is smaller than one slice per design (always for the 24-warp kernel)
+  const int scratch_slots = f3.ok ? kScratchSlots : ((fp.ok && batch > kScratchSlots) ? kScratchSlots : 0);
   if (g > 0) {
     const size_t need = (size_t)g * sizeof(double) * (size_t)(scratch_slots ? scratch_slots : batch);
     if (workspace) {
@@ -638,7 +667,15 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
       own_ws = true;
     }
   }
-  if (fp.ok) {
+  if (f3.ok) {
+    Adj3Args A3;
+    A3.a = a;
+    A3.node_bond = t->node_bond;
+    A3.scratch_per_slot = g;
+    A3.scratch_slots = scratch_slots;
+    cudaError_t le = launch_adjoint3(A3, f3.npb, f3.contact, f3.damp, batch, stream);
+    if (le != cudaSuccess) { if (own_ws) cudaFreeAsync(a.scratch, stream); return fail(DFX_ERR_CUDA, "adjoint3_kernel launch failed: %s", cudaGetErrorString(le)); }
+  } else if (fp.ok) {
     Adj2Args A2;
     A2.a = a;
     A2.node_bond = t->node_bond;

@@ -69,9 +69,14 @@ struct AdjArgs {
 //   kinetic:  dJ/dv_f = w m_f v_f on the target DOFs
 //   angular:  J = sum (arm + u) x (m v) + I omega  ->  dJ/du_x = w m_y v_y, dJ/du_y = -w m_x v_x,
 //             dJ/dv_x = -w (arm_y + u_y) m_x, dJ/dv_y = w (arm_x + u_x) m_y, dJ/domega = w I
-__device__ inline double objective_cotangent(const AdjArgs& a, int design, int i, int f, bool is_v) {
+// position of free DOF f in the objective's target list, or -1
+__device__ inline int objective_target_index(const AdjArgs& a, int f) {
   int k = -1;
   for (int q = 0; q < a.obj_n; ++q) if (a.obj_ids[q] == f) k = q;
+  return k;
+}
+// k = objective_target_index(a, f), looked up once per thread by the fast kernels
+__device__ inline double objective_cotangent_k(const AdjArgs& a, int design, int i, int f, bool is_v, int k) {
   if (k < 0) return 0.0;
   const int nf = a.topo.n_free;
   const double w = a.obj_w ? a.obj_w[design] : 1.0;
@@ -85,6 +90,9 @@ __device__ inline double objective_cotangent(const AdjArgs& a, int design, int i
   if (c == 0) return -w * (arm[1] + y[fy]) * m[fx];
   if (c == 1) return w * (arm[0] + y[fx]) * m[fy];
   return w * m[f];
+}
+__device__ inline double objective_cotangent(const AdjArgs& a, int design, int i, int f, bool is_v) {
+  return objective_cotangent_k(a, design, i, f, is_v, objective_target_index(a, f));
 }
 
 struct QuadCtx {

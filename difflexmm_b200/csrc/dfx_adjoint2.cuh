@@ -15,6 +15,7 @@
 //   n_blocks <= T <= 512, n_bonds <= 2 T, n_npb <= 4.
 #pragma once
 
+#include <cstdio>
 #include <type_traits>
 
 #include "dfx_adjoint.cuh"

@@ -31,36 +31,43 @@ namespace k3 {
 
 constexpr int TT = 768, TU = 384, NW = TT / 32, NDW = TU / 32;
 // tensor-memory slots (doubles) of the two unit roles
-constexpr int P_KV = 0, P_U0 = 21, P_V0 = 24, P_TV = 27, P_N = 30;
-constexpr int D_KLU = 0, D_KLV = 21, D_LU0 = 42, D_LV0 = 45, D_TLU = 48, D_N = 51;
-constexpr int P_COLS = 2 * P_N, D_COLS = 2 * D_N;  // 60 + 102 columns per (P, D) warp pair, three pairs per lane quarter
+// (the last slot of each role holds per-thread topology words that would otherwise occupy registers in the bond phase)
+constexpr int P_KV = 0, P_U0 = 21, P_V0 = 24, P_TV = 27, P_TOPO = 30, P_N = 32;
+constexpr int D_KLU = 0, D_KLV = 21, D_LU0 = 42, D_LV0 = 45, D_TLU = 48, D_TOPO = 51, D_N = 53;
+constexpr int P_COLS = 2 * P_N, D_COLS = 2 * D_N;  // 64 + 106 columns per (P, D) warp pair, three pairs per lane quarter
 static_assert(3 * (P_COLS + D_COLS) <= 512, "tensor memory columns");
+constexpr int NCU = 40;   // constrained units whose drive vectors are cached in shared memory
+constexpr int NDRV = 14;  // one row of the drive table: s[2], ds/dt[2], ds/dparam[2][5]
 constexpr int NBC = 10;  // bond constants: r0x r0y L0 1/L0 r1x r1y r2x r2y da1 da2
-constexpr int NE3 = 10;  // quadrature entries per thread: 0..7 unit role (P: inertia[3] damping[3]; D: cnv x[4] y[4]), 8..9 bond role
+constexpr int NE3 = 12;  // quadrature entries per thread: 0..9 unit role (P: inertia[3] damping[3] cnv x[4]; D: cnv y[4]), 10..11 bond role
 // L2 scratch of one SM (doubles); every array is [..][TT], a thread touches its own column only
 constexpr long long G_BC = 0;
-constexpr long long G_SPART = G_BC + (long long)NBC * TT;   // [6][TT] partials of k_stretch k_shear k_rot c_min c_cut k_c
+constexpr long long G_SPART = G_BC + (long long)NBC * TT;   // [6][TT] per-bond partials of k_stretch k_shear k_rot c_min c_cut k_c
 constexpr long long G_BQ = G_SPART + 6LL * TT;              // [sol, err][2][TT] running sums of the reference-vector quadratures
 constexpr long long G_Q = G_BQ + 4LL * TT;                  // [q0 a, q0 b, k1 a, k1 b][NE3][TT]
 constexpr long long G_TOTAL = G_Q + 4LL * NE3 * TT;
 // scalar leaves: running sums [k1, k7, sol, err, mid][NSLOT]
-constexpr int NS_DENSE = 6;                                  // k_stretch k_shear k_rot c_min c_cut k_c: one total each
-constexpr int SLOT_T = NS_DENSE;                             // t0_bar, drive[5]: one partial per D warp
+constexpr int SLOT_K = 0;                                    // k_stretch k_shear k_rot c_min c_cut k_c: four partials each (see phase C)
+constexpr int SLOT_T = SLOT_K + 6 * 4;                       // t0_bar, drive[5]: one partial per D warp
 constexpr int SLOT_DAMP = SLOT_T + 6 * NDW;                  // scalar damping leaf: one partial per P warp
 constexpr int NSLOT = SLOT_DAMP + NDW;
 
 struct Ctrl {
   double h, h0, d1, s0, s_target, s_cur, x;
+  double hst;  // step size of the evaluation in progress (h0 for the probe)
   long long n_steps, n_acc, n_rhs, istep;
   int status, crossing, contact_seen;
+  int i, par;  // output interval in progress; which copy of q0 / k1 is current
   uint32_t tmem_base;
 };
 
 template <int NSL>
 struct Lay {  // shared-memory layout (doubles)
   static constexpr int RED = 0, US = 40, WS = US + 5 * TU, SL = WS + 6 * TU, INVM = SL + NSL * TT, CD = INVM + 3 * TU,
-                       QSP = CD + 3 * TU, QSD = QSP + 12 * TU, SQ = QSD + 16 * TU, ACC = SQ + 2 * NSCAL, DRV = ACC + 5 * NSLOT,
-                       CTRL = DRV + 32, END = CTRL + (int)((sizeof(Ctrl) + 7) / 8);
+                       QSP = CD + 3 * TU, QSD = QSP + 20 * TU, SQ = QSD + 8 * TU, ACC = SQ + 2 * NSCAL, DRV = ACC + 5 * NSLOT,
+                       PC = DRV + 8 * NDRV /* k_stretch k_shear k_rot c_min c_cut k_c */, CV = PC + 6 /* [NCU][6] drive vectors */,
+                       CTRL = CV + 6 * NCU,
+                       END = CTRL + (int)((sizeof(Ctrl) + 7) / 8);
 };
 
 template <int N>
@@ -142,77 +149,82 @@ __device__ __forceinline__ void stage_D(uint32_t ta, const Tableau& tab, double 
   for (int j = 0; j < 3; ++j) { lus[j] = y0[j] + h * alu[j]; lvs[j] = y0[3 + j] + h * alv[j]; }
 }
 
-// What one quadrature entry needs from the step controller
+// Kind of an augmented-RHS evaluation, a compile-time tag of the phase code: 0..5 = Runge-Kutta stage ev of a step
+// (the derivative lands in history slot ev + 1), 6 = f0 at the start of an output interval (slot 0), 7 = the second
+// evaluation of initial_step_size (slot 1).  Quadrature "mode" of the evaluation (as in dfx_adjoint2.cuh):
+// 0: k1 at interval start | 1: nothing (zero weights) | 2: first accumulating stage | 3..5: accumulating | 6: last stage |
+// 7: probe.
+constexpr int EV_INIT = 6, EV_PROBE = 7;
+template <int V> using IC = std::integral_constant<int, V>;
+template <int EV> struct Ev {
+  static constexpr int kidx = EV < 6 ? EV + 1 : (EV == EV_INIT ? 0 : 1);
+  static constexpr int mode = EV < 6 ? EV + 1 : (EV == EV_INIT ? 0 : 7);
+};
+// what the quadratures need from the step controller besides the tableau
 struct QC {
-  int mode;  // 0: k1 at interval start | 1: nothing | 2..5: accumulating stage | 6: last stage | 7: initial-step probe
-  int par;   // which copy of q0 / k1 is current
-  bool crossing;
+  int par;        // which copy of q0 / k1 is current
+  bool crossing;  // the step reaches the output time: also integrate the midpoint sum, interpolate at the end
   double h, x, atol, rtol;
-  double cs, ce, cm, cs0, ce0, cm0;
 };
 
 // N quadrature entries of one thread receive their integrand values.  `qg` = the thread's column of G_Q, entry e0 + k;
 // running solution / error sums at sol[k * sstride], err[k * sstride] (shared memory for the unit role, scratch for the
 // bond role).  Returns the thread's contribution to the error norm (mode 6) or to d2 of initial_step_size (mode 7).
-template <int N>
-__device__ __forceinline__ double quad_entries(const QC& c, double* qg, int e0, double* sol, double* err, int sstride,
-                                               const double (&val)[N]) {
+template <int MODE, int N>
+__device__ __forceinline__ double quad_entries(const QC& c, const Tableau& tab, double* qg, int e0, double* sol, double* err,
+                                               int sstride, const double (&val)[N]) {
   double acc = 0.0;
+  constexpr int K = MODE >= 1 && MODE <= 6 ? MODE : 0;
+  const double cs = tab.c_sol[K], ce = tab.c_err[K], cm = tab.c_mid[K];
   double* q0p = qg + (long long)(c.par * NE3 + e0) * TT;
   double* qnp = qg + (long long)((1 - c.par) * NE3 + e0) * TT;
   double* k1p = qg + (long long)((2 + c.par) * NE3 + e0) * TT;
   double* k7p = qg + (long long)((3 - c.par) * NE3 + e0) * TT;  // spare copy: k7, or the midpoint sum on a crossing step
-  const int mode = c.mode;
-  if (mode >= 3 && mode <= 5) {
-    double s_in[N], e_in[N];
+  if constexpr (MODE >= 3 && MODE <= 5) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) { s_in[k] = sol[k * sstride]; e_in[k] = err[k * sstride]; }
+    for (int k0 = 0; k0 < N; k0 += 4) {  // groups of four: loads in flight together, few live registers
+      double s_in[4], e_in[4];
 #pragma unroll
-    for (int k = 0; k < N; ++k) { sol[k * sstride] = fma(c.cs, val[k], s_in[k]); err[k * sstride] = fma(c.ce, val[k], e_in[k]); }
-    if (c.crossing) {
-      double m_in[N];
+      for (int k = k0; k < k0 + 4 && k < N; ++k) { s_in[k - k0] = sol[k * sstride]; e_in[k - k0] = err[k * sstride]; }
 #pragma unroll
-      for (int k = 0; k < N; ++k) m_in[k] = k7p[k * TT];
-#pragma unroll
-      for (int k = 0; k < N; ++k) k7p[k * TT] = fma(c.cm, val[k], m_in[k]);
+      for (int k = k0; k < k0 + 4 && k < N; ++k) {
+        sol[k * sstride] = fma(cs, val[k], s_in[k - k0]);
+        err[k * sstride] = fma(ce, val[k], e_in[k - k0]);
+      }
     }
-  } else if (mode == 2) {
+    if (c.crossing) {
+#pragma unroll
+      for (int k = 0; k < N; ++k) k7p[k * TT] = fma(cm, val[k], k7p[k * TT]);
+    }
+  } else if constexpr (MODE == 2) {
     double k1[N];
 #pragma unroll
     for (int k = 0; k < N; ++k) k1[k] = k1p[k * TT];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      sol[k * sstride] = fma(c.cs, val[k], c.cs0 * k1[k]);
-      err[k * sstride] = fma(c.ce, val[k], c.ce0 * k1[k]);
-      if (c.crossing) k7p[k * TT] = fma(c.cm, val[k], c.cm0 * k1[k]);
+      sol[k * sstride] = fma(cs, val[k], tab.c_sol[0] * k1[k]);
+      err[k * sstride] = fma(ce, val[k], tab.c_err[0] * k1[k]);
+      if (c.crossing) k7p[k * TT] = fma(cm, val[k], tab.c_mid[0] * k1[k]);
     }
-  } else if (mode == 6) {
-    double q_in[N], s_in[N], e_in[N];
+  } else if constexpr (MODE == 6) {
+    double q_in[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) { q_in[k] = q0p[k * TT]; s_in[k] = sol[k * sstride]; e_in[k] = err[k * sstride]; }
-    if (!c.crossing) {
+    for (int k = 0; k < N; ++k) q_in[k] = q0p[k * TT];
 #pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const double q1 = fma(c.h, s_in[k], q_in[k]);
-        const double r = c.h * fma(c.ce, val[k], e_in[k]) * rcp_pos(c.atol + c.rtol * fmax(fabs(q_in[k]), fabs(q1)));
-        acc = fma(r, r, acc);
-        qnp[k * TT] = q1;
-        k7p[k * TT] = val[k];
-      }
-    } else {
-#pragma unroll
-      for (int k = 0; k < N; ++k) {
-        const double q1 = fma(c.h, s_in[k], q_in[k]);
-        const double r = c.h * fma(c.ce, val[k], e_in[k]) * rcp_pos(c.atol + c.rtol * fmax(fabs(q_in[k]), fabs(q1)));
-        acc = fma(r, r, acc);
-        const double amid = fma(c.cm, val[k], k7p[k * TT]);
+    for (int k = 0; k < N; ++k) {
+      const double q1 = fma(c.h, sol[k * sstride], q_in[k]);
+      const double r = c.h * fma(ce, val[k], err[k * sstride]) * rcp_pos(c.atol + c.rtol * fmax(fabs(q_in[k]), fabs(q1)));
+      acc = fma(r, r, acc);
+      if (!c.crossing) { qnp[k * TT] = q1; k7p[k * TT] = val[k]; }
+      else {
+        const double amid = fma(cm, val[k], k7p[k * TT]);
         qnp[k * TT] = interp_eval(q_in[k], q1, q_in[k] + c.h * amid, c.h * k1p[k * TT], c.h * val[k], c.x);
       }
     }
-  } else if (mode == 0) {
+  } else if constexpr (MODE == 0) {
 #pragma unroll
     for (int k = 0; k < N; ++k) k1p[k * TT] = val[k];
-  } else if (mode == 7) {
+  } else if constexpr (MODE == 7) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
       const double d = (val[k] - k1p[k * TT]) * rcp_pos(c.atol + fabs(q0p[k * TT]) * c.rtol);
@@ -223,28 +235,57 @@ __device__ __forceinline__ double quad_entries(const QC& c, double* qg, int e0, 
 }
 
 // one running-sum slot of a scalar leaf receives the total (or a warp's partial) of this evaluation
-__device__ __forceinline__ void scal_slot(const QC& c, double* accb, int slot, double v) {
+template <int MODE>
+__device__ __forceinline__ void scal_slot(const Tableau& tab, double* accb, int slot, double v) {
+  constexpr int K = MODE >= 1 && MODE <= 6 ? MODE : 0;
   double* k1 = accb + slot; double* k7 = k1 + NSLOT; double* sol = k7 + NSLOT; double* err = sol + NSLOT; double* mid = err + NSLOT;
-  switch (c.mode) {
-    case 0: *k1 = v; break;
-    case 7: *k7 = v; break;
-    case 2: { const double a = *k1; *sol = c.cs0 * a + c.cs * v; *err = c.ce0 * a + c.ce * v; *mid = c.cm0 * a + c.cm * v; } break;
-    case 6: *err += c.ce * v; *mid += c.cm * v; *k7 = v; break;
-    default: *sol += c.cs * v; *err += c.ce * v; *mid += c.cm * v; break;
-  }
+  if constexpr (MODE == 0) *k1 = v;
+  else if constexpr (MODE == 7) *k7 = v;
+  else if constexpr (MODE == 2) {
+    const double a = *k1;
+    *sol = tab.c_sol[0] * a + tab.c_sol[K] * v; *err = tab.c_err[0] * a + tab.c_err[K] * v; *mid = tab.c_mid[0] * a + tab.c_mid[K] * v;
+  } else if constexpr (MODE == 6) { *err += tab.c_err[K] * v; *mid += tab.c_mid[K] * v; *k7 = v; }
+  else if constexpr (MODE >= 3 && MODE <= 5) { *sol += tab.c_sol[K] * v; *err += tab.c_err[K] * v; *mid += tab.c_mid[K] * v; }
+}
+// a further contribution of the same evaluation to a slot that scal_slot has already been applied to
+template <int MODE>
+__device__ __forceinline__ void scal_slot_more(const Tableau& tab, double* k1, double v) {
+  constexpr int K = MODE >= 1 && MODE <= 6 ? MODE : 0;
+  double* k7 = k1 + NSLOT; double* sol = k7 + NSLOT; double* err = sol + NSLOT; double* mid = err + NSLOT;
+  if constexpr (MODE == 0) *k1 += v;
+  else if constexpr (MODE == 7) *k7 += v;
+  else if constexpr (MODE == 6) { *err += tab.c_err[K] * v; *mid += tab.c_mid[K] * v; *k7 += v; }
+  else if constexpr (MODE >= 2 && MODE <= 5) { *sol += tab.c_sol[K] * v; *err += tab.c_err[K] * v; *mid += tab.c_mid[K] * v; }
 }
 // total of scalar leaf `which` (NSCAL numbering of dfx_adjoint.cuh) in running-sum array m (0 k1, 1 k7, 2 sol, 3 err, 4 mid)
 __device__ __forceinline__ double scal_total(const double* accb, int m, int which) {
   const double* p = accb + m * NSLOT;
-  if (which >= SC_KS && which <= SC_KR) return p[which - SC_KS];
-  if (which >= SC_CONTACT && which < SC_CONTACT + 3) return p[3 + which - SC_CONTACT];
-  int s0 = SLOT_DAMP;
-  if (which == SC_T0) s0 = SLOT_T;
+  int s0 = SLOT_DAMP, n = NDW;
+  if (which >= SC_KS && which <= SC_KR) { s0 = SLOT_K + (which - SC_KS) * 4; n = 4; }
+  else if (which >= SC_CONTACT && which < SC_CONTACT + 3) { s0 = SLOT_K + (3 + which - SC_CONTACT) * 4; n = 4; }
+  else if (which == SC_T0) s0 = SLOT_T;
   else if (which >= SC_DRIVE) s0 = SLOT_T + (1 + which - SC_DRIVE) * NDW;
   double s = 0.0;
 #pragma unroll 1
-  for (int w = 0; w < NDW; ++w) s += p[s0 + w];
+  for (int w = 0; w < n; ++w) s += p[s0 + w];
   return s;
+}
+
+// cotangent of ys[design][i][(is_v ? n_free : 0) + f] (see cotangent_nl) with the objective's target index of f known
+// (kf = index + 1, 0 = not a target, 1023 = not cached: look it up)
+static __device__ __noinline__ double cotangent_k_nl(const AdjArgs& a, int design, int i, int f, bool is_v, int kf) {
+  if (a.g) return __ldcs(&a.g[((long long)design * a.n_t + i) * 2 * a.topo.n_free + (is_v ? a.topo.n_free : 0) + f]);
+  return objective_cotangent_k(a, design, i, f, is_v, kf == 1023 ? objective_target_index(a, f) : kf - 1);
+}
+static __device__ __noinline__ int target_index_nl(const AdjArgs& a, int f) { return objective_target_index(a, f); }
+
+// one row of the drive table (out of line: several call sites, none of them inside the RHS phases)
+static __device__ __noinline__ void drive_row_nl(int kind, double t, const double* g_drive, DriveTable table, double* r) {
+  DriveEval de;
+  drive_eval(kind, t, g_drive, true, de, table);
+  r[0] = de.s[0]; r[1] = de.s[1]; r[2] = de.sdot[0]; r[3] = de.sdot[1];
+#pragma unroll
+  for (int q = 0; q < DFX_MAX_DRIVE_PARAMS; ++q) { r[4 + q] = de.dsdp[0][q]; r[9 + q] = de.dsdp[1][q]; }
 }
 
 }  // namespace k3
@@ -281,6 +322,8 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
   double* Sqnew = Sq0 + NSCAL;
   double* accb = smem + L::ACC;   // [5][NSLOT]
   double* drv = smem + L::DRV;
+  double* PC = smem + L::PC;      // k_stretch k_shear k_rot c_min c_cut k_c
+  double* CV = smem + L::CV;      // [NCU][6] drive vectors (vec0[3], vec1[3]) of the constrained units
   Ctrl* C = (Ctrl*)(smem + L::CTRL);
 
   unsigned smid;
@@ -323,7 +366,6 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
   const double* ts = a.ts + (long long)design * a.ts_bstride;
   const double* ys = a.ys + (long long)design * a.n_t * 2 * nf;
   const double rtol = a.rtol, atol = a.atol;
-  const int ndp = T.n_drive_params;
 
   // per-thread topology packed in one register: bit j free, bit 3+j constrained, bit 6+j damped, bit 9 contact seen by this bond
   unsigned flags = 0;
@@ -339,18 +381,68 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
   const bool has_cons = (flags & 56u) != 0;
   const bool warp_t0 = __any_sync(0xffffffffu, has_cons);
   auto fidx = [&](int j) { return T.free_of_dof[3 * blk + j]; };  // cold paths only
-  int nbq[NPB];  // bond * 2 + side attached to each vertex of this thread's unit (-1: none)
+  // target index (+1) of each DOF in the device objective, 10 bits each; 0 = not a target, 1023 = look it up.  Kept in
+  // tensor memory (cold)
+  unsigned tgt = 0;
+  if (!a.g) {
 #pragma unroll
-  for (int l = 0; l < NPB; ++l) nbq[l] = has_unit ? A.node_bond[blk * NPB + l] : -1;
+    for (int j = 0; j < 3; ++j) {
+      if (is_free(j)) {
+        const int k = target_index_nl(a, fidx(j));
+        tgt |= (unsigned)(k < 0 ? 0 : (k + 1 < 1023 ? k + 1 : 1023)) << (10 * j);
+      }
+    }
+  }
+  const uint32_t ta_topo = ta + 2 * (isD ? D_TOPO : P_TOPO);
+  auto cot3 = [&](int it, bool is_v, double (&out)[3]) {  // cotangents of the three DOFs of this thread's unit (cold)
+    double tw[1];
+    tm_ld<1>(ta_topo, tw);
+    const unsigned tg = (unsigned)__double2loint(tw[0]);
+#pragma unroll
+    for (int j = 0; j < 3; ++j)
+      out[j] = is_free(j) ? cotangent_k_nl(a, design, it, fidx(j), is_v, (int)((tg >> (10 * j)) & 1023u)) : 0.0;
+  };
+  // bond * 2 + side attached to each vertex of this thread's unit (0xffff: none), two vertices per register
+  unsigned nbp[2] = {0xffffffffu, 0xffffffffu};
+#pragma unroll
+  for (int l = 0; l < NPB; ++l) {
+    const int nb_ = has_unit ? A.node_bond[blk * NPB + l] : -1;
+    const unsigned f = nb_ < 0 ? 0xffffu : (unsigned)nb_;
+    nbp[l >> 1] = (l & 1) ? ((nbp[l >> 1] & 0x0000ffffu) | (f << 16)) : ((nbp[l >> 1] & 0xffff0000u) | f);
+  }
+  tmem_st(ta_topo, __hiloint2double(0, (int)tgt));
+  tmem_st(ta_topo + 2, __hiloint2double((int)nbp[1], (int)nbp[0]));
+  // slot of this unit in the shared-memory table of drive vectors: its rank among the constrained units
+  {
+    const unsigned bal = __ballot_sync(0xffffffffu, has_cons);
+    if (!isD && lane == 0) red[warp] = (double)__popc(bal);
+    __syncthreads();
+    if (has_cons) {
+      int slot = __popc(bal & ((1u << lane) - 1u));
+      for (int w = 0; w < (isD ? warp - NDW : warp); ++w) slot += (int)red[w];
+      flags |= (unsigned)slot << 10;
+      if (!isD) {
+#pragma unroll
+        for (int j = 0; j < 3; ++j) {
+          const int cs_ = T.cons_slot[3 * blk + j];
+          CV[slot * 6 + j] = cs_ >= 0 ? T.drive_vec0[cs_] : 0.0;
+          CV[slot * 6 + 3 + j] = cs_ >= 0 ? T.drive_vec1[cs_] : 0.0;
+        }
+      }
+    }
+    __syncthreads();
+  }
   int bbp;  // the two blocks of this thread's bond, packed
   { const int2 bb = T.bond_blocks[bnd]; bbp = bb.x | (bb.y << 16); }
 
   // ---- constants ----------------------------------------------------------------------------------------------
   for (int i = tid; i < NSL * TT; i += TT) SL[i] = 0.0;
   for (int i = tid; i < 28 * TU; i += TT) smem[L::QSP + i] = 0.0;
-  for (int i = tid; i < 2 * NSCAL + 5 * NSLOT + 32; i += TT) Sq0[i] = 0.0;
+  for (int i = tid; i < 2 * NSCAL + 5 * NSLOT + 8 * NDRV; i += TT) Sq0[i] = 0.0;
   if (tid == 0) {
-    drv[30] = nan(""); drv[31] = nan("");
+    PC[0] = leaf_ptr(a.p.k_stretch, design)[0]; PC[1] = leaf_ptr(a.p.k_shear, design)[0]; PC[2] = leaf_ptr(a.p.k_rot, design)[0];
+    PC[3] = 0.0; PC[4] = 0.0; PC[5] = 0.0;
+    if (CONTACT) { const double* g_contact = leaf_ptr(a.p.contact, design); PC[3] = g_contact[0]; PC[4] = g_contact[1]; PC[5] = g_contact[2]; }
     C->h = 0; C->h0 = 0; C->d1 = 0; C->s0 = 0; C->s_target = 0; C->s_cur = 0; C->x = 0;
     C->n_steps = 0; C->n_acc = 0; C->n_rhs = 0; C->istep = 0; C->status = 0; C->crossing = 0; C->contact_seen = 0;
   }
@@ -389,86 +481,67 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     bcg[8 * TT] = da1; bcg[9 * TT] = da2;
   }
   for (int q = 0; q < 6 + 4 + 4 * NE3; ++q) gcol[G_SPART + (long long)q * TT] = 0.0;
-  double cmin = 0, ccut = 0, ckc = 0;
-  if (CONTACT) { const double* g_contact = leaf_ptr(a.p.contact, design); cmin = g_contact[0]; ccut = g_contact[1]; ckc = g_contact[2]; }
   // y_bar = g[-1]
   if (isD) {
+    double cu[3], cv[3];
+    tmem_st_wait();
+    cot3(a.n_t - 1, false, cu); cot3(a.n_t - 1, true, cv);
 #pragma unroll
-    for (int j = 0; j < 3; ++j) {
-      tmem_st(ta + 2 * (D_LU0 + j), is_free(j) ? cotangent_nl(a, design, a.n_t - 1, fidx(j), false) : 0.0);
-      tmem_st(ta + 2 * (D_LV0 + j), is_free(j) ? cotangent_nl(a, design, a.n_t - 1, fidx(j), true) : 0.0);
-    }
+    for (int j = 0; j < 3; ++j) { tmem_st(ta + 2 * (D_LU0 + j), cu[j]); tmem_st(ta + 2 * (D_LV0 + j), cv[j]); }
     tmem_st_wait();
   }
   __syncthreads();
 
   const double inv_n = 1.0 / (double)a.aug_size;
-  constexpr int EV_INIT = 6, EV_PROBE = 7;
-  int ev = EV_INIT, i = a.n_t - 1, par = 0;
-  unsigned nev = 0;  // evaluation counter: selects the Ws buffer
-  double hst = 0.0;  // step size of the stage about to be evaluated (h0 for the probe)
-  bool running = i >= 1;
+  // Drive table: row e holds the drive channels, their time derivatives and parameter derivatives at the time of
+  // evaluation e (0..5 stages of the coming step, 6 interval start, 7 probe).  The rows of a whole step are filled at once
+  // by the lanes of the last warp (one lane per row, SIMT-parallel) before the barrier that ends the previous step, so
+  // no signal is evaluated inside phases A / B / C.
+  auto fill_drive = [&](int row, double t) { drive_row_nl(T.drive_kind, t, g_drive, T.table, drv + row * NDRV); };
+  const bool drive_on = T.drive_kind != DFX_DRIVE_ZERO;
+  if (drive_on && tid == TT - 32 + EV_INIT && a.n_t >= 2) fill_drive(EV_INIT, ts[a.n_t - 1]);
+  __syncthreads();
 
-  while (running) {
-    // ================= stage state (phase A) =================
-    QC qc;
-    qc.par = par; qc.atol = atol; qc.rtol = rtol;
-    const double s_cur = C->s_cur;
-    double time;
-    int kidx;
-    if (ev == EV_INIT) { time = ts[i]; kidx = 0; qc.mode = 0; }
-    else if (ev == EV_PROBE) { time = -(C->s0 + hst); kidx = 1; qc.mode = 7; }
-    else { kidx = ev + 1; time = -(s_cur + hst * tab.alpha[ev]); qc.mode = kidx; }
-    qc.h = hst; qc.crossing = C->crossing != 0; qc.x = C->x;
-    qc.cs = tab.c_sol[kidx]; qc.ce = tab.c_err[kidx]; qc.cm = tab.c_mid[kidx];
-    qc.cs0 = tab.c_sol[0]; qc.ce0 = tab.c_err[0]; qc.cm0 = tab.c_mid[0];
-    const bool want_q = qc.mode != 1;
-    const double time_next = ev < 5 ? -(s_cur + hst * tab.alpha[ev + 1]) : nan("");
-    double* Wcur = Ws + (nev & 1u) * 3 * TU;
-    ++nev;
-    // bond constants: fetched from L2 now, used after the barrier
-    double bc[NBC];
-#pragma unroll
-    for (int k = 0; k < NBC; ++k) bc[k] = gcol[G_BC + (long long)k * TT];
+  // The only loop-carried register is the kind of the next evaluation; the output interval, the quadrature parity and the
+  // step size live in the control block (written by thread 0 between barriers).
+  int ev = EV_INIT;
+  bool running = a.n_t >= 2;
+  if (tid == 0) { C->i = a.n_t - 1; C->par = 0; C->hst = 0.0; }
+  __syncthreads();
 
+  // ---- phase A: stage state of this thread's half of its unit, published to shared memory ------------------------
+  auto phaseA = [&](auto tag, double* Wcur) {
+    constexpr int EV = decltype(tag)::value;
+    const double hst = C->hst;
     if (!isD) {
       double us[3], vs[3];
-      if (ev == EV_INIT) {
-        const double* yi = ys + (long long)i * 2 * nf;
+      if constexpr (EV == EV_INIT) {
+        const double* yi = ys + (long long)C->i * 2 * nf;
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           us[j] = is_free(j) ? __ldcs(&yi[fidx(j)]) : 0.0;
           vs[j] = is_free(j) ? __ldcs(&yi[nf + fidx(j)]) : 0.0;
           tmem_st(ta + 2 * (P_U0 + j), us[j]); tmem_st(ta + 2 * (P_V0 + j), vs[j]);
         }
-      } else if (ev == EV_PROBE) {
+      } else if constexpr (EV == EV_PROBE) {
         double y0[6], k0[3];
         tm_ld<6>(ta + 2 * P_U0, y0);
         tm_ld<3>(ta + 2 * P_KV, k0);
 #pragma unroll
         for (int j = 0; j < 3; ++j) { us[j] = y0[j] - hst * y0[3 + j]; vs[j] = y0[3 + j] + hst * k0[j]; }
       } else {
-        switch (ev) {
-          case 0: stage_P<0>(ta, tab, hst, us, vs); break;
-          case 1: stage_P<1>(ta, tab, hst, us, vs); break;
-          case 2: stage_P<2>(ta, tab, hst, us, vs); break;
-          case 3: stage_P<3>(ta, tab, hst, us, vs); break;
-          case 4: stage_P<4>(ta, tab, hst, us, vs); break;
-          default: stage_P<5>(ta, tab, hst, us, vs); break;
-        }
+        stage_P<EV>(ta, tab, hst, us, vs);
       }
-      if (has_cons && T.drive_kind != DFX_DRIVE_ZERO) {
-        double s0_, s1_;
-        if (drv[30] == time) { s0_ = drv[28]; s1_ = drv[29]; }
-        else {
-          DriveEval de;
-          drive_eval(T.drive_kind, time, g_drive, false, de, T.table);
-          s0_ = de.s[0]; s1_ = de.s[1];
-        }
+#ifndef ABL_NO_CONS
+      if (has_cons && drive_on) {
+        const double s0_ = drv[EV * NDRV], s1_ = drv[EV * NDRV + 1];
+#pragma unroll
+        const double* cvp = CV + ((flags >> 10) & 63u) * 6;
 #pragma unroll
         for (int j = 0; j < 3; ++j)
-          if (is_cons(j)) { const int cs_ = T.cons_slot[3 * blk + j]; us[j] = T.drive_vec0[cs_] * s0_ + T.drive_vec1[cs_] * s1_; }
+          if (is_cons(j)) us[j] = cvp[j] * s0_ + cvp[3 + j] * s1_;
       }
+#endif
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
         if (!is_free(j)) { vs[j] = 0.0; if (!is_cons(j)) us[j] = 0.0; }
@@ -476,17 +549,17 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       }
       if (has_unit) {
         double sn, cs;
-        sincos(us[2], &sn, &cs);
+        sincos_fast(us[2], &sn, &cs);
         Us[tid] = us[0]; Us[TU + tid] = us[1]; Us[2 * TU + tid] = us[2]; Us[3 * TU + tid] = sn; Us[4 * TU + tid] = cs;
       }
     } else {
       double lus[3], lvs[3];
-      if (ev == EV_INIT) {
+      if constexpr (EV == EV_INIT) {
         double y0[6];
         tm_ld<6>(ta + 2 * D_LU0, y0);
 #pragma unroll
         for (int j = 0; j < 3; ++j) { lus[j] = y0[j]; lvs[j] = y0[3 + j]; }
-      } else if (ev == EV_PROBE) {
+      } else if constexpr (EV == EV_PROBE) {
         double y0[6], k0[3], k1[3];
         tm_ld<6>(ta + 2 * D_LU0, y0);
         tm_ld<3>(ta + 2 * D_KLU, k0);
@@ -494,14 +567,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 #pragma unroll
         for (int j = 0; j < 3; ++j) { lus[j] = y0[j] + hst * k0[j]; lvs[j] = y0[3 + j] + hst * k1[j]; }
       } else {
-        switch (ev) {
-          case 0: stage_D<0>(ta, tab, hst, lus, lvs); break;
-          case 1: stage_D<1>(ta, tab, hst, lus, lvs); break;
-          case 2: stage_D<2>(ta, tab, hst, lus, lvs); break;
-          case 3: stage_D<3>(ta, tab, hst, lus, lvs); break;
-          case 4: stage_D<4>(ta, tab, hst, lus, lvs); break;
-          default: stage_D<5>(ta, tab, hst, lus, lvs); break;
-        }
+        stage_D<EV>(ta, tab, hst, lus, lvs);
       }
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -511,85 +577,85 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       }
     }
     tmem_st_wait();
-    __syncthreads();
+  };
 
-    // ================= phase B: this thread's bond =================
-    double accq = 0.0;  // this thread's contribution to the error norm / probe norm
-    if (tid == TT - 1 && T.drive_kind != DFX_DRIVE_ZERO) {  // drive channels: now (with derivatives) and next
-      DriveEval de;
-      drive_eval(T.drive_kind, time, g_drive, true, de, T.table);
-      drv[2] = de.sdot[0]; drv[3] = de.sdot[1];
-#pragma unroll
-      for (int q = 0; q < DFX_MAX_DRIVE_PARAMS; ++q) { drv[4 + q] = de.dsdp[0][q]; drv[9 + q] = de.dsdp[1][q]; }
-      drive_eval(T.drive_kind, time_next, g_drive, false, de, T.table);
-      drv[28] = de.s[0]; drv[29] = de.s[1]; drv[30] = time_next;
-    }
+  // ---- phase C: gather the bond slots of this thread's half of its unit, stage derivatives, quadratures -----------
+  // (qb0, qb1: integrands of the reference-vector quadratures of this thread's bond, from phase B.)  Returns the
+  // thread's contribution to the error norm (last stage) or to d2 of initial_step_size (probe).
+  auto phaseC = [&](auto tag, const double* Wcur, double qb0, double qb1) -> double {
+    constexpr int EV = decltype(tag)::value;
+    constexpr int KIDX = Ev<EV>::kidx, MODE = Ev<EV>::mode;
+#ifdef ABL_NO_Q
+    constexpr bool WANT_Q = false;
+#else
+    constexpr bool WANT_Q = MODE != 1;
+#endif
+    constexpr bool HOT = MODE >= 3 && MODE <= 5;
+    double accq = 0.0;
+    QC qc;
+    qc.par = C->par; qc.crossing = C->crossing != 0; qc.h = C->hst; qc.x = C->x; qc.atol = a.atol; qc.rtol = a.rtol;
+    // vertex -> bond table of this thread's unit (two vertices per 32-bit word, 0xffff: none), parked in tensor memory
+    unsigned nbp[2];
     {
-      double p_c0 = 0, p_c1 = 0, p_c2 = 0;
-      bool act = false;
-      if (has_bnd) {
-        const int b1 = bbp & 0xffff, b2 = bbp >> 16;
-        BlockState<Dual> s1, s2;
-        make_block(Us[b1], Us[TU + b1], Us[2 * TU + b1], Us[3 * TU + b1], Us[4 * TU + b1], Wcur[b1], Wcur[TU + b1], Wcur[2 * TU + b1], s1);
-        make_block(Us[b2], Us[TU + b2], Us[2 * TU + b2], Us[3 * TU + b2], Us[4 * TU + b2], Wcur[b2], Wcur[TU + b2], Wcur[2 * TU + b2], s2);
-        const double* g_ks = leaf_ptr(a.p.k_stretch, design);
-        const double* g_ksh = leaf_ptr(a.p.k_shear, design);
-        const double* g_kr = leaf_ptr(a.p.k_rot, design);
-        BondConst bcs = {bc[0], bc[1], bc[2], bc[3]};
-        BondOut<Dual> o;
-        bond_gradient<Dual, true>(DFX_BOND_LIGAMENT, s1, s2, bc[4], bc[5], bc[6], bc[7], bcs, g_ks[0], g_ksh[0], g_kr[0], o);
-        double a1 = 0.0, a2 = 0.0;
-        if (CONTACT) {
-          Dual psi1 = wrapT(s1.th - s2.th + bc[8]);
-          Dual psi2 = wrapT(s2.th - s1.th + bc[9]);
-          const bool act1 = !(psi1.v < cmin) && psi1.v < ccut, act2 = !(psi2.v < cmin) && psi2.v < ccut;
-          act = act1 || act2;
-          if (act) {
-            Dual e1, e2, m1, m2, c1, c2, k1, k2;
-            contact_term<Dual>(psi1, cmin, ccut, ckc, e1, m1, c1, k1);
-            contact_term<Dual>(psi2, cmin, ccut, ckc, e2, m2, c2, k2);
-            o.f1[2] = o.f1[2] + e1 - e2;
-            o.f2[2] = o.f2[2] + e2 - e1;
-            a1 = e1.d; a2 = e2.d;
-            p_c0 = -(m1.d + m2.d); p_c1 = -(c1.d + c2.d); p_c2 = -(k1.d + k2.d);
-            if (!(flags & 512u)) { flags |= 512u; C->contact_seen = 1; }
-          }
-        }
-        const int b = tid;
-        // forces on the two ends are equal and opposite: store (gdx, gdy) once, the two torques separately
-        SL[b] = o.f2[0].v; SL[TT + b] = o.f2[1].v; SL[2 * TT + b] = -o.f1[2].v; SL[3 * TT + b] = -o.f2[2].v;
-        SL[4 * TT + b] = o.f2[0].d; SL[5 * TT + b] = o.f2[1].d; SL[6 * TT + b] = o.f1[2].d; SL[7 * TT + b] = o.f2[2].d;
-        SL[8 * TT + b] = -o.gr1[0].d; SL[9 * TT + b] = -o.gr1[1].d;
-        SL[10 * TT + b] = -o.gr2[0].d; SL[11 * TT + b] = -o.gr2[1].d;
-        if (CONTACT && (flags & 512u)) { SL[12 * TT + b] = a1; SL[13 * TT + b] = a2; }
-        if (want_q) {
-          // d(w.F)/dp = -(dual part of dE/dp)
-          const double qb[2] = {-o.gr0[0].d, -o.gr0[1].d};
-          accq = quad_entries<2>(qc, qg, 8, gcol + G_BQ, gcol + G_BQ + 2 * TT, TT, qb);
-          double* sp = gcol + G_SPART;
-          sp[0] = -o.gks.d; sp[TT] = -o.gksh.d; sp[2 * TT] = -o.gkr.d;
-          if (CONTACT && (flags & 512u)) { sp[3 * TT] = p_c0; sp[4 * TT] = p_c1; sp[5 * TT] = p_c2; }
+      uint32_t lo, hi;
+      tmem_ld_issue(ta_topo + 2, lo, hi);
+      tmem_ld_wait();
+      tmem_pin(lo, hi);
+      nbp[0] = lo; nbp[1] = hi;
+    }
+    auto nbq = [&](int l) { const int f = (int)((nbp[l >> 1] >> ((l & 1) * 16)) & 0xffffu); return f == 0xffff ? -1 : f; };
+    // bond role: running sums of the reference-vector quadratures live in L2: fetched now, committed at the end
+    double bq_in[4];
+#ifndef ABL_NO_BQ
+    if (HOT && has_bnd) {
+#pragma unroll
+      for (int k = 0; k < 4; ++k) bq_in[k] = gcol[G_BQ + (long long)k * TT];
+    }
+#endif
+    const bool seen = CONTACT && C->contact_seen;
+    if (!isD) {
+      // dense scalar leaves: P warp w sums the partials of bonds [192 q, 192 q + 192), q = w / 3, of leaf w % 3 (and of
+      // contact leaf w % 3 once a bond has touched), fixed order; loads issued first, consumed last
+      double rk[6] = {0, 0, 0, 0, 0, 0}, rc[6] = {0, 0, 0, 0, 0, 0};
+#ifndef ABL_NO_REDUCE
+      if (WANT_Q) {
+        const double* sp = gbase + G_SPART + (long long)(warp % 3) * TT + (warp / 3) * 192 + lane;
+#pragma unroll
+        for (int q = 0; q < 6; ++q) rk[q] = __ldcg(&sp[q * 32]);
+        if (seen) {
+#pragma unroll
+          for (int q = 0; q < 6; ++q) rc[q] = __ldcg(&sp[3 * TT + q * 32]);
         }
       }
-    }
-    __syncthreads();
-
-    // ================= phase C: this thread's half of its unit =================
-    if (!isD) {
-      double F[3] = {0, 0, 0};
+#endif
+      double F[3] = {0, 0, 0}, val[10], An[NPB], Ap[NPB];
+#pragma unroll
+      for (int l = 0; l < 4; ++l) val[6 + l] = 0.0;
 #pragma unroll
       for (int l = 0; l < NPB; ++l) {
-        const int nb_ = nbq[l];
+        An[l] = 0.0; Ap[l] = 0.0;
+        const int nb_ = nbq(l);
         if (nb_ >= 0) {
           const int b = nb_ >> 1;
           const bool second = nb_ & 1;
           const double sg = second ? -1.0 : 1.0;
           F[0] += sg * SL[b]; F[1] += sg * SL[TT + b]; F[2] += SL[(second ? 3 : 2) * TT + b];
+          if (WANT_Q) {
+            val[6 + l] = SL[(second ? 10 : 8) * TT + b];
+            if (seen) {
+              // dS/dalpha = -(dual part of dE/dalpha): a1next:+e1, a1prev:-e2, a2next:+e2, a2prev:-e1
+              const double e1d = SL[12 * TT + b], e2d = SL[13 * TT + b];
+              An[l] = second ? -e2d : -e1d;
+              Ap[l] = second ? e1d : e2d;
+            }
+          }
         }
       }
+      // partial sums of the dense scalar leaves (the loads were issued before the gather)
+      double sk = ((rk[0] + rk[1]) + (rk[2] + rk[3])) + (rk[4] + rk[5]);
+      double scn = seen ? ((rc[0] + rc[1]) + (rc[2] + rc[3])) + (rc[4] + rc[5]) : 0.0;
       double vst[3];
       tm_ld<3>(ta + 2 * P_TV, vst);
-      double val[6];
       double p_damp = 0.0;
 #pragma unroll
       for (int j = 0; j < 3; ++j) {
@@ -602,49 +668,70 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
           val[j] = -wj * acc;
           if (DAMP != 0 && ((flags >> (6 + j)) & 1u)) { if (DAMP == 2) val[3 + j] = -wj * vst[j]; else p_damp -= wj * vst[j]; }
         }
-        tmem_st(ta + 2 * (P_KV + kidx * 3 + j), kvv);
+        tmem_st(ta + 2 * (P_KV + KIDX * 3 + j), kvv);
       }
-      if (want_q) {
-        double* qs = smem + L::QSP + tid;
-        if (DAMP == 2) accq += quad_entries<6>(qc, qg, 0, qs, qs + 6 * TU, TU, val);
-        else { const double v3[3] = {val[0], val[1], val[2]}; accq += quad_entries<3>(qc, qg, 0, qs, qs + 6 * TU, TU, v3); }
-        if (DAMP == 1) { const double tot = warp_sum(p_damp); if (lane == 0) scal_slot(qc, accb, SLOT_DAMP + warp, tot); }
-        // dense scalar leaves: warp k sums the 768 per-bond partials of leaf k (fixed order)
-        if (warp < (CONTACT ? 6 : 3) && (warp < 3 || C->contact_seen)) {
-          const double* sp = gbase + G_SPART + (long long)warp * TT + lane;
-          double s = 0.0;
+      if (WANT_Q) {
+        if (seen) {
+          bool any_contact = false;
 #pragma unroll
-          for (int q0_ = 0; q0_ < NW; q0_ += 8) {
-            double v8[8];
+          for (int l = 0; l < NPB; ++l) any_contact |= (An[l] != 0.0) | (Ap[l] != 0.0);
+          if (any_contact) {
+            // contact chain of the centroid_node_vectors cotangent (x components; the D thread does y): edge l -> l+1 is
+            // node l's "next" edge and, reversed, node (l+1)'s "previous" edge
 #pragma unroll
-            for (int q = 0; q < 8; ++q) v8[q] = __ldcg(&sp[(q0_ + q) * 32]);
-#pragma unroll
-            for (int q = 0; q < 8; ++q) s += v8[q];
+            for (int l = 0; l < NPB; ++l) {
+              const int ln = l + 1 == NPB ? 0 : l + 1;
+              const int n = blk * NPB + l, m = blk * NPB + ln;
+              const double ex = g_cnv[2 * m] - g_cnv[2 * n], ey = g_cnv[2 * m + 1] - g_cnv[2 * n + 1];
+              const double wx = -(An[l] + Ap[ln]) * ey / (ex * ex + ey * ey);
+              val[6 + ln] += wx; val[6 + l] -= wx;
+            }
           }
-          s = warp_sum(s);
-          if (lane == 0) scal_slot(qc, accb, warp, s);
         }
+        double* qs = smem + L::QSP + tid;
+        {
+          const double v3[3] = {val[0], val[1], val[2]};
+          accq += quad_entries<MODE, 3>(qc, tab, qg, 0, qs, qs + 10 * TU, TU, v3);
+        }
+        if (DAMP == 2) {
+          const double v3[3] = {val[3], val[4], val[5]};
+          accq += quad_entries<MODE, 3>(qc, tab, qg, 3, qs + 3 * TU, qs + 13 * TU, TU, v3);
+        }
+        {
+          const double v4[4] = {val[6], val[7], val[8], val[9]};
+          accq += quad_entries<MODE, 4>(qc, tab, qg, 6, qs + 6 * TU, qs + 16 * TU, TU, v4);
+        }
+        if (DAMP == 1) { const double tot = warp_sum(p_damp); if (lane == 0) scal_slot<MODE>(tab, accb, SLOT_DAMP + warp, tot); }
+#ifndef ABL_NO_REDUCE
+        {
+#pragma unroll
+          for (int o = 16; o > 0; o >>= 1) {
+            sk += __shfl_xor_sync(0xffffffffu, sk, o);
+            if (CONTACT) scn += __shfl_xor_sync(0xffffffffu, scn, o);
+          }
+          if (lane == 0) scal_slot<MODE>(tab, accb, SLOT_K + (warp % 3) * 4 + warp / 3, sk);
+          if (CONTACT && lane == 1 && seen) scal_slot<MODE>(tab, accb, SLOT_K + (3 + warp % 3) * 4 + warp / 3, scn);
+        }
+#endif
       }
     } else {
-      double HW[3] = {0, 0, 0}, val[8], An[NPB], Ap[NPB];
-      const bool seen = CONTACT && C->contact_seen;
-#pragma unroll
-      for (int l = 0; l < 4; ++l) { val[l] = 0.0; val[4 + l] = 0.0; }
+      double HW[3] = {0, 0, 0}, val[4] = {0, 0, 0, 0}, An[NPB], Ap[NPB];
 #pragma unroll
       for (int l = 0; l < NPB; ++l) {
         An[l] = 0.0; Ap[l] = 0.0;
-        const int nb_ = nbq[l];
+        const int nb_ = nbq(l);
         if (nb_ >= 0) {
           const int b = nb_ >> 1;
           const bool second = nb_ & 1;
           const double sg = second ? -1.0 : 1.0;
           HW[0] -= sg * SL[4 * TT + b]; HW[1] -= sg * SL[5 * TT + b]; HW[2] += SL[(second ? 7 : 6) * TT + b];
-          val[l] = SL[(second ? 10 : 8) * TT + b]; val[4 + l] = SL[(second ? 11 : 9) * TT + b];
-          if (seen) {
-            // dS/dalpha = -(dual part of dE/dalpha): a1next:+e1, a1prev:-e2, a2next:+e2, a2prev:-e1
-            const double e1d = SL[12 * TT + b], e2d = SL[13 * TT + b];
-            An[l] = second ? -e2d : -e1d;
-            Ap[l] = second ? e1d : e2d;
+          if (WANT_Q) {
+            val[l] = SL[(second ? 11 : 9) * TT + b];
+            if (seen) {
+              const double e1d = SL[12 * TT + b], e2d = SL[13 * TT + b];
+              An[l] = second ? -e2d : -e1d;
+              Ap[l] = second ? e1d : e2d;
+            }
           }
         }
       }
@@ -654,74 +741,238 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       for (int j = 0; j < 3; ++j) {
         double kluv = 0.0, klvv = 0.0;
         if (is_free(j)) { kluv = -HW[j]; klvv = lust[j] - CDs[j * TU + unit] * Wcur[j * TU + unit]; }
-        tmem_st(ta + 2 * (D_KLU + kidx * 3 + j), kluv);
-        tmem_st(ta + 2 * (D_KLV + kidx * 3 + j), klvv);
+        tmem_st(ta + 2 * (D_KLU + KIDX * 3 + j), kluv);
+        tmem_st(ta + 2 * (D_KLV + KIDX * 3 + j), klvv);
       }
-      if (want_q) {
+      if (WANT_Q) {
         if (seen) {
           bool any_contact = false;
 #pragma unroll
           for (int l = 0; l < NPB; ++l) any_contact |= (An[l] != 0.0) | (Ap[l] != 0.0);
           if (any_contact) {
-            // contact chain of the centroid_node_vectors cotangent: edge l -> l+1 is node l's "next" edge and,
-            // reversed, node (l+1)'s "previous" edge; both angles have the same derivative w.r.t. the end points
 #pragma unroll
             for (int l = 0; l < NPB; ++l) {
               const int ln = l + 1 == NPB ? 0 : l + 1;
               const int n = blk * NPB + l, m = blk * NPB + ln;
               const double ex = g_cnv[2 * m] - g_cnv[2 * n], ey = g_cnv[2 * m + 1] - g_cnv[2 * n + 1];
-              const double inv = 1.0 / (ex * ex + ey * ey);
-              const double wx = -(An[l] + Ap[ln]) * ey * inv, wy = (An[l] + Ap[ln]) * ex * inv;
-              val[ln] += wx; val[4 + ln] += wy;
-              val[l] -= wx; val[4 + l] -= wy;
+              const double wy = (An[l] + Ap[ln]) * ex / (ex * ex + ey * ey);
+              val[ln] += wy; val[l] -= wy;
             }
           }
         }
         double* qs = smem + L::QSD + unit;
-        accq += quad_entries<8>(qc, qg, 0, qs, qs + 8 * TU, TU, val);
+        accq += quad_entries<MODE, 4>(qc, tab, qg, 0, qs, qs + 4 * TU, TU, val);
         // t0_bar and the drive parameters only receive contributions from constrained DOFs
-        if (warp_t0 && T.drive_kind != DFX_DRIVE_ZERO) {
+#ifndef ABL_NO_T0
+        if (warp_t0 && drive_on) {
+          // the few constrained units of the warp add their terms to the warp's running sums one after the other (fixed
+          // order: no shuffles, no atomics); the first one assigns in the modes that assign
           double p[6] = {0, 0, 0, 0, 0, 0};
           if (has_cons) {
+            const double* dr = drv + EV * NDRV;
+            const double* cvp = CV + ((flags >> 10) & 63u) * 6;
 #pragma unroll
             for (int j = 0; j < 3; ++j) {
               if (is_cons(j)) {
-                const int cs_ = T.cons_slot[3 * blk + j];
-                const double v0_ = T.drive_vec0[cs_], v1_ = T.drive_vec1[cs_];
-                p[0] -= HW[j] * (v0_ * drv[2] + v1_ * drv[3]);
+                const double v0_ = cvp[j], v1_ = cvp[3 + j];
+                p[0] -= HW[j] * (v0_ * dr[2] + v1_ * dr[3]);
 #pragma unroll
-                for (int q = 0; q < DFX_MAX_DRIVE_PARAMS; ++q) p[1 + q] -= HW[j] * (v0_ * drv[4 + q] + v1_ * drv[9 + q]);
+                for (int q = 0; q < DFX_MAX_DRIVE_PARAMS; ++q) p[1 + q] -= HW[j] * (v0_ * dr[4 + q] + v1_ * dr[9 + q]);
               }
             }
           }
+          unsigned todo = __ballot_sync(0xffffffffu, has_cons);
+          const int first = __ffs(todo) - 1;
+          while (todo) {
+            const int c = __ffs(todo) - 1;
+            todo &= todo - 1;
+            if (lane == c) {
 #pragma unroll
-          for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-            for (int q = 0; q < 6; ++q) p[q] += __shfl_xor_sync(0xffffffffu, p[q], o);
-          }
-          if (lane <= ndp) {
-            double mine = p[0];
-#pragma unroll
-            for (int q = 1; q < 6; ++q) if (lane == q) mine = p[q];
-            scal_slot(qc, accb, SLOT_T + lane * NDW + (warp - NDW), mine);
+              for (int q = 0; q < 6; ++q) {
+                if (q <= T.n_drive_params) {
+                  double* k1 = accb + SLOT_T + q * NDW + (warp - NDW);
+                  if (c == first) scal_slot<MODE>(tab, accb, SLOT_T + q * NDW + (warp - NDW), p[q]);
+                  else scal_slot_more<MODE>(tab, k1, p[q]);
+                }
+              }
+            }
+            __syncwarp();
           }
         }
+#endif
       }
     }
+#ifndef ABL_NO_BQ
+    if (WANT_Q && has_bnd) {
+      if constexpr (HOT) {
+        const double cs = tab.c_sol[MODE], ce = tab.c_err[MODE];
+        gcol[G_BQ] = fma(cs, qb0, bq_in[0]); gcol[G_BQ + TT] = fma(cs, qb1, bq_in[1]);
+        gcol[G_BQ + 2 * TT] = fma(ce, qb0, bq_in[2]); gcol[G_BQ + 3 * TT] = fma(ce, qb1, bq_in[3]);
+        if (qc.crossing) {
+          const double cm = tab.c_mid[MODE];
+          double* k7p = qg + (long long)((3 - qc.par) * NE3 + 10) * TT;
+          k7p[0] = fma(cm, qb0, k7p[0]); k7p[TT] = fma(cm, qb1, k7p[TT]);
+        }
+      } else {
+        const double qb[2] = {qb0, qb1};
+        accq += quad_entries<MODE, 2>(qc, tab, qg, 10, gcol + G_BQ, gcol + G_BQ + 2 * TT, TT, qb);
+      }
+    }
+#endif
     tmem_st_wait();
+    return accq;
+  };
+
+#define DFX_A3_DISPATCH(CALL)                                                                          \
+  switch (ev) {                                                                                        \
+    case 0: CALL(IC<0>{}); break;                                             \
+    case 1: CALL(IC<1>{}); break;                                             \
+    case 2: CALL(IC<2>{}); break;                                             \
+    case 3: CALL(IC<3>{}); break;                                             \
+    case 4: CALL(IC<4>{}); break;                                             \
+    case 5: CALL(IC<5>{}); break;                                             \
+    case EV_INIT: CALL(IC<EV_INIT>{}); break;                                 \
+    default: CALL(IC<EV_PROBE>{}); break;                                     \
+  }
+
+#ifdef DFX_PHASE_TIMERS
+  // cycles of lane 0 of every warp: A | wait A->B | B | wait B->C | C | what follows (DFX_PHASE_TIMERS builds only)
+  long long pt_acc[6] = {0, 0, 0, 0, 0, 0}, pt_mark = clock64();
+#define PT_MARK(k) do { const long long now_ = clock64(); pt_acc[k] += now_ - pt_mark; pt_mark = now_; } while (0)
+#else
+#define PT_MARK(k) do { } while (0)
+#endif
+  while (running) {
+    PT_MARK(5);
+    double* Wcur = Ws + (ev & 1) * 3 * TU;  // consecutive evaluations never have the same parity (6 -> 7 -> 0..5 -> 0 | 6)
+    // bond constants: fetched from L2 now, used after the barrier
+    double bc[NBC];
+#pragma unroll
+    for (int k = 0; k < (CONTACT ? NBC : NBC - 2); ++k) bc[k] = gcol[G_BC + (long long)k * TT];
+#define DFX_A3_A(TAG) phaseA(TAG, Wcur)
+    DFX_A3_DISPATCH(DFX_A3_A)
+#undef DFX_A3_A
+    PT_MARK(0);
+    __syncthreads();
+    PT_MARK(1);
+
+    // ================= phase B: this thread's bond (one copy of the code for every kind of evaluation) =================
+    double qb0 = 0.0, qb1 = 0.0;  // integrands of the two reference-vector quadratures of this thread's bond
+    if (has_bnd) {
+      const bool want_q = ev != 0;  // the second stage of a step has zero weight in every combination
+      const int b1 = bbp & 0xffff, b2 = bbp >> 16;
+      const int b = tid;
+      // The ligament gradient on dual numbers (bond_gradient of dfx_device.cuh, ligament energy, with the parameter
+      // cotangents), written out in two sections so that the block rotations are not kept in registers across the
+      // energy arithmetic: they are read again from shared memory for the node-vector cotangents.
+      Dual gdx, gdy;          // dE/d(dU)
+      double a1 = 0.0, a2 = 0.0, p_c0 = 0, p_c1 = 0, p_c2 = 0;
+      double gks_d, gksh_d, gkr_d;
+      {
+        BlockState<Dual> s1, s2;
+        make_block(Us[b1], Us[TU + b1], Us[2 * TU + b1], Us[3 * TU + b1], Us[4 * TU + b1], Wcur[b1], Wcur[TU + b1], Wcur[2 * TU + b1], s1);
+        make_block(Us[b2], Us[TU + b2], Us[2 * TU + b2], Us[3 * TU + b2], Us[4 * TU + b2], Wcur[b2], Wcur[TU + b2], Wcur[2 * TU + b2], s2);
+        const double r0x = bc[0], r0y = bc[1], L0 = bc[2], iL0 = bc[3], r1x = bc[4], r1y = bc[5], r2x = bc[6], r2y = bc[7];
+        const double ks = PC[0], ksh = PC[1], kr = PC[2];
+        Dual c1m = s1.c - 1.0, c2m = s2.c - 1.0;
+        Dual dx = (s2.x + c2m * r2x - s2.s * r2y) - (s1.x + c1m * r1x - s1.s * r1y) + r0x;
+        Dual dy = (s2.y + s2.s * r2x + c2m * r2y) - (s1.y + s1.s * r1x + c1m * r1y) + r0y;
+        Dual t1x = -(s1.s * r1x) - s1.c * r1y, t1y = s1.c * r1x - s1.s * r1y;  // d(node)/d(theta) = R'(theta) r
+        Dual t2x = -(s2.s * r2x) - s2.c * r2y, t2y = s2.c * r2x - s2.s * r2y;
+        Dual dth = s2.th - s1.th;
+        Dual mean = (s2.th + s1.th) * 0.5;
+        const double L0sq = L0 * L0;
+        Dual L2 = dx * dx + dy * dy;
+        const double rinv = rsqrt_pos(L2.v);
+        Dual iL2 = inv_from(L2, rinv);
+        Dual L = len_from(L2, rinv);
+        double gv;
+        {
+          const double cp = r0x * iL0, sp = r0y * iL0;
+          const double ex = dx.v * rinv, ey = dy.v * rinv;
+          gv = wrap_value(angle_of_unit(cp * ey - sp * ex, cp * ex + sp * ey) - mean.v);
+        }
+        Dual gam(gv, (dx.v * dy.d - dy.v * dx.d) * iL2.v - mean.d);
+        Dual ext = L - L0;
+        Dual A = ext * ks * L * iL2;  // ks (L-L0)/L
+        Dual M = gam * (ksh * L0sq);  // dE/dgamma
+        Dual Bc = M * iL2;
+        gdx = A * dx - Bc * dy;
+        gdy = A * dy + Bc * dx;
+        Dual bend = dth * kr;
+        Dual f1t = M * (-0.5) - (gdx * t1x + gdy * t1y) - bend;
+        Dual f2t = M * (-0.5) + (gdx * t2x + gdy * t2y) + bend;
+        if (CONTACT) {
+          Dual psi1 = wrapT(s1.th - s2.th + bc[8]);
+          Dual psi2 = wrapT(s2.th - s1.th + bc[9]);
+          const double cmin = PC[3], ccut = PC[4], ckc = PC[5];
+          const bool act1 = !(psi1.v < cmin) && psi1.v < ccut, act2 = !(psi2.v < cmin) && psi2.v < ccut;
+          if (act1 || act2) {
+            Dual e1, e2, m1, m2, c1, c2, k1, k2;
+            contact_term<Dual>(psi1, cmin, ccut, ckc, e1, m1, c1, k1);
+            contact_term<Dual>(psi2, cmin, ccut, ckc, e2, m2, c2, k2);
+            f1t = f1t + e1 - e2;
+            f2t = f2t + e2 - e1;
+            a1 = e1.d; a2 = e2.d;
+            p_c0 = -(m1.d + m2.d); p_c1 = -(c1.d + c2.d); p_c2 = -(k1.d + k2.d);
+            if (!(flags & 512u)) { flags |= 512u; C->contact_seen = 1; }
+          }
+        }
+        // forces on the two ends are equal and opposite: store (gdx, gdy) once, the two torques separately
+        SL[b] = gdx.v; SL[TT + b] = gdy.v; SL[2 * TT + b] = -f1t.v; SL[3 * TT + b] = -f2t.v;
+        SL[4 * TT + b] = gdx.d; SL[5 * TT + b] = gdy.d; SL[6 * TT + b] = f1t.d; SL[7 * TT + b] = f2t.d;
+        if (CONTACT && (flags & 512u)) { SL[12 * TT + b] = a1; SL[13 * TT + b] = a2; }
+        // parameter cotangent integrands: -(dual part of dE/dp)
+        gks_d = ext.v * ext.d; gksh_d = gam.v * gam.d * L0sq; gkr_d = dth.v * dth.d;
+        Dual dE_dL0 = gam * gam * (ksh * L0) - ext * ks;
+        qb0 = -(gdx.d + dE_dL0.d * (r0x * iL0) + M.d * (r0y / L0sq));
+        qb1 = -(gdy.d + dE_dL0.d * (r0y * iL0) - M.d * (r0x / L0sq));
+      }
+      asm volatile("" ::: "memory");  // the block rotations are re-read below instead of being carried in registers
+      {
+        const double sn1 = Us[3 * TU + b1], cs1 = Us[4 * TU + b1], w1 = Wcur[2 * TU + b1];
+        const double sn2 = Us[3 * TU + b2], cs2 = Us[4 * TU + b2], w2 = Wcur[2 * TU + b2];
+        const Dual s1(sn1, cs1 * w1), c1m(cs1 - 1.0, -sn1 * w1), s2(sn2, cs2 * w2), c2m(cs2 - 1.0, -sn2 * w2);
+        // dE/d(centroid_node_vector) of the two nodes: gr1 = -(R1 - I)^T g, gr2 = (R2 - I)^T g; stored with the sign of the integrand
+        SL[8 * TT + b] = (c1m * gdx + s1 * gdy).d; SL[9 * TT + b] = -(s1 * gdx - c1m * gdy).d;
+        SL[10 * TT + b] = -(c2m * gdx + s2 * gdy).d; SL[11 * TT + b] = -(c2m * gdy - s2 * gdx).d;
+      }
+      if (want_q) {
+        // d(w.F)/dp = -(dual part of dE/dp).  The reference-vector quadratures are updated at the end of phase C; the dense
+        // scalar leaves go through per-bond partials in the scratch, summed in phase C by the P warps.
+#ifndef ABL_NO_SPART
+        double* sp = gcol + G_SPART;
+        sp[0] = -gks_d; sp[TT] = -gksh_d; sp[2 * TT] = -gkr_d;
+        if (CONTACT && (flags & 512u)) { sp[3 * TT] = p_c0; sp[4 * TT] = p_c1; sp[5 * TT] = p_c2; }
+#endif
+      }
+    }
+    PT_MARK(2);
+    __syncthreads();
+    PT_MARK(3);
+
+    double accq = 0.0;  // this thread's contribution to the error norm / probe norm
+#define DFX_A3_C(TAG) accq = phaseC(TAG, Wcur, qb0, qb1)
+    DFX_A3_DISPATCH(DFX_A3_C)
+#undef DFX_A3_C
+    PT_MARK(4);
 
     // ================= what follows the evaluation =================
+    if (ev < 5) { ++ev; continue; }
+    int i = C->i, par = C->par;
+    const double hst = C->hst;
     if (ev == EV_INIT) {
       double sd0 = 0, sd1 = 0, pt = 0.0;
       if (!isD) {
-        double y0[6], k0[3];
+        double y0[6], k0[3], cu[3], cv[3];
         tm_ld<6>(ta + 2 * P_U0, y0);
         tm_ld<3>(ta + 2 * P_KV, k0);
+        cot3(i, false, cu); cot3(i, true, cv);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           if (is_free(j)) {
             // t_bar = func(ys[i], ts[i]) . g[i] with func = (v0, -kv[0])
-            pt += y0[3 + j] * cotangent_nl(a, design, i, fidx(j), false) - k0[j] * cotangent_nl(a, design, i, fidx(j), true);
+            pt += y0[3 + j] * cu[j] - k0[j] * cv[j];
             const double su = atol + fabs(y0[j]) * rtol, sv = atol + fabs(y0[3 + j]) * rtol;
             const double a0 = y0[j] / su, a1 = y0[3 + j] / sv, b0 = -y0[3 + j] / su, b1 = k0[j] / sv;
             sd0 += a0 * a0 + a1 * a1;
@@ -764,8 +1015,8 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       const double d0 = sqrt(block_sum(sd0, red));
       const double d1 = sqrt(block_sum(sd1, red));
       const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
-      if (tid == 0) { C->s0 = -ts[i]; C->s_target = -ts[i - 1]; C->h0 = h0; C->d1 = d1; C->n_rhs += 1; C->crossing = 0; }
-      hst = h0;
+      if (tid == 0) { C->s0 = -ts[i]; C->s_target = -ts[i - 1]; C->h0 = h0; C->d1 = d1; C->n_rhs += 1; C->crossing = 0; C->hst = h0; }
+      if (drive_on && tid == TT - 32 + EV_PROBE) fill_drive(EV_PROBE, ts[i] - h0);
       ev = EV_PROBE;
       __syncthreads();
     } else if (ev == EV_PROBE) {
@@ -818,17 +1069,20 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         C->n_rhs += 1; C->h = h; C->s_cur = s0; C->istep = 0; C->status |= status;
         if (!empty && !stop) { const double s_new = s0 + h; C->crossing = !(s_new < s_target); C->x = (s_target - s0) / (s_new - s0); }
       }
-      hst = h;
       if (empty) { if (--i < 1) running = false; else ev = EV_INIT; }
       else if (stop) running = false;
       else ev = 0;
+      if (tid == 0) { C->hst = h; C->i = i; }
+      if (drive_on && running && warp == NW - 1) {
+        if (ev == 0 && lane < 6) fill_drive(lane, -(s0 + h * tab.alpha[lane]));
+        else if (ev == EV_INIT && lane == EV_INIT) fill_drive(EV_INIT, ts[i]);
+      }
       __syncthreads();
-    } else if (ev < 5) {
-      ++ev;
     } else {
       double se = accq;
       const double h = hst;
-      const bool crossing = qc.crossing;
+      const bool crossing = C->crossing != 0;
+      const double xq = C->x, s_cur = C->s_cur;
       double y1a[3], y1b[3];  // P: u, v at the end of the step; D: lambda_u, lambda_v
       if (!isD) {
         double y0[6];
@@ -883,7 +1137,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         const double q1 = q0 + h * scal_total(accb, 2, tid);
         const double r = h * scal_total(accb, 3, tid) / (atol + rtol * fmax(fabs(q0), fabs(q1)));
         se += r * r;
-        Sqnew[tid] = crossing ? interp_eval(q0, q1, q0 + h * scal_total(accb, 4, tid), h * k1, h * k7, qc.x) : q1;
+        Sqnew[tid] = crossing ? interp_eval(q0, q1, q0 + h * scal_total(accb, 4, tid), h * k1, h * k7, xq) : q1;
       }
       const double ratio = sqrt(block_sum(se, red) * inv_n);
       const long long istep = C->istep + 1;
@@ -899,7 +1153,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
           if (crossing) {
             // interval finished: cotangents interpolated at s_target, plus g[i-1]
             if (isD) {
-              double y0[6];
+              double y0[6], nl[6];
               tm_ld<6>(ta + 2 * D_LU0, y0);
 #pragma unroll
               for (int j = 0; j < 3; ++j) {
@@ -909,10 +1163,16 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
                 double mlu = 0.0, mlv = 0.0;
 #pragma unroll
                 for (int l = 0; l < 7; ++l) { mlu = fma(tab.c_mid[l], klu[l], mlu); mlv = fma(tab.c_mid[l], klv[l], mlv); }
-                const double nlu = interp_eval(y0[j], y1a[j], y0[j] + h * mlu, h * klu[0], h * klu[6], qc.x);
-                const double nlv = interp_eval(y0[3 + j], y1b[j], y0[3 + j] + h * mlv, h * klv[0], h * klv[6], qc.x);
-                tmem_st(ta + 2 * (D_LU0 + j), is_free(j) ? nlu + cotangent_nl(a, design, i - 1, fidx(j), false) : 0.0);
-                tmem_st(ta + 2 * (D_LV0 + j), is_free(j) ? nlv + cotangent_nl(a, design, i - 1, fidx(j), true) : 0.0);
+                const double nlu = interp_eval(y0[j], y1a[j], y0[j] + h * mlu, h * klu[0], h * klu[6], xq);
+                const double nlv = interp_eval(y0[3 + j], y1b[j], y0[3 + j] + h * mlv, h * klv[0], h * klv[6], xq);
+                nl[j] = nlu; nl[3 + j] = nlv;
+              }
+              double cu[3], cv[3];
+              cot3(i - 1, false, cu); cot3(i - 1, true, cv);
+#pragma unroll
+              for (int j = 0; j < 3; ++j) {
+                tmem_st(ta + 2 * (D_LU0 + j), is_free(j) ? nl[j] + cu[j] : 0.0);
+                tmem_st(ta + 2 * (D_LV0 + j), is_free(j) ? nl[3 + j] + cv[j] : 0.0);
               }
             }
             interval_done = true;
@@ -956,18 +1216,30 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         C->h = h_new; C->s_cur = s_new;
         if (!interval_done && !stop) { const double s_nn = s_new + h_new; C->crossing = !(s_nn < s_target); C->x = (s_target - s_new) / (s_nn - s_new); }
       }
-      hst = h_new;
       if (stop) running = false;
       else if (interval_done) { if (--i < 1) running = false; else ev = EV_INIT; }
       else ev = 0;
+      if (tid == 0) { C->hst = h_new; C->i = i; C->par = par; }
+      if (drive_on && running && warp == NW - 1) {
+        if (ev == 0 && lane < 6) fill_drive(lane, -(s_new + h_new * tab.alpha[lane]));
+        else if (ev == EV_INIT && lane == EV_INIT) fill_drive(EV_INIT, ts[i]);
+      }
       __syncthreads();
     }
   }
 
+#ifdef DFX_PHASE_TIMERS
+  if (design == 0 && lane == 0 && (warp == 0 || warp == 4 || warp == 12 || warp == 15 || warp == 23)) {
+    const double n_ = (double)C->n_rhs;
+    printf("warp %2d cycles/eval: A %.0f | wait A->B %.0f | B %.0f | wait B->C %.0f | C %.0f | post %.0f | total %.0f | evaluations %.0f\n", warp,
+           pt_acc[0] / n_, pt_acc[1] / n_, pt_acc[2] / n_, pt_acc[3] / n_, pt_acc[4] / n_, pt_acc[5] / n_,
+           (pt_acc[0] + pt_acc[1] + pt_acc[2] + pt_acc[3] + pt_acc[4] + pt_acc[5]) / n_, n_);
+  }
+#endif
   // ---- outputs ----------------------------------------------------------------------------------------------
   __syncthreads();
   const double nanv = nan("");
-  const int status = C->status;
+  const int status = C->status, par = C->par;
   const bool bad = status != 0;
   {
     double qv[NE3];
@@ -980,6 +1252,9 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
           a.grads.damping[(long long)design * T.n_damped * 3 + T.damp_slot[3 * blk + j]] = is_free(j) ? qv[3 + j] : (bad ? nanv : 0.0);
         if (is_free(j) && a.grads.inertia) a.grads.inertia[(long long)design * nf + fidx(j)] = qv[j];
       }
+      if (has_unit && a.grads.centroid_node_vectors)
+#pragma unroll
+        for (int l = 0; l < NPB; ++l) a.grads.centroid_node_vectors[((long long)design * T.n_nodes + blk * NPB + l) * 2] = qv[6 + l];
     } else {
       double y0[6];
       tm_ld<6>(ta + 2 * D_LU0, y0);
@@ -994,13 +1269,12 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 #pragma unroll
         for (int l = 0; l < NPB; ++l) {
           const long long n = (long long)design * T.n_nodes + blk * NPB + l;
-          a.grads.centroid_node_vectors[n * 2] = qv[l];
-          a.grads.centroid_node_vectors[n * 2 + 1] = qv[4 + l];
+          a.grads.centroid_node_vectors[n * 2 + 1] = qv[l];
         }
     }
     if (has_bnd && a.grads.reference_vector) {
-      a.grads.reference_vector[((long long)design * NBONDS + bnd) * 2] = qv[8];
-      a.grads.reference_vector[((long long)design * NBONDS + bnd) * 2 + 1] = qv[9];
+      a.grads.reference_vector[((long long)design * NBONDS + bnd) * 2] = qv[10];
+      a.grads.reference_vector[((long long)design * NBONDS + bnd) * 2 + 1] = qv[11];
     }
   }
   if (tid == 0) {
@@ -1009,7 +1283,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     if (a.grads.k_rot) a.grads.k_rot[design] = bad ? nanv : Sq0[SC_KR];
     if (a.grads.damping && DAMP == 1) a.grads.damping[design] = bad ? nanv : Sq0[SC_DAMP];
     if (a.grads.contact && CONTACT) for (int k = 0; k < 3; ++k) a.grads.contact[(long long)design * 3 + k] = bad ? nanv : Sq0[SC_CONTACT + k];
-    if (a.grads.drive) for (int k = 0; k < ndp; ++k) a.grads.drive[(long long)design * ndp + k] = bad ? nanv : Sq0[SC_DRIVE + k];
+    if (a.grads.drive) for (int k = 0; k < T.n_drive_params; ++k) a.grads.drive[(long long)design * T.n_drive_params + k] = bad ? nanv : Sq0[SC_DRIVE + k];
     if (a.ts_bar) a.ts_bar[(long long)design * a.n_t] = bad ? nanv : Sq0[SC_T0];
     if (a.stats) {
       DfxStats st;

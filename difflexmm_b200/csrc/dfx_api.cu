@@ -62,6 +62,7 @@ struct DfxTopology {
   int device;
   DevTopo dev;
   const int* node_bond;  // [n_nodes] bond*2+side or -1 (fast adjoint kernel)
+  int n_cons_units;      // rigid units with at least one constrained DOF
   std::vector<void*> allocs;
   int sm_count;
 };
@@ -261,7 +262,7 @@ FastPlan plan_fast_adjoint(const DevTopo& T) {
 // DFX_ADJOINT_KERNEL=v2 keeps them on dfx_adjoint2.cuh (A/B comparisons).
 struct Fast3Plan { bool ok; int npb, damp; bool contact; };
 
-Fast3Plan plan_adjoint3(const DevTopo& T, const DfxParams& p) {
+Fast3Plan plan_adjoint3(const DevTopo& T, const DfxParams& p, int n_cons_units) {
   Fast3Plan f = {};
   const char* mode = getenv("DFX_ADJOINT_KERNEL");
   if (mode && (!strcmp(mode, "generic") || !strcmp(mode, "notmem") || !strcmp(mode, "v2"))) return f;
@@ -269,6 +270,7 @@ Fast3Plan plan_adjoint3(const DevTopo& T, const DfxParams& p) {
   if (T.bond_energy != DFX_BOND_LIGAMENT || T.load_kind != DFX_LOAD_NONE) return f;
   if (p.k_per_bond[0] || p.k_per_bond[1] || p.k_per_bond[2]) return f;
   if (T.n_blocks > k3::TU || T.n_bonds > k3::TT || T.n_blocks < 1 || T.n_bonds < 1) return f;
+  if (n_cons_units > k3::NCU) return f;  // the drive vectors of the constrained units are cached in shared memory
   const bool has_damp = T.n_damped > 0 && p.damping.ptr != nullptr;
   f.npb = T.n_npb; f.contact = T.contact != 0; f.damp = !has_damp ? 0 : (p.damping_per_dof ? 2 : 1);
   f.ok = adjoint3_supported(f.npb, f.contact, f.damp);
@@ -408,6 +410,9 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   D.bond_nodes = dbn; D.bond_blocks = dbb; D.free_of_dof = dfo; D.cons_slot = dcs; D.damp_slot = dds; D.free_dofs = dfd;
   D.drive_vec0 = dv0; D.drive_vec1 = dv1; D.load_mul = dlm;
   t->node_bond = dnb;
+  t->n_cons_units = 0;
+  for (int b = 0; b < D.n_blocks; ++b)
+    if (cons_slot[3 * b] >= 0 || cons_slot[3 * b + 1] >= 0 || cons_slot[3 * b + 2] >= 0) t->n_cons_units++;
   D.table.t = dtt; D.table.v = dtv; D.table.n = (int)tab_t.size();
   t->allocs = {dbn, dbb, dfo, dcs, dds, dfd, dv0, dv1, dlm, dnb, dtt, dtv};
   cudaDeviceGetAttribute(&t->sm_count, cudaDevAttrMultiProcessorCount, device);
@@ -624,7 +629,7 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   long long sz[AA_COUNT], g;
   size_t smem;
   const FastPlan fp = plan_fast_adjoint(T);
-  const Fast3Plan f3 = fp.ok ? plan_adjoint3(T, *params) : Fast3Plan{};
+  const Fast3Plan f3 = fp.ok ? plan_adjoint3(T, *params, t->n_cons_units) : Fast3Plan{};
   const MultiCta mc = fp.ok ? MultiCta{0, 1} : pick_multi_cta(T, batch, t->sm_count);
   const int cluster = mc.ncta;
   adjoint_sizes(T, q, sz, cluster);

@@ -186,6 +186,34 @@ __device__ __forceinline__ double angle_of_unit(double sg, double cg) {
   }
   return atan2(sg, cg);
 }
+// sin and cos of a moderate angle (block rotations): quadrant reduction with a two-term pi/2 (the products are exact
+// inside the fma) and the fdlibm kernel polynomials on [-pi/4, pi/4] (< 1 ulp, checked by dfx_math_selftest); the
+// library's sincos spends ~250 instructions on its general range reduction.  |x| >= 1e5 or NaN: library call.
+__device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
+  if (!(fabs(x) < 1.0e5)) { sincos(x, sn, cs); return; }
+  const double q = rint(x * 0.6366197723675814);
+  double r = fma(-q, 1.5707963267948966, x);
+  r = fma(-q, 6.123233995736766e-17, r);
+  const double z = r * r;
+  double ps = 1.58969099521155010221e-10;
+  ps = fma(ps, z, -2.50507602534068634195e-08);
+  ps = fma(ps, z, 2.75573137070700676789e-06);
+  ps = fma(ps, z, -1.98412698298579493134e-04);
+  ps = fma(ps, z, 8.33333333332248946124e-03);
+  ps = fma(ps, z, -1.66666666666666324348e-01);
+  double pc = -1.13596475577881948265e-11;
+  pc = fma(pc, z, 2.08757232129817482790e-09);
+  pc = fma(pc, z, -2.75573143513906633035e-07);
+  pc = fma(pc, z, 2.48015872894767294178e-05);
+  pc = fma(pc, z, -1.38888888888741095749e-03);
+  pc = fma(pc, z, 4.16666666666666019037e-02);
+  const double s = fma(r * z, ps, r);
+  const double c = fma(z * z, pc, fma(-0.5, z, 1.0));
+  const int n = (int)q;
+  const double ss = (n & 1) ? c : s, cc = (n & 1) ? s : c;
+  *sn = (n & 2) ? -ss : ss;
+  *cs = ((n + 1) & 2) ? -cc : cc;
+}
 // 1/sqrt(x) for positive normal x: hardware approximation + two Newton steps
 __device__ __forceinline__ double rsqrt_pos(double x) {
   double r;

@@ -39,7 +39,7 @@ lib.dfx_fp64_peak.restype = C.c_double
 EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free", "dfx_drive_n_params",
            "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
            "dfx_expand_fields", "dfx_objective", "dfx_adjoint_objective",
-           "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp", "dfx_fp64_peak", "dfx_math_selftest", "dfx_last_error", "dfx_version")
+           "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp", "dfx_fp64_peak", "dfx_math_selftest", "dfx_sincos_selftest", "dfx_last_error", "dfx_version")
 
 
 def _check(rc, what):

@@ -685,7 +685,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
     }
     if (has_blk) {
       double sn, cs;
-      sincos(u[2], &sn, &cs);
+      sincos_fast(u[2], &sn, &cs);
       Us[blk] = u[0]; Us[NBS + blk] = u[1]; Us[2 * NBS + blk] = u[2]; Us[3 * NBS + blk] = sn; Us[4 * NBS + blk] = cs;
       Ws[blk] = w[0]; Ws[NBS + blk] = w[1]; Ws[2 * NBS + blk] = w[2];
     }

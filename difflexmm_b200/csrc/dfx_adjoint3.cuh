@@ -271,6 +271,34 @@ __device__ __forceinline__ double scal_total(const double* accb, int m, int whic
   return s;
 }
 
+// the five totals (k1, k7, sol, err, mid) of scalar leaf `which`, computed by one warp: lane l fetches partial l of every
+// array, four shuffle steps add them up; valid in lane 0 (fixed order: deterministic)
+__device__ __forceinline__ void scal_totals_warp(const double* accb, int which, int lane, double (&out)[5]) {
+  int s0 = SLOT_DAMP, n = NDW;
+  if (which >= SC_KS && which <= SC_KR) { s0 = SLOT_K + (which - SC_KS) * 4; n = 4; }
+  else if (which >= SC_CONTACT && which < SC_CONTACT + 3) { s0 = SLOT_K + (3 + which - SC_CONTACT) * 4; n = 4; }
+  else if (which == SC_T0) s0 = SLOT_T;
+  else if (which >= SC_DRIVE) s0 = SLOT_T + (1 + which - SC_DRIVE) * NDW;
+#pragma unroll
+  for (int m = 0; m < 5; ++m) out[m] = lane < n ? accb[m * NSLOT + s0 + lane] : 0.0;
+#pragma unroll
+  for (int o = 8; o > 0; o >>= 1) {
+#pragma unroll
+    for (int m = 0; m < 5; ++m) out[m] += __shfl_xor_sync(0xffffffffu, out[m], o);
+  }
+}
+// ratio^(-1/5) for the step-size controller: float estimate + two Newton steps on y^-5 = r (y <- y (6 - r y^5) / 5), ~1 ulp
+__device__ __forceinline__ double inv_fifth_root(double r) {
+  if (!(r > 1e-30)) return 1e6;  // the controller clamps the factor to 10
+  double y = (double)__powf((float)r, -0.2f);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double y2 = y * y, y5 = y2 * y2 * y;
+    y = y * fma(-r, y5, 6.0) * 0.2;
+  }
+  return y;
+}
+
 // cotangent of ys[design][i][(is_v ? n_free : 0) + f] (see cotangent_nl) with the objective's target index of f known
 // (kf = index + 1, 0 = not a target, 1023 = not cached: look it up)
 static __device__ __noinline__ double cotangent_k_nl(const AdjArgs& a, int design, int i, int f, bool is_v, int kf) {
@@ -765,38 +793,24 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         // t0_bar and the drive parameters only receive contributions from constrained DOFs
 #ifndef ABL_NO_T0
         if (warp_t0 && drive_on) {
-          // the few constrained units of the warp add their terms to the warp's running sums one after the other (fixed
-          // order: no shuffles, no atomics); the first one assigns in the modes that assign
-          double p[6] = {0, 0, 0, 0, 0, 0};
+          // every t0 / drive-parameter integrand is -(A_q S0 + B_q S1) with S_c = sum over the constrained DOFs of
+          // (H w)_dof * drive_vec_c[dof] and (A_q, B_q) the derivatives of the two drive channels: two warp sums serve all leaves
+          double S0 = 0.0, S1 = 0.0;
           if (has_cons) {
-            const double* dr = drv + EV * NDRV;
             const double* cvp = CV + ((flags >> 10) & 63u) * 6;
 #pragma unroll
-            for (int j = 0; j < 3; ++j) {
-              if (is_cons(j)) {
-                const double v0_ = cvp[j], v1_ = cvp[3 + j];
-                p[0] -= HW[j] * (v0_ * dr[2] + v1_ * dr[3]);
-#pragma unroll
-                for (int q = 0; q < DFX_MAX_DRIVE_PARAMS; ++q) p[1 + q] -= HW[j] * (v0_ * dr[4 + q] + v1_ * dr[9 + q]);
-              }
-            }
+            for (int j = 0; j < 3; ++j)
+              if (is_cons(j)) { S0 = fma(HW[j], cvp[j], S0); S1 = fma(HW[j], cvp[3 + j], S1); }
           }
-          unsigned todo = __ballot_sync(0xffffffffu, has_cons);
-          const int first = __ffs(todo) - 1;
-          while (todo) {
-            const int c = __ffs(todo) - 1;
-            todo &= todo - 1;
-            if (lane == c) {
 #pragma unroll
-              for (int q = 0; q < 6; ++q) {
-                if (q <= T.n_drive_params) {
-                  double* k1 = accb + SLOT_T + q * NDW + (warp - NDW);
-                  if (c == first) scal_slot<MODE>(tab, accb, SLOT_T + q * NDW + (warp - NDW), p[q]);
-                  else scal_slot_more<MODE>(tab, k1, p[q]);
-                }
-              }
-            }
-            __syncwarp();
+          for (int o = 16; o > 0; o >>= 1) {
+            S0 += __shfl_xor_sync(0xffffffffu, S0, o);
+            S1 += __shfl_xor_sync(0xffffffffu, S1, o);
+          }
+          if (lane <= T.n_drive_params) {
+            const double* dr = drv + EV * NDRV;
+            const double Aq = lane == 0 ? dr[2] : dr[3 + lane], Bq = lane == 0 ? dr[3] : dr[8 + lane];
+            scal_slot<MODE>(tab, accb, SLOT_T + lane * NDW + (warp - NDW), -(Aq * S0 + Bq * S1));
           }
         }
 #endif
@@ -1132,12 +1146,16 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         }
       }
       __syncthreads();  // scalar running sums of the last stage complete
-      if (tid < NSCAL) {
-        const double q0 = Sq0[tid], k1 = scal_total(accb, 0, tid), k7 = scal_total(accb, 1, tid);
-        const double q1 = q0 + h * scal_total(accb, 2, tid);
-        const double r = h * scal_total(accb, 3, tid) / (atol + rtol * fmax(fabs(q0), fabs(q1)));
-        se += r * r;
-        Sqnew[tid] = crossing ? interp_eval(q0, q1, q0 + h * scal_total(accb, 4, tid), h * k1, h * k7, xq) : q1;
+      if (warp < NSCAL) {  // warp k: scalar leaf k
+        double tot[5];
+        scal_totals_warp(accb, warp, lane, tot);
+        if (lane == 0) {
+          const double q0 = Sq0[warp];
+          const double q1 = q0 + h * tot[2];
+          const double r = h * tot[3] / (atol + rtol * fmax(fabs(q0), fabs(q1)));
+          se += r * r;
+          Sqnew[warp] = crossing ? interp_eval(q0, q1, q0 + h * tot[4], h * tot[0], h * tot[1], xq) : q1;
+        }
       }
       const double ratio = sqrt(block_sum(se, red) * inv_n);
       const long long istep = C->istep + 1;
@@ -1198,12 +1216,12 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
             if (tid < NSLOT) accb[tid] = accb[NSLOT + tid];  // k1 <- k7 of every scalar running sum
           }
           tmem_st_wait();
-          if (tid < NSCAL) Sq0[tid] = Sqnew[tid];
+          if (tid < NSCAL) Sq0[tid] = Sqnew[tid];  // (written above by lane 0 of warp tid; block_sum's barriers are in between)
           par ^= 1;  // q0 <- qnew, k1 <- k7 for every thread-private quadrature
           s_new = s_cur + h;
         }
         const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
-        const double factor = fmin(10.0, fmax(pow(ratio, -0.2) * 0.9, dfactor));
+        const double factor = fmin(10.0, fmax(inv_fifth_root(ratio) * 0.9, dfactor));
         h_new = (ratio == 0.0) ? h * 10.0 : h * factor;
         if (!interval_done) {
           if (!(h_new > 0.0)) { status = DFX_STATUS_DT_UNDERFLOW; stop = true; }

@@ -934,7 +934,18 @@ __global__ void math_selftest_kernel(const double* x, const double* y, double* o
   const double r = rsqrt_pos(x[i] * x[i] + y[i] * y[i]);
   o_angle[i] = angle_of_unit(y[i] * r, x[i] * r);
 }
+__global__ void sincos_selftest_kernel(const double* x, double* o_sin, double* o_cos, int n) {
+  const int i = blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < n) sincos_fast(x[i], &o_sin[i], &o_cos[i]);
+}
 }  // namespace
+
+extern "C" int dfx_sincos_selftest(const double* x, double* o_sin, double* o_cos, int n, void* stream_) {
+  sincos_selftest_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(x, o_sin, o_cos, n);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "sincos_selftest launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
 
 extern "C" int dfx_math_selftest(const double* x, const double* y, double* o_rsqrt, double* o_angle, double* o_rcp, int n, void* stream_) {
   math_selftest_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(x, y, o_rsqrt, o_angle, o_rcp, n);

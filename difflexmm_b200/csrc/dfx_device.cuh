@@ -368,7 +368,7 @@ __device__ __forceinline__ void pulse_eval(double tau, double A, double f, bool 
   if (on) {
     const double ph = 2.0 * kPi * f * tau;
     double sn, cs;
-    sincos(ph, &sn, &cs);
+    sincos_fast(ph, &sn, &cs);
     const double shape = (1.0 - cs) * 0.5;
     s = A * shape;
     if (want_grad) {

@@ -227,7 +227,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
     }
     if (has_blk) {
       double sn, cs;
-      sincos(u[2], &sn, &cs);
+      sincos_fast(u[2], &sn, &cs);
       Us[blk] = u[0]; Us[NBS + blk] = u[1]; Us[2 * NBS + blk] = u[2]; Us[3 * NBS + blk] = sn; Us[4 * NBS + blk] = cs;
     }
     tp.fence_st();

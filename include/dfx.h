@@ -252,6 +252,8 @@ double dfx_fp64_peak(void* stream);
 
 /* test helper: evaluates the device math primitives (1/sqrt(x), angle of the unit vector along (x,y), 1/x) */
 int dfx_math_selftest(const double* x, const double* y, double* out_rsqrt, double* out_angle, double* out_rcp, int n, void* stream);
+/* test helper: the kernels' sin / cos of a block rotation (quadrant reduction + fdlibm kernel polynomials) */
+int dfx_sincos_selftest(const double* x, double* out_sin, double* out_cos, int n, void* stream);
 
 const char* dfx_last_error(void);
 const char* dfx_version(void);

@@ -170,10 +170,13 @@ struct QC {
 // N quadrature entries of one thread receive their integrand values.  `qg` = the thread's column of G_Q, entry e0 + k;
 // running solution / error sums at sol[k * sstride], err[k * sstride] (shared memory for the unit role, scratch for the
 // bond role).  Returns the thread's contribution to the error norm (mode 6) or to d2 of initial_step_size (mode 7).
-template <int MODE, int N>
+// CG: the sums live in the scratch and are also the target of red.global.add (bond role): read / written at L2.
+template <int MODE, int N, bool CG = false>
 __device__ __forceinline__ double quad_entries(const QC& c, const Tableau& tab, double* qg, int e0, double* sol, double* err,
                                                int sstride, const double (&val)[N]) {
   double acc = 0.0;
+  auto ldv = [](const double* p) { return CG ? __ldcg(p) : *p; };
+  auto stv = [](double* p, double v) { if (CG) __stcg(p, v); else *p = v; };
   constexpr int K = MODE >= 1 && MODE <= 6 ? MODE : 0;
   const double cs = tab.c_sol[K], ce = tab.c_err[K], cm = tab.c_mid[K];
   double* q0p = qg + (long long)(c.par * NE3 + e0) * TT;
@@ -185,26 +188,26 @@ __device__ __forceinline__ double quad_entries(const QC& c, const Tableau& tab, 
     for (int k0 = 0; k0 < N; k0 += 4) {  // groups of four: loads in flight together, few live registers
       double s_in[4], e_in[4];
 #pragma unroll
-      for (int k = k0; k < k0 + 4 && k < N; ++k) { s_in[k - k0] = sol[k * sstride]; e_in[k - k0] = err[k * sstride]; }
+      for (int k = k0; k < k0 + 4 && k < N; ++k) { s_in[k - k0] = ldv(&sol[k * sstride]); e_in[k - k0] = ldv(&err[k * sstride]); }
 #pragma unroll
       for (int k = k0; k < k0 + 4 && k < N; ++k) {
-        sol[k * sstride] = fma(cs, val[k], s_in[k - k0]);
-        err[k * sstride] = fma(ce, val[k], e_in[k - k0]);
+        stv(&sol[k * sstride], fma(cs, val[k], s_in[k - k0]));
+        stv(&err[k * sstride], fma(ce, val[k], e_in[k - k0]));
       }
     }
     if (c.crossing) {
 #pragma unroll
-      for (int k = 0; k < N; ++k) k7p[k * TT] = fma(cm, val[k], k7p[k * TT]);
+      for (int k = 0; k < N; ++k) stv(&k7p[k * TT], fma(cm, val[k], ldv(&k7p[k * TT])));
     }
   } else if constexpr (MODE == 2) {
     double k1[N];
 #pragma unroll
-    for (int k = 0; k < N; ++k) k1[k] = k1p[k * TT];
+    for (int k = 0; k < N; ++k) k1[k] = ldv(&k1p[k * TT]);
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      sol[k * sstride] = fma(cs, val[k], tab.c_sol[0] * k1[k]);
-      err[k * sstride] = fma(ce, val[k], tab.c_err[0] * k1[k]);
-      if (c.crossing) k7p[k * TT] = fma(cm, val[k], tab.c_mid[0] * k1[k]);
+      stv(&sol[k * sstride], fma(cs, val[k], tab.c_sol[0] * k1[k]));
+      stv(&err[k * sstride], fma(ce, val[k], tab.c_err[0] * k1[k]));
+      if (c.crossing) stv(&k7p[k * TT], fma(cm, val[k], tab.c_mid[0] * k1[k]));
     }
   } else if constexpr (MODE == 6) {
     double q_in[N];
@@ -212,22 +215,22 @@ __device__ __forceinline__ double quad_entries(const QC& c, const Tableau& tab, 
     for (int k = 0; k < N; ++k) q_in[k] = q0p[k * TT];
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double q1 = fma(c.h, sol[k * sstride], q_in[k]);
-      const double r = c.h * fma(ce, val[k], err[k * sstride]) * rcp_pos(c.atol + c.rtol * fmax(fabs(q_in[k]), fabs(q1)));
+      const double q1 = fma(c.h, ldv(&sol[k * sstride]), q_in[k]);
+      const double r = c.h * fma(ce, val[k], ldv(&err[k * sstride])) * rcp_pos(c.atol + c.rtol * fmax(fabs(q_in[k]), fabs(q1)));
       acc = fma(r, r, acc);
-      if (!c.crossing) { qnp[k * TT] = q1; k7p[k * TT] = val[k]; }
+      if (!c.crossing) { qnp[k * TT] = q1; stv(&k7p[k * TT], val[k]); }
       else {
-        const double amid = fma(cm, val[k], k7p[k * TT]);
-        qnp[k * TT] = interp_eval(q_in[k], q1, q_in[k] + c.h * amid, c.h * k1p[k * TT], c.h * val[k], c.x);
+        const double amid = fma(cm, val[k], ldv(&k7p[k * TT]));
+        qnp[k * TT] = interp_eval(q_in[k], q1, q_in[k] + c.h * amid, c.h * ldv(&k1p[k * TT]), c.h * val[k], c.x);
       }
     }
   } else if constexpr (MODE == 0) {
 #pragma unroll
-    for (int k = 0; k < N; ++k) k1p[k * TT] = val[k];
+    for (int k = 0; k < N; ++k) stv(&k1p[k * TT], val[k]);
   } else if constexpr (MODE == 7) {
 #pragma unroll
     for (int k = 0; k < N; ++k) {
-      const double d = (val[k] - k1p[k * TT]) * rcp_pos(c.atol + fabs(q0p[k * TT]) * c.rtol);
+      const double d = (val[k] - ldv(&k1p[k * TT])) * rcp_pos(c.atol + fabs(q0p[k * TT]) * c.rtol);
       acc = fma(d, d, acc);
     }
   }
@@ -297,6 +300,18 @@ __device__ __forceinline__ double inv_fifth_root(double r) {
     y = y * fma(-r, y5, 6.0) * 0.2;
   }
   return y;
+}
+
+// bond role, the modes that occur once per step or per interval (0, 2, 6, 7); out of line to keep the bond phase lean
+static __device__ __noinline__ double bond_quad_rare_nl(int mode, const QC& c, const Tableau& tab, double* qg, double* bq, double qb0,
+                                                        double qb1) {
+  const double qb[2] = {qb0, qb1};
+  switch (mode) {
+    case 0: return quad_entries<0, 2, true>(c, tab, qg, 10, bq, bq + 2 * TT, TT, qb);
+    case 2: return quad_entries<2, 2, true>(c, tab, qg, 10, bq, bq + 2 * TT, TT, qb);
+    case 6: return quad_entries<6, 2, true>(c, tab, qg, 10, bq, bq + 2 * TT, TT, qb);
+    default: return quad_entries<7, 2, true>(c, tab, qg, 10, bq, bq + 2 * TT, TT, qb);
+  }
 }
 
 // cotangent of ys[design][i][(is_v ? n_free : 0) + f] (see cotangent_nl) with the objective's target index of f known
@@ -608,9 +623,8 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
   };
 
   // ---- phase C: gather the bond slots of this thread's half of its unit, stage derivatives, quadratures -----------
-  // (qb0, qb1: integrands of the reference-vector quadratures of this thread's bond, from phase B.)  Returns the
-  // thread's contribution to the error norm (last stage) or to d2 of initial_step_size (probe).
-  auto phaseC = [&](auto tag, const double* Wcur, double qb0, double qb1) -> double {
+  // Returns the thread's contribution to the error norm (last stage) or to d2 of initial_step_size (probe).
+  auto phaseC = [&](auto tag, const double* Wcur) -> double {
     constexpr int EV = decltype(tag)::value;
     constexpr int KIDX = Ev<EV>::kidx, MODE = Ev<EV>::mode;
 #ifdef ABL_NO_Q
@@ -618,7 +632,6 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 #else
     constexpr bool WANT_Q = MODE != 1;
 #endif
-    constexpr bool HOT = MODE >= 3 && MODE <= 5;
     double accq = 0.0;
     QC qc;
     qc.par = C->par; qc.crossing = C->crossing != 0; qc.h = C->hst; qc.x = C->x; qc.atol = a.atol; qc.rtol = a.rtol;
@@ -632,14 +645,6 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       nbp[0] = lo; nbp[1] = hi;
     }
     auto nbq = [&](int l) { const int f = (int)((nbp[l >> 1] >> ((l & 1) * 16)) & 0xffffu); return f == 0xffff ? -1 : f; };
-    // bond role: running sums of the reference-vector quadratures live in L2: fetched now, committed at the end
-    double bq_in[4];
-#ifndef ABL_NO_BQ
-    if (HOT && has_bnd) {
-#pragma unroll
-      for (int k = 0; k < 4; ++k) bq_in[k] = gcol[G_BQ + (long long)k * TT];
-    }
-#endif
     const bool seen = CONTACT && C->contact_seen;
     if (!isD) {
       // dense scalar leaves: P warp w sums the partials of bonds [192 q, 192 q + 192), q = w / 3, of leaf w % 3 (and of
@@ -816,23 +821,6 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 #endif
       }
     }
-#ifndef ABL_NO_BQ
-    if (WANT_Q && has_bnd) {
-      if constexpr (HOT) {
-        const double cs = tab.c_sol[MODE], ce = tab.c_err[MODE];
-        gcol[G_BQ] = fma(cs, qb0, bq_in[0]); gcol[G_BQ + TT] = fma(cs, qb1, bq_in[1]);
-        gcol[G_BQ + 2 * TT] = fma(ce, qb0, bq_in[2]); gcol[G_BQ + 3 * TT] = fma(ce, qb1, bq_in[3]);
-        if (qc.crossing) {
-          const double cm = tab.c_mid[MODE];
-          double* k7p = qg + (long long)((3 - qc.par) * NE3 + 10) * TT;
-          k7p[0] = fma(cm, qb0, k7p[0]); k7p[TT] = fma(cm, qb1, k7p[TT]);
-        }
-      } else {
-        const double qb[2] = {qb0, qb1};
-        accq += quad_entries<MODE, 2>(qc, tab, qg, 10, gcol + G_BQ, gcol + G_BQ + 2 * TT, TT, qb);
-      }
-    }
-#endif
     tmem_st_wait();
     return accq;
   };
@@ -871,7 +859,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     PT_MARK(1);
 
     // ================= phase B: this thread's bond (one copy of the code for every kind of evaluation) =================
-    double qb0 = 0.0, qb1 = 0.0;  // integrands of the two reference-vector quadratures of this thread's bond
+    double accq = 0.0;  // this thread's contribution to the error norm / probe norm
     if (has_bnd) {
       const bool want_q = ev != 0;  // the second stage of a step has zero weight in every combination
       const int b1 = bbp & 0xffff, b2 = bbp >> 16;
@@ -939,8 +927,29 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         // parameter cotangent integrands: -(dual part of dE/dp)
         gks_d = ext.v * ext.d; gksh_d = gam.v * gam.d * L0sq; gkr_d = dth.v * dth.d;
         Dual dE_dL0 = gam * gam * (ksh * L0) - ext * ks;
-        qb0 = -(gdx.d + dE_dL0.d * (r0x * iL0) + M.d * (r0y / L0sq));
-        qb1 = -(gdy.d + dE_dL0.d * (r0y * iL0) - M.d * (r0x / L0sq));
+#ifndef ABL_NO_BQ
+        if (want_q) {
+          // reference-vector quadratures of this bond (running sums in L2, thread private): the accumulating stages add
+          // their terms with fire-and-forget reductions at L2 -- no load, no latency, nothing carried into phase C
+          const double qb0 = -(gdx.d + dE_dL0.d * (r0x * iL0) + M.d * (r0y / L0sq));
+          const double qb1 = -(gdy.d + dE_dL0.d * (r0y * iL0) - M.d * (r0x / L0sq));
+          double* bq = gcol + G_BQ;
+          if (ev >= 2 && ev <= 4) {
+            const double cs = tab.c_sol[ev + 1], ce = tab.c_err[ev + 1];
+            atomicAdd(bq, cs * qb0); atomicAdd(bq + TT, cs * qb1);
+            atomicAdd(bq + 2 * TT, ce * qb0); atomicAdd(bq + 3 * TT, ce * qb1);
+            if (C->crossing) {
+              const double cm = tab.c_mid[ev + 1];
+              double* k7p = qg + (long long)((3 - C->par) * NE3 + 10) * TT;
+              atomicAdd(k7p, cm * qb0); atomicAdd(k7p + TT, cm * qb1);
+            }
+          } else {
+            QC qc;
+            qc.par = C->par; qc.crossing = C->crossing != 0; qc.h = C->hst; qc.x = C->x; qc.atol = a.atol; qc.rtol = a.rtol;
+            accq = bond_quad_rare_nl(ev == EV_INIT ? 0 : (ev == EV_PROBE ? 7 : ev + 1), qc, tab, qg, bq, qb0, qb1);
+          }
+        }
+#endif
       }
       asm volatile("" ::: "memory");  // the block rotations are re-read below instead of being carried in registers
       {
@@ -965,8 +974,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     __syncthreads();
     PT_MARK(3);
 
-    double accq = 0.0;  // this thread's contribution to the error norm / probe norm
-#define DFX_A3_C(TAG) accq = phaseC(TAG, Wcur, qb0, qb1)
+#define DFX_A3_C(TAG) accq += phaseC(TAG, Wcur)
     DFX_A3_DISPATCH(DFX_A3_C)
 #undef DFX_A3_C
     PT_MARK(4);
@@ -1017,7 +1025,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       // initial_step_size over the whole augmented vector
 #pragma unroll 1
       for (int e = 0; e < NE3; ++e) {
-        const double q0 = qg[(long long)(par * NE3 + e) * TT], k1 = qg[(long long)((2 + par) * NE3 + e) * TT];
+        const double q0 = __ldcg(&qg[(long long)(par * NE3 + e) * TT]), k1 = __ldcg(&qg[(long long)((2 + par) * NE3 + e) * TT]);
         const double s = atol + fabs(q0) * rtol;
         sd0 += (q0 / s) * (q0 / s); sd1 += (k1 / s) * (k1 / s);
       }
@@ -1262,7 +1270,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
   {
     double qv[NE3];
 #pragma unroll
-    for (int e = 0; e < NE3; ++e) qv[e] = bad ? nanv : qg[(long long)(par * NE3 + e) * TT];
+    for (int e = 0; e < NE3; ++e) qv[e] = bad ? nanv : __ldcg(&qg[(long long)(par * NE3 + e) * TT]);
     if (!isD) {
 #pragma unroll
       for (int j = 0; j < 3; ++j) {

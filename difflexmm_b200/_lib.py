@@ -35,11 +35,12 @@ lib.dfx_version.restype = C.c_char_p
 lib.dfx_forward_workspace_bytes.restype = C.c_size_t
 lib.dfx_adjoint_workspace_bytes.restype = C.c_size_t
 lib.dfx_fp64_peak.restype = C.c_double
+lib.dfx_adjoint_plan.restype = C.c_char_p
 
 EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free", "dfx_drive_n_params",
            "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
            "dfx_expand_fields", "dfx_objective", "dfx_adjoint_objective",
-           "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp", "dfx_fp64_peak", "dfx_math_selftest", "dfx_sincos_selftest", "dfx_last_error", "dfx_version")
+           "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp", "dfx_fp64_peak", "dfx_math_selftest", "dfx_sincos_selftest", "dfx_adjoint_plan", "dfx_last_error", "dfx_version")
 
 
 def _check(rc, what):
@@ -141,6 +142,12 @@ def forward(topo: Topology, ps: _abi.ParamSet, y0, ts, rtol, atol, options: _abi
                                C.c_void_p(ys.data_ptr()), C.c_void_p(stats.data_ptr()),
                                C.c_void_p(ws.data_ptr()), C.c_size_t(ws_bytes), _stream_ptr(dev)), "dfx_forward")
     return ys, _Stats(stats)
+
+
+def adjoint_plan(topo: Topology, ps: _abi.ParamSet) -> str:
+    """name of the adjoint kernel the library launches for this topology / these leaf forms / this batch (diagnostic)"""
+    p = ps.to_struct()
+    return lib.dfx_adjoint_plan(topo._h, C.byref(p), ps.batch).decode()
 
 
 def adjoint(topo: Topology, ps: _abi.ParamSet, ys, ts, g, rtol, atol, aug_size, options: _abi.DfxOptions):

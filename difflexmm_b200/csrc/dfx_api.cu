@@ -940,6 +940,22 @@ __global__ void sincos_selftest_kernel(const double* x, double* o_sin, double* o
 }
 }  // namespace
 
+/* which adjoint kernel dfx_adjoint / dfx_adjoint_objective would launch for this topology, these leaf forms and this batch
+ * (diagnostic: tests and bench.py report it).  The string lives in thread-local storage until the next call. */
+extern "C" const char* dfx_adjoint_plan(const DfxTopology* t, const DfxParams* params, int batch) {
+  static thread_local char buf[96];
+  if (!t || !params) return "invalid";
+  const FastPlan fp = plan_fast_adjoint(t->dev);
+  const Fast3Plan f3 = fp.ok ? plan_adjoint3(t->dev, *params, t->n_cons_units) : Fast3Plan{};
+  if (f3.ok) std::snprintf(buf, sizeof(buf), "adjoint3_kernel<%d,%d,%d> 768 threads", f3.npb, (int)f3.contact, f3.damp);
+  else if (fp.ok) std::snprintf(buf, sizeof(buf), "adjoint2_kernel<%d,%d,%d>", fp.nt, fp.nt == 84 && fp.ns == 32 ? 32 : -1, fp.threads);
+  else {
+    const MultiCta mc = pick_multi_cta(t->dev, batch, t->sm_count);
+    std::snprintf(buf, sizeof(buf), "adjoint_kernel<%d> %d CTA(s) per design", mc.mode == 2 ? 2 : (mc.ncta > 1 ? 1 : 0), mc.ncta);
+  }
+  return buf;
+}
+
 extern "C" int dfx_sincos_selftest(const double* x, double* o_sin, double* o_cos, int n, void* stream_) {
   sincos_selftest_kernel<<<(n + 255) / 256, 256, 0, (cudaStream_t)stream_>>>(x, o_sin, o_cos, n);
   cudaError_t e = cudaGetLastError();

@@ -247,6 +247,10 @@ int dfx_expand_fields(const DfxTopology* topo, const DfxParams* params, int batc
                       const double* ys, const double* ts, int64_t ts_bstride, int n_t,
                       double* fields, void* stream);
 
+/* diagnostic: name of the adjoint kernel that dfx_adjoint / dfx_adjoint_objective would launch for this topology, these
+ * leaf forms and this batch size (thread-local string, valid until the next call) */
+const char* dfx_adjoint_plan(const DfxTopology* topology, const DfxParams* params, int batch);
+
 /* measurement helper: FP64 FMA throughput of the current device in TFLOP/s (roofline denominator) */
 double dfx_fp64_peak(void* stream);
 

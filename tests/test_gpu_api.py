@@ -223,7 +223,12 @@ def test_tabulated_drive_matches_oracle():
     y0b, tsb, gr, sb = _lib.adjoint(topo, ps, torch.as_tensor(ys_h, device="cuda"), ts.cuda(), torch.as_tensor(g, device="cuda"),
                                     P.rtol, P.atol, 0, opt)
     assert sb.numpy()["status"][0] == 0
-    assert rel_l2(tsb[0].cpu().numpy(), tsb_h[0]) <= 1e-5
+    # ts_bar[1:] are the t_bar terms of the interval starts; ts_bar[0] = t0_bar is the quadrature of an integrand that
+    # jumps at every knot of the table (d drive / dt is piecewise constant), so it is only first-order accurate in the
+    # step size and moves with the accept / reject sequence: it is compared on the scale of the vector
+    tsb_d = tsb[0].cpu().numpy()
+    assert rel_l2(tsb_d[1:], tsb_h[0][1:]) <= 1e-5
+    assert abs(tsb_d[0] - tsb_h[0][0]) <= 1e-4 * np.abs(tsb_h[0]).max()
     for k in gr_h:
         if np.abs(gr_h[k]).max() > 1e-9:
             assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= 1e-5, k

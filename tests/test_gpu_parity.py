@@ -72,10 +72,11 @@ def test_forward_matches_golden(name, forward_kernel_mode):
     assert abs(int(st["steps"]) - int(c.ref["fwd_steps"])) <= max(2, int(0.01 * c.ref["fwd_steps"]))
 
 
-@pytest.fixture(params=["fast_tmem", "notmem", "generic", "cluster4", "cluster16", "group40"])
+@pytest.fixture(params=["fast_tmem", "v2", "notmem", "generic", "cluster4", "cluster16", "group40"])
 def adjoint_kernel_mode(request, monkeypatch):
-    """the adjoint code paths of libdfx: fast kernel with TMEM-resident stage history (default), fast kernel
-    without TMEM, generic kernel (any lattice size), generic kernel over a thread-block cluster"""
+    """the adjoint code paths of libdfx: the default choice (the 24-warp kernel adjoint3 where the lattice and the leaf
+    forms allow it, else the 12-warp kernel adjoint2, both with TMEM-resident stage history), adjoint2 forced ("v2"),
+    adjoint2 without TMEM, generic kernel (any lattice size), generic kernel over a thread-block cluster / group"""
     return _kernel_mode(monkeypatch, "DFX_ADJOINT_KERNEL", request.param)
 
 
@@ -103,6 +104,41 @@ def test_adjoint_matches_golden(name, adjoint_kernel_mode):
             assert rel_l2(got, c.ref[key]) <= GRAD_TOL, k
         else:
             assert np.abs(got - c.ref[key]).max() <= 1e-9, k
+
+
+def test_default_adjoint_kernel_choice(monkeypatch):
+    """the goldens with the common vocabulary (ligament energy, scalar stiffnesses, no external load) run the 24-warp
+    kernel by default; per-bond stiffnesses, loads and the other energies stay on adjoint2 / the generic kernel"""
+    monkeypatch.delenv("DFX_ADJOINT_KERNEL", raising=False)
+    seen = {}
+    for name in golden_names():
+        c = load_golden(name)
+        lib, topo = _solver(c.spec)
+        seen[name] = lib.adjoint_plan(topo, _dev_params(c))
+    assert seen["quads_4x3_contact_active"].startswith("adjoint3_kernel<4,1,"), seen
+    assert seen["quads_5x4_tight"].startswith("adjoint3_kernel<4,"), seen
+    assert seen["kagome_3x2_perbond"].startswith("adjoint2_kernel"), seen
+    assert seen["springs_4x3"].startswith("adjoint_kernel"), seen
+    monkeypatch.setenv("DFX_ADJOINT_KERNEL", "v2")
+    c = load_golden("quads_4x3_contact_active")
+    lib, topo = _solver(c.spec)
+    assert lib.adjoint_plan(topo, _dev_params(c)).startswith("adjoint2_kernel")
+
+
+def test_sincos_fast_matches_numpy():
+    """the kernels' sin / cos of a block rotation: < 2 ulp against numpy over several quadrants, library fallback beyond"""
+    import ctypes as C
+    from difflexmm_b200 import _lib
+    rng = np.random.default_rng(3)
+    x = np.concatenate([rng.uniform(-0.8, 0.8, 4000), rng.uniform(-40, 40, 4000), rng.uniform(-1e5, 1e5, 2000),
+                        np.array([0.0, -0.0, np.pi / 4, -np.pi / 4, np.pi / 2, np.pi, 3e7, -5e9])])
+    xs = torch.as_tensor(x, device="cuda")
+    o_s, o_c = torch.empty_like(xs), torch.empty_like(xs)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    assert _lib.lib.dfx_sincos_selftest(C.c_void_p(xs.data_ptr()), C.c_void_p(o_s.data_ptr()), C.c_void_p(o_c.data_ptr()),
+                                        len(x), stream) == 0
+    assert np.max(np.abs(o_s.cpu().numpy() - np.sin(x))) < 4.5e-16
+    assert np.max(np.abs(o_c.cpu().numpy() - np.cos(x))) < 4.5e-16
 
 
 @pytest.fixture(params=["default", "cluster4", "group40"])
@@ -473,3 +509,107 @@ def test_bench_workload_members_match_cpp_oracle():
                 gbest = min(rel_l2(got, a[k][b]) for a in alts_g)
                 assert gbest <= GRAD_TOL or rel_l2(got, gr_h[k][b]) <= 2 * gspread, (k, b, gbest, gspread)
     assert n_tight >= 1  # at least one member is well conditioned and meets the north-star tolerance outright
+
+
+def _variant_case(lattice, contact, damping, drive, seed):
+    """small lattice with scalar stiffness leaves and no external load (the vocabulary of the 24-warp adjoint kernel);
+    lattice: "quads" | "kagome"; damping: None | "scalar" | "per_dof"; drive: None | "pulse" | "harmonic" | "static_pulse" """
+    from difflexmm_b200.geometry import DOFsInfo, KagomeGeometry, QuadGeometry, compute_inertia
+    rng = np.random.default_rng(seed)
+    torch.manual_seed(seed)
+    if lattice == "quads":
+        n1, n2 = 5, 4
+        geo = QuadGeometry(n1, n2, spacing=15.0, bond_length=2.25)
+        bc, cnvf, bonds, refv = geo.get_parametrization()
+        hs, vs = geo.get_design_from_rotated_square(25 * math.pi / 180)
+        cnv = cnvf(hs + 0.4 * torch.randn_like(hs), vs + 0.4 * torch.randn_like(vs))
+        npb, drv_blk, corner = 4, (n2 // 2) * n1, n1 - 1
+    else:
+        n1, n2 = 4, 3
+        geo = KagomeGeometry(n1, n2, direct_basis=20.0 * np.array([[1.0, 0.0], [math.cos(math.pi / 3), math.sin(math.pi / 3)]]),
+                             bond_length=2.25)
+        bc, cnvf, bonds, refv = geo.get_parametrization()
+        F64 = torch.float64
+        cnv = cnvf(0.4 * torch.randn(n1 + 1, n2, 2, dtype=F64), 0.4 * torch.randn(n1, n2 + 1, 2, dtype=F64),
+                   0.4 * torch.randn(n1, n2, 2, dtype=F64))
+        npb, drv_blk, corner = 3, 2 * n1 * (n2 // 2), 2 * n1 - 1
+    nb_ = geo.n_blocks
+    kw, leaves = {}, {}
+    if drive is not None:
+        pairs = np.array([[drv_blk, 0], [drv_blk, 1], [drv_blk, 2], [0, 0], [0, 1], [0, 2], [corner, 0], [corner, 1], [corner, 2]])
+        cons = pairs[:, 0] * 3 + pairs[:, 1]
+        free, _, _ = DOFsInfo(nb_, pairs)
+        v0 = np.zeros(len(cons)); v0[0] = 1.0
+        kind = {"pulse": _abi.DFX_DRIVE_PULSE, "harmonic": _abi.DFX_DRIVE_HARMONIC, "static_pulse": _abi.DFX_DRIVE_STATIC_PULSE}[drive]
+        kw = dict(constrained_dofs=cons, drive_kind=kind, drive_vec0=v0)
+        if drive == "static_pulse":
+            v1 = np.zeros(len(cons)); v1[4] = -1.0; v1[7] = 1.0   # the two corner blocks are pushed towards each other in y
+            kw["drive_vec1"] = v1
+            leaves["drive"] = np.array([6.0, 40.0, 0.02, 8.0, 0.0005])  # amplitude, rate, strain, strain rate, delay
+        else:
+            leaves["drive"] = np.array([6.0, 40.0, 0.002])
+    else:
+        free = np.arange(3 * nb_)
+    if damping is not None:
+        kw["damped_blocks"] = np.arange(nb_)
+    spec = _abi.TopologySpec(nb_, npb, bonds(), contact=contact, **kw)
+    rho = 6.18e-9
+    leaves.update(centroid_node_vectors=cnv.numpy(), reference_vector=refv().numpy(), k_stretch=np.array(120.0),
+                  k_shear=np.array(1.19), k_rot=np.array(1.5), inertia=compute_inertia(cnv, rho).reshape(-1).numpy()[free])
+    if damping == "scalar":
+        leaves["damping"] = np.array(2.0e-5)
+    elif damping == "per_dof":
+        leaves["damping"] = 2.0e-5 * (1 + rng.random((nb_, 3)))
+    if contact:  # a window that the driven lattice really enters
+        leaves["contact"] = np.array([20 * math.pi / 180, 38 * math.pi / 180, 1.5]) if lattice == "quads" else \
+            np.array([95 * math.pi / 180, 112 * math.pi / 180, 1.5])  # (rest void angles of this kagome lattice: 110..131 degrees)
+    nf = spec.n_free
+    y0 = np.concatenate([0.05 * rng.standard_normal(nf), 20.0 * rng.standard_normal(nf)])
+    return spec, leaves, damping == "per_dof", y0
+
+
+@pytest.mark.parametrize("lattice,contact,damping,drive,expect", [
+    ("quads", False, None, None, "adjoint3_kernel<4,0,0>"),
+    ("quads", True, "scalar", "harmonic", "adjoint3_kernel<4,1,1>"),
+    ("quads", False, "per_dof", "static_pulse", "adjoint3_kernel<4,0,2>"),
+    ("quads", True, None, "pulse", "adjoint3_kernel<4,1,0>"),
+    ("kagome", True, "per_dof", "pulse", "adjoint3_kernel<3,1,2>"),
+    ("kagome", False, "scalar", "harmonic", "adjoint3_kernel<3,0,1>"),
+    ("kagome", True, None, None, "adjoint3_kernel<3,1,0>"),
+])
+def test_adjoint3_instances_match_cpp_oracle(lattice, contact, damping, drive, expect, monkeypatch):
+    """every compiled instance family of the 24-warp adjoint kernel (nodes per block, contact, damping leaf form) with the
+    drive kinds it meets, against the C++ oracle and against the 12-warp kernel on the same inputs"""
+    from oracle import Oracle
+    monkeypatch.delenv("DFX_ADJOINT_KERNEL", raising=False)
+    spec, leaves, dpd, y0 = _variant_case(lattice, contact, damping, drive, seed=11)
+    ts = np.linspace(0.0, 0.006, 5)
+    # tight tolerances: with contact this active, a 1e-15 perturbation moves the oracle's own contact gradient by 5e-5 at
+    # rtol 1e-8 (accept / reject decisions flip) but only by 5e-7 at 1e-10, where the step sequence stops mattering
+    rtol, atol = 1e-10, 1e-10
+    orc = Oracle(spec)
+    ph = orc.params(1, leaves, (), dpd)
+    ys_h, st_h = orc.forward(ph, y0, ts, rtol, atol)
+    g = np.cos(ys_h) + 0.2
+    y0b_h, tsb_h, gr_h, sb_h = orc.adjoint(ph, ys_h, ts, g, rtol, atol)
+    if contact:
+        assert np.abs(gr_h["contact"]).max() > 0  # the contact window is entered
+    lib, topo = _solver(spec)
+    dl = {k: torch.as_tensor(np.asarray(v), dtype=torch.float64, device="cuda").contiguous() for k, v in leaves.items()}
+    ps = _abi.ParamSet(spec, 1, dl, (), dpd)
+    assert lib.adjoint_plan(topo, ps).startswith(expect)
+    args = (topo, ps, torch.as_tensor(ys_h, device="cuda"), torch.as_tensor(ts, device="cuda"), torch.as_tensor(g, device="cuda"),
+            rtol, atol, 0, _abi.DfxOptions(0, 0, 0))
+    y0b, tsb, gr, sb = lib.adjoint(*args)
+    assert sb.numpy()["status"][0] == 0
+    assert abs(int(sb.numpy()["steps"][0]) - int(sb_h["steps"][0])) <= max(2, 0.03 * sb_h["steps"][0])
+    assert rel_l2(y0b[0].cpu().numpy(), y0b_h[0]) <= GRAD_TOL and rel_l2(tsb[0].cpu().numpy(), tsb_h[0]) <= GRAD_TOL
+    assert set(gr) == set(gr_h)
+    for k in gr_h:
+        if np.abs(gr_h[k]).max() > 1e-9:
+            assert rel_l2(gr[k][0].cpu().numpy(), gr_h[k][0]) <= GRAD_TOL, k
+    monkeypatch.setenv("DFX_ADJOINT_KERNEL", "v2")
+    y0b2, tsb2, gr2, sb2 = lib.adjoint(*args)
+    for k in gr_h:
+        if np.abs(gr_h[k]).max() > 1e-9:
+            assert rel_l2(gr[k][0].cpu().numpy(), gr2[k][0].cpu().numpy()) <= GRAD_TOL, k

@@ -4,15 +4,18 @@
 Workload (config.workload): cfg3 of BASELINE.json, the quads_focusing random-initial-guess ensemble
 (24x16 quads, contact, pulse drive, n_t=200, rtol 1e-8 / atol 1e-4; designs = initial design +
 U(-1,1)*0.15*spacing, one numpy PRNG stream per design).  One "step" = one forward solve + one
-adjoint solve (objective: target kinetic energy) of every design of the rank's batch.  Each rank
-holds `--designs` designs (default 1024, the whole ensemble of the north star on one GPU); ranks
-are independent (no data-path collective), so N GPUs process N*designs per step: weak scaling.
+adjoint solve (objective: target kinetic energy) of every design of the ensemble.  The ensemble of
+`--designs` designs (default 1024, BASELINE.json configs[2]) is SHARDED over the ranks
+(`parallel.shard_range`: contiguous slices, no data-path collective): strong scaling, the stated
+configuration.  `--designs-per-gpu D` instead gives every rank D designs of its own (weak scaling).
 
   value      designs/s with all inputs resident in HBM (forward kernel + objective cotangent + adjoint kernel)
   e2e        the same through the public API (DynamicSolver.odeint + torch.autograd) with the per-design leaves
              copied host->device from pinned memory and objective values + gradients read back, every step
   roofline   adjoint kernel: algorithmic FP64 flops (convention W, with the step counts
-             the kernel reports) / CUDA-event duration, against the FP64-FMA peak measured in this run
+             the kernel reports) / CUDA-event duration, against the FP64-FMA peak measured in this run;
+             frac_executed rescales it to the DFMA/DADD/DMUL instructions the kernel really executes (ratio
+             from the committed ncu counters, profiles/r02_fp64_instruction_counts.json)
   cpu_baseline  the C++ CPU oracle (a port of the reference algorithm, NOT the reference) on the host cores
 
 `--impl reference` times the CPU implementation of the path (oracle port: JAX is not installable in
@@ -118,9 +121,12 @@ def target_free_index(prob, spec):
 
 def run_cpu(args, rank_out=True):
     """CPU implementation of the path (C++ oracle port of the reference algorithm), all host cores."""
+    import oracle
     from oracle import Oracle
+    fast = oracle.use_fast_build(True)  # -O3 -march=x86-64-v3 (AVX2 + FMA) when the host has them, else the -O2 checker build
     cores = os.cpu_count() or 1
-    n = args.cpu_designs if args.cpu_designs > 0 else 2 * max(cores, 1)  # two per host thread: about 10 s of CPU work per step
+    # at least 64 designs, two per host thread: 10-25 s of CPU work per step
+    n = args.cpu_designs if args.cpu_designs > 0 else max(64, 2 * max(cores, 1))
     prob, spec, drive, leaves, pb, dpd, aug, y0, ts = build_problem(n, seed0=0)
     orc = Oracle(spec)
     lv = {k: v.numpy() for k, v in leaves.items()}
@@ -133,6 +139,7 @@ def run_cpu(args, rank_out=True):
         g = np.zeros_like(ys)
         g[:, :, nf + tidx] = ys[:, :, nf + tidx] * lv["inertia"][:, None, tidx]
         orc.adjoint(ps, ys, ts.numpy(), g, prob.rtol, prob.atol, aug, n_threads=cores)
+    step.build = "g++ -O3 -march=x86-64-v3 (AVX2, FMA)" if fast else "g++ -O2"
     return step, n, cores
 
 
@@ -142,7 +149,8 @@ def main():
     ap.add_argument("--steps", type=int, default=3)
     ap.add_argument("--warmup", type=int, default=3)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
-    ap.add_argument("--designs", type=int, default=1024, help="designs per GPU per step")
+    ap.add_argument("--designs", type=int, default=1024, help="designs of the ensemble, sharded over the ranks (strong scaling)")
+    ap.add_argument("--designs-per-gpu", type=int, default=0, help="weak scaling instead: this many designs on every rank")
     ap.add_argument("--cpu-designs", type=int, default=0,
                     help="designs per step of the CPU legs (default: two per host thread)")
     ap.add_argument("--no-cpu-baseline", action="store_true")
@@ -156,9 +164,14 @@ def main():
     world = int(os.environ.get("WORLD_SIZE", "1"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
 
+    weak = args.designs_per_gpu > 0
+    total = args.designs_per_gpu * world if weak else args.designs
+    from difflexmm_b200.parallel import shard_range
+    lo, hi = shard_range(total, rank, world)
     config = {"workload": "quads_focusing 24x16 random-initial-guess ensemble (cfg3): forward + adjoint per design, "
                           "n_t=200, rtol=1e-8, atol=1e-4, contact on, noise 0.15*spacing",
-              "designs_per_gpu": args.designs, "parallelism": f"designs sharded over {world} rank(s), no collective",
+              "designs_total": total, "designs_per_gpu": [shard_range(total, r, world)[1] - shard_range(total, r, world)[0] for r in range(world)],
+              "parallelism": f"the {total}-design ensemble sharded over {world} rank(s) (contiguous slices), no collective",
               "l2": "inputs larger than L2 (trajectory ys = 3.5 MB per design, x designs_per_gpu)",
               "objective": "target kinetic energy evaluated on the device, cotangent formed inside the adjoint kernel"}
     if args.horizon_scale != 1.0:
@@ -168,17 +181,17 @@ def main():
         if rank != 0:
             return
         step, n, cores = run_cpu(args)
-        for _ in range(min(args.warmup, 1)):  # the CPU path has no warm-up effects worth 3 x 15 s
+        for _ in range(min(args.warmup, 1)):  # the CPU path has no warm-up effects worth 3 x 20 s
             step()
         t0 = time.perf_counter()
         for _ in range(args.steps):
             step()
         dt = (time.perf_counter() - t0) / args.steps
         val = n / dt
-        sample = f"{n} designs of the same ensemble per step on {cores} host threads"
+        sample = f"{n} designs of the same ensemble per step on {cores} host threads, C++ port of the reference algorithm ({step.build})"
         print(json.dumps({"impl": "reference", "metric": METRIC, "value": val, "unit": UNIT, "n_gpus": args.gpus,
                           "steps": args.steps, "warmup": min(args.warmup, 1), "ms_per_step": dt * 1e3, "higher_is_better": True,
-                          "scaling": "weak", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
+                          "scaling": "weak" if weak else "strong", "vs_baseline": None, "dtype": "f64", "data": "synthetic", "config": config,
                           "cpu_baseline": {"value": val, "unit": UNIT, "cores": cores, "kind": "port", "sample": sample},
                           "e2e": {"value": val, "unit": UNIT, "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
         return
@@ -192,8 +205,8 @@ def main():
     dev = torch.device("cuda", local_rank)
     if world > 1:
         dist.init_process_group("nccl", device_id=dev)
-    B = args.designs
-    prob, spec, drive, leaves_h, pb, dpd, aug, y0_h, ts_h = build_problem(B, seed0=rank * B)
+    B = hi - lo
+    prob, spec, drive, leaves_h, pb, dpd, aug, y0_h, ts_h = build_problem(B, seed0=lo)
     solver = DynamicSolver(spec, drive, prob.rtol, prob.atol, dev)
     lib = solver._lib
     nf = spec.n_free
@@ -206,6 +219,7 @@ def main():
     leaves_d = {k: v.to(dev) for k, v in leaves_pinned.items()}
     y0, ts = y0_h.to(dev), ts_h.to(dev)
     ps = _abi.ParamSet(spec, B, leaves_d, pb, dpd)
+    config["adjoint_kernel"] = lib.adjoint_plan(solver.handle, ps)
 
     ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
     kernel_ms = {"forward": [], "adjoint": []}
@@ -250,7 +264,7 @@ def main():
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
     ms_per_step = t.item() / args.steps
-    value = world * B / (ms_per_step * 1e-3)
+    value = total / (ms_per_step * 1e-3)
 
     st_f, st_b = last["st_f"].numpy(), last["st_b"].numpy()
     bad = int((st_f["status"] != 0).sum() + (st_b["status"] != 0).sum())
@@ -284,7 +298,7 @@ def main():
         for _ in range(max(1, min(args.warmup, 2))):  # the first calls grow the allocator pools
             e2e_step()
         barrier()
-        n_e2e = max(1, min(args.steps, 3))
+        n_e2e = args.steps
         e2e_step_ms = []
         with ClockSampler(local_rank) as e2e_clocks:
             t0 = time.perf_counter()
@@ -296,8 +310,13 @@ def main():
             te = torch.tensor([(time.perf_counter() - t0) / n_e2e], dtype=torch.float64, device=dev)
         if world > 1:
             dist.all_reduce(te, op=dist.ReduceOp.MAX)
-        e2e = {"value": world * B / te.item(), "unit": UNIT, "h2d_bytes_per_step": world * h2d, "d2h_bytes_per_step": world * d2h,
-               "step_ms": e2e_step_ms, "clocks": e2e_clocks.summary()}
+        bytes_t = torch.tensor([h2d, d2h], dtype=torch.float64, device=dev)
+        if world > 1:
+            dist.all_reduce(bytes_t)
+        e2e = {"value": total / te.item(), "unit": UNIT, "h2d_bytes_per_step": int(bytes_t[0].item()),
+               "d2h_bytes_per_step": int(bytes_t[1].item()), "steps": n_e2e,
+               "step_ms_median": float(np.median(e2e_step_ms)), "step_ms_max": float(np.max(e2e_step_ms)),
+               "step_ms": [round(x, 1) for x in e2e_step_ms], "clocks": e2e_clocks.summary()}
 
     if rank != 0:
         if world > 1:
@@ -317,12 +336,21 @@ def main():
     if not peak:
         peak = 148 * 64 * 2 * (cl["sm_max_mhz"] or 1965.0) * 1e6 / 1e12
     achieved = flops_adj / (adj_ms * 1e-3) / 1e12
-    roofline = {"kernel": "adjoint_kernel", "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
-                "frac": achieved / peak,
-                # DRAM bytes of ONE 1024-design adjoint launch from the `ncu --set full` capture of round 1
-                # (dram__bytes_read.sum 26 GB + dram__bytes_write.sum 332 GB: L2 write-backs of the quadrature scratch,
-                # see DESIGN.md section 4); scaled to this launch's design count; the bound of this kernel is FP64 issue
-                "traffic": 358e9 * B / 1024.0, "traffic_unit": "bytes/launch (ncu, round 1)", "peak_source": peak_src,
+    # executed DFMA (x2) + DADD + DMUL per algorithmic flop of the same launch, from the committed ncu counters of this
+    # build's adjoint kernel (tools/fp64_counts.py); None when the file is missing
+    exe_ratio, traffic_note = None, None
+    try:
+        with open(os.path.join(ROOT, "profiles", "r02_fp64_instruction_counts.json")) as f:
+            prof = json.load(f)
+        exe_ratio = prof["executed_over_model"]
+        traffic_note = prof.get("dram_note")
+    except Exception:
+        pass
+    roofline = {"kernel": config["adjoint_kernel"], "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
+                "frac": achieved / peak, "frac_of_nominal_37.2": achieved / 37.2,
+                "frac_executed": None if exe_ratio is None else achieved * exe_ratio / peak,
+                # DRAM traffic is not measured in this run (it needs ncu); the capture of this build is cited instead
+                "traffic": None, "traffic_profile": traffic_note, "peak_source": peak_src,
                 "note": "HBM and tensor rooflines do not bind this path (10.7 MB and 10 Gflop per design, no dense contraction)",
                 "forward_kernel": {"achieved": flops_fwd / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms}, "adjoint_ms": adj_ms,
                 "steps_fwd_mean": float(st_f["steps"].mean()), "steps_bwd_mean": float(st_b["steps"].mean())}
@@ -334,10 +362,12 @@ def main():
         cstep()
         dtc = time.perf_counter() - t0
         cpu_baseline = {"value": n / dtc, "unit": UNIT, "cores": cores, "kind": "port",
-                        "sample": f"{n} designs of the same ensemble on {cores} host threads, C++ oracle (not the JAX reference)"}
+                        "sample": f"{n} designs of the same ensemble on {cores} host threads, C++ port of the reference "
+                                  f"algorithm ({cstep.build}; not the JAX reference)"}
 
     out = {"metric": METRIC, "value": value, "unit": UNIT, "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f64",
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak" if weak else "strong", "vs_baseline": None,
+           "dtype": "f64",
            "data": "synthetic", "config": config, "clocks": cl, "e2e": e2e, "gpu_launches": 3 * args.steps,
            "roofline": roofline, "cpu_baseline": cpu_baseline, "failed_designs": bad}
     print(json.dumps(out))

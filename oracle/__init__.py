@@ -18,19 +18,42 @@ _LIB = None
 
 
 def build(force=False):
+    """builds the checker (literal arithmetic: -O2, no FMA contraction) and the baseline build of the same source
+    (-O3 -march=x86-64-v3 with FMA: the fastest honest CPU port, used by bench.py's CPU legs only)"""
     so = os.path.join(_HERE, "libdfx_oracle.so")
+    fast = os.path.join(_HERE, "libdfx_oracle_fast.so")
     src = os.path.join(_HERE, "dfx_oracle.cpp")
     hdr = os.path.join(_HERE, "..", "include", "dfx.h")
-    if force or not os.path.exists(so) or (
-            os.path.exists(src) and os.path.getmtime(so) < max(os.path.getmtime(src), os.path.getmtime(hdr))):
-        subprocess.check_call(["make", "-C", _HERE, "-B", "libdfx_oracle.so"], stdout=subprocess.DEVNULL)
+    newest = max(os.path.getmtime(src), os.path.getmtime(hdr)) if os.path.exists(src) else 0.0
+    if force or not os.path.exists(so) or not os.path.exists(fast) or min(os.path.getmtime(so), os.path.getmtime(fast)) < newest:
+        subprocess.check_call(["make", "-C", _HERE, "-B", "all"], stdout=subprocess.DEVNULL)
     return so
+
+
+_FAST = False
+
+
+def use_fast_build(on=True):
+    """bench.py's CPU legs: switch to the -O3 / AVX2 / FMA build when the host supports it (results differ from the
+    checker build at round-off level).  Returns whether the fast build is in use."""
+    global _LIB, _FAST
+    ok = False
+    if on:
+        try:
+            flags = open("/proc/cpuinfo").read()
+            ok = " avx2" in flags and " fma" in flags and os.path.exists(os.path.join(_HERE, "libdfx_oracle_fast.so"))
+        except OSError:
+            ok = False
+    if ok != _FAST:
+        _LIB, _FAST = None, ok
+    return ok
 
 
 def lib():
     global _LIB
     if _LIB is None:
-        _LIB = C.CDLL(build())
+        so = build()
+        _LIB = C.CDLL(os.path.join(_HERE, "libdfx_oracle_fast.so") if _FAST else so)
         _LIB.dfxo_energy.restype = C.c_double
     return _LIB
 

@@ -328,7 +328,7 @@ def test_bench_reference_arm_prints_the_contract_line():
     assert out.returncode == 0, out.stderr[-2000:]
     line = json.loads(out.stdout.strip().splitlines()[-1])
     assert line["impl"] == "reference" and line["unit"] == "designs/s" and line["higher_is_better"] is True
-    assert line["value"] > 0 and line["steps"] == 1 and line["dtype"] == "f64" and line["scaling"] == "weak"
+    assert line["value"] > 0 and line["steps"] == 1 and line["dtype"] == "f64" and line["scaling"] == "strong"
     assert line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
     assert line["e2e"] == {"value": line["value"], "unit": "designs/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}
     assert "workload" in line["config"]

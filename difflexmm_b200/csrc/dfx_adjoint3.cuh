@@ -42,8 +42,8 @@ constexpr int NBC = 10;  // bond constants: r0x r0y L0 1/L0 r1x r1y r2x r2y da1 
 constexpr int NE3 = 12;  // quadrature entries per thread: 0..9 unit role (P: inertia[3] damping[3] cnv x[4]; D: cnv y[4]), 10..11 bond role
 // L2 scratch of one SM (doubles); every array is [..][TT], a thread touches its own column only
 constexpr long long G_BC = 0;
-constexpr long long G_SPART = G_BC + (long long)NBC * TT;   // [6][TT] per-bond partials of k_stretch k_shear k_rot c_min c_cut k_c
-constexpr long long G_BQ = G_SPART + 6LL * TT;              // [sol, err][2][TT] running sums of the reference-vector quadratures
+constexpr long long G_SPART = G_BC + (long long)NBC * TT;   // [2 (parity of the evaluation)][6][TT] per-bond partials of k_stretch k_shear k_rot c_min c_cut k_c
+constexpr long long G_BQ = G_SPART + 12LL * TT;              // [sol, err][2][TT] running sums of the reference-vector quadratures
 constexpr long long G_Q = G_BQ + 4LL * TT;                  // [q0 a, q0 b, k1 a, k1 b][NE3][TT]
 constexpr long long G_TOTAL = G_Q + 4LL * NE3 * TT;
 // scalar leaves: running sums [k1, k7, sol, err, mid][NSLOT]
@@ -523,7 +523,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     }
     bcg[8 * TT] = da1; bcg[9 * TT] = da2;
   }
-  for (int q = 0; q < 6 + 4 + 4 * NE3; ++q) gcol[G_SPART + (long long)q * TT] = 0.0;
+  for (int q = 0; q < 12 + 4 + 4 * NE3; ++q) gcol[G_SPART + (long long)q * TT] = 0.0;
   // y_bar = g[-1]
   if (isD) {
     double cu[3], cv[3];
@@ -649,10 +649,12 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     if (!isD) {
       // dense scalar leaves: P warp w sums the partials of bonds [192 q, 192 q + 192), q = w / 3, of leaf w % 3 (and of
       // contact leaf w % 3 once a bond has touched), fixed order; loads issued first, consumed last
+      // (accumulating stages 2..4: the partials are summed by the last warp, which has no bonds, during the NEXT bond phase)
+      constexpr bool REDUCE_NOW = WANT_Q && !(EV >= 1 && EV <= 4);
       double rk[6] = {0, 0, 0, 0, 0, 0}, rc[6] = {0, 0, 0, 0, 0, 0};
 #ifndef ABL_NO_REDUCE
-      if (WANT_Q) {
-        const double* sp = gbase + G_SPART + (long long)(warp % 3) * TT + (warp / 3) * 192 + lane;
+      if (REDUCE_NOW) {
+        const double* sp = gbase + G_SPART + (long long)((EV & 1) * 6 + warp % 3) * TT + (warp / 3) * 192 + lane;
 #pragma unroll
         for (int q = 0; q < 6; ++q) rk[q] = __ldcg(&sp[q * 32]);
         if (seen) {
@@ -736,7 +738,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         }
         if (DAMP == 1) { const double tot = warp_sum(p_damp); if (lane == 0) scal_slot<MODE>(tab, accb, SLOT_DAMP + warp, tot); }
 #ifndef ABL_NO_REDUCE
-        {
+        if (REDUCE_NOW) {
 #pragma unroll
           for (int o = 16; o > 0; o >>= 1) {
             sk += __shfl_xor_sync(0xffffffffu, sk, o);
@@ -964,12 +966,52 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         // d(w.F)/dp = -(dual part of dE/dp).  The reference-vector quadratures are updated at the end of phase C; the dense
         // scalar leaves go through per-bond partials in the scratch, summed in phase C by the P warps.
 #ifndef ABL_NO_SPART
-        double* sp = gcol + G_SPART;
+        double* sp = gcol + G_SPART + (long long)((ev & 1) * 6) * TT;
         sp[0] = -gks_d; sp[TT] = -gksh_d; sp[2 * TT] = -gkr_d;
         if (CONTACT && (flags & 512u)) { sp[3 * TT] = p_c0; sp[4 * TT] = p_c1; sp[5 * TT] = p_c2; }
 #endif
       }
     }
+#ifndef ABL_NO_REDUCE
+    if (warp == NW - 1 && ev >= 2 && ev <= 5) {
+      // the dense scalar leaves of the PREVIOUS evaluation (an accumulating stage, mode = ev): this warp has no bonds, it
+      // sums the 768 per-bond partials of every leaf (fixed order) while the others do their bond arithmetic
+      const bool seen = CONTACT && C->contact_seen;
+      const double* sp = gbase + G_SPART + (long long)(((ev - 1) & 1) * 6) * TT + lane;
+      double tot[6] = {0, 0, 0, 0, 0, 0};
+#pragma unroll
+      for (int l = 0; l < 6; ++l) {
+        if (l < 3 || seen) {
+          double v[NW];
+#pragma unroll
+          for (int q = 0; q < NW; ++q) v[q] = __ldcg(&sp[(long long)l * TT + q * 32]);
+          double sacc = 0.0;
+#pragma unroll
+          for (int q = 0; q < NW; ++q) sacc += v[q];
+          tot[l] = sacc;
+        }
+      }
+#pragma unroll
+      for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+        for (int l = 0; l < 6; ++l) if (l < 3 || CONTACT) tot[l] += __shfl_xor_sync(0xffffffffu, tot[l], o);
+      }
+      // lane 4 l + q updates partial slot q of leaf l: the total goes to slot 0, the others receive 0 (mode 2 rebuilds all four)
+      if (lane < (seen ? 24 : 12)) {
+        const int l = lane >> 2, q = lane & 3;
+        double mine = 0.0;
+#pragma unroll
+        for (int k = 0; k < 6; ++k) if (k == l && q == 0) mine = tot[k];
+        const int slot = SLOT_K + l * 4 + q;
+        switch (ev) {
+          case 2: scal_slot<2>(tab, accb, slot, mine); break;
+          case 3: scal_slot<3>(tab, accb, slot, mine); break;
+          case 4: scal_slot<4>(tab, accb, slot, mine); break;
+          default: scal_slot<5>(tab, accb, slot, mine); break;
+        }
+      }
+    }
+#endif
     PT_MARK(2);
     __syncthreads();
     PT_MARK(3);

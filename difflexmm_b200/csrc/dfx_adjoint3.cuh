@@ -59,6 +59,8 @@ struct Ctrl {
   int status, crossing, contact_seen;
   int i, par;  // output interval in progress; which copy of q0 / k1 is current
   uint32_t tmem_base;
+  int ev_w[NW];  // kind of the evaluation in progress, one copy per warp (written by its lane 0): a register carried round
+                 // the loop is spilled to local memory = an L2 round trip at the top of every phase
 };
 
 template <int NSL>
@@ -547,11 +549,17 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 
   // The only loop-carried register is the kind of the next evaluation; the output interval, the quadrature parity and the
   // step size live in the control block (written by thread 0 between barriers).
-  int ev = EV_INIT;
-  bool running = a.n_t >= 2;
+  constexpr int EV_STOP = 8;
+  if (lane == 0) C->ev_w[warp] = a.n_t >= 2 ? EV_INIT : EV_STOP;
   if (tid == 0) { C->i = a.n_t - 1; C->par = 0; C->hst = 0.0; }
   __syncthreads();
 
+  // scratch column of this thread, re-derived from %smid where it is used (not carried in registers)
+  auto gcol_now = [&]() {
+    unsigned sm_;
+    asm volatile("mov.u32 %0, %%smid;" : "=r"(sm_));
+    return a.scratch + (long long)sm_ * A.scratch_per_slot + tid;
+  };
   // ---- phase A: stage state of this thread's half of its unit, published to shared memory ------------------------
   auto phaseA = [&](auto tag, double* Wcur) {
     constexpr int EV = decltype(tag)::value;
@@ -627,6 +635,9 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
   auto phaseC = [&](auto tag, const double* Wcur) -> double {
     constexpr int EV = decltype(tag)::value;
     constexpr int KIDX = Ev<EV>::kidx, MODE = Ev<EV>::mode;
+    double* const gcol = gcol_now();  // (shadows: the scratch pointers are re-derived, not carried round the loop)
+    double* const qg = gcol + G_Q;
+    const double* const gbase = gcol - tid;
 #ifdef ABL_NO_Q
     constexpr bool WANT_Q = false;
 #else
@@ -846,13 +857,20 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 #else
 #define PT_MARK(k) do { } while (0)
 #endif
-  while (running) {
+  while (true) {
     PT_MARK(5);
+    int ev = *(volatile int*)&C->ev_w[warp];
+    if (ev == EV_STOP) break;
+    bool running = true;
     double* Wcur = Ws + (ev & 1) * 3 * TU;  // consecutive evaluations never have the same parity (6 -> 7 -> 0..5 -> 0 | 6)
     // bond constants: fetched from L2 now, used after the barrier
     double bc[NBC];
 #pragma unroll
-    for (int k = 0; k < (CONTACT ? NBC : NBC - 2); ++k) bc[k] = gcol[G_BC + (long long)k * TT];
+    {
+      const double* gc_ = gcol_now();
+#pragma unroll
+      for (int k = 0; k < (CONTACT ? NBC : NBC - 2); ++k) bc[k] = gc_[G_BC + (long long)k * TT];
+    }
 #define DFX_A3_A(TAG) phaseA(TAG, Wcur)
     DFX_A3_DISPATCH(DFX_A3_A)
 #undef DFX_A3_A
@@ -862,7 +880,10 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 
     // ================= phase B: this thread's bond (one copy of the code for every kind of evaluation) =================
     double accq = 0.0;  // this thread's contribution to the error norm / probe norm
+    ev = *(volatile int*)&C->ev_w[warp];
     if (has_bnd) {
+      double* const gcol = gcol_now();
+      double* const qg = gcol + G_Q;
       const bool want_q = ev != 0;  // the second stage of a step has zero weight in every combination
       const int b1 = bbp & 0xffff, b2 = bbp >> 16;
       const int b = tid;
@@ -881,8 +902,15 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         Dual c1m = s1.c - 1.0, c2m = s2.c - 1.0;
         Dual dx = (s2.x + c2m * r2x - s2.s * r2y) - (s1.x + c1m * r1x - s1.s * r1y) + r0x;
         Dual dy = (s2.y + s2.s * r2x + c2m * r2y) - (s1.y + s1.s * r1x + c1m * r1y) + r0y;
-        Dual t1x = -(s1.s * r1x) - s1.c * r1y, t1y = s1.c * r1x - s1.s * r1y;  // d(node)/d(theta) = R'(theta) r
-        Dual t2x = -(s2.s * r2x) - s2.c * r2y, t2y = s2.c * r2x - s2.s * r2y;
+        {
+          // d(node)/d(theta) = R'(theta) r of the two nodes: only needed for the torques at the end -- parked in this bond's
+          // own (still unused) result slots instead of eight registers across the energy arithmetic
+          const Dual t1x = -(s1.s * r1x) - s1.c * r1y, t1y = s1.c * r1x - s1.s * r1y;
+          const Dual t2x = -(s2.s * r2x) - s2.c * r2y, t2y = s2.c * r2x - s2.s * r2y;
+          SL[6 * TT + b] = t1x.v; SL[7 * TT + b] = t1x.d; SL[8 * TT + b] = t1y.v; SL[9 * TT + b] = t1y.d;
+          SL[10 * TT + b] = t2x.v; SL[11 * TT + b] = t2x.d;
+          if (CONTACT) { SL[12 * TT + b] = t2y.v; SL[13 * TT + b] = t2y.d; } else { SL[4 * TT + b] = t2y.v; SL[5 * TT + b] = t2y.d; }
+        }
         Dual dth = s2.th - s1.th;
         Dual mean = (s2.th + s1.th) * 0.5;
         const double L0sq = L0 * L0;
@@ -904,6 +932,9 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         gdx = A * dx - Bc * dy;
         gdy = A * dy + Bc * dx;
         Dual bend = dth * kr;
+        asm volatile("" ::: "memory");
+        const Dual t1x(SL[6 * TT + b], SL[7 * TT + b]), t1y(SL[8 * TT + b], SL[9 * TT + b]), t2x(SL[10 * TT + b], SL[11 * TT + b]);
+        const Dual t2y = CONTACT ? Dual(SL[12 * TT + b], SL[13 * TT + b]) : Dual(SL[4 * TT + b], SL[5 * TT + b]);
         Dual f1t = M * (-0.5) - (gdx * t1x + gdy * t1y) - bend;
         Dual f2t = M * (-0.5) + (gdx * t2x + gdy * t2y) + bend;
         if (CONTACT) {
@@ -925,7 +956,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         // forces on the two ends are equal and opposite: store (gdx, gdy) once, the two torques separately
         SL[b] = gdx.v; SL[TT + b] = gdy.v; SL[2 * TT + b] = -f1t.v; SL[3 * TT + b] = -f2t.v;
         SL[4 * TT + b] = gdx.d; SL[5 * TT + b] = gdy.d; SL[6 * TT + b] = f1t.d; SL[7 * TT + b] = f2t.d;
-        if (CONTACT && (flags & 512u)) { SL[12 * TT + b] = a1; SL[13 * TT + b] = a2; }
+        if (CONTACT) { SL[12 * TT + b] = a1; SL[13 * TT + b] = a2; }  // (always: the slots were used as scratch above)
         // parameter cotangent integrands: -(dual part of dE/dp)
         gks_d = ext.v * ext.d; gksh_d = gam.v * gam.d * L0sq; gkr_d = dth.v * dth.d;
         Dual dE_dL0 = gam * gam * (ksh * L0) - ext * ks;
@@ -1017,14 +1048,22 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     PT_MARK(3);
 
 #define DFX_A3_C(TAG) accq += phaseC(TAG, Wcur)
+    ev = *(volatile int*)&C->ev_w[warp];
+    Wcur = Ws + (ev & 1) * 3 * TU;
     DFX_A3_DISPATCH(DFX_A3_C)
 #undef DFX_A3_C
     PT_MARK(4);
 
     // ================= what follows the evaluation =================
-    if (ev < 5) { ++ev; continue; }
+    if (ev < 5) {
+      __syncwarp();
+      if (lane == 0) C->ev_w[warp] = ev + 1;
+      __syncwarp();
+      continue;
+    }
     int i = C->i, par = C->par;
     const double hst = C->hst;
+    double* const qg = gcol_now() + G_Q;
     if (ev == EV_INIT) {
       double sd0 = 0, sd1 = 0, pt = 0.0;
       if (!isD) {
@@ -1081,7 +1120,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       const double h0 = (d0 < 1e-5 || d1 < 1e-5) ? 1e-6 : 0.01 * d0 / d1;
       if (tid == 0) { C->s0 = -ts[i]; C->s_target = -ts[i - 1]; C->h0 = h0; C->d1 = d1; C->n_rhs += 1; C->crossing = 0; C->hst = h0; }
       if (drive_on && tid == TT - 32 + EV_PROBE) fill_drive(EV_PROBE, ts[i] - h0);
-      ev = EV_PROBE;
+      if (lane == 0) C->ev_w[warp] = EV_PROBE;
       __syncthreads();
     } else if (ev == EV_PROBE) {
       double sd2 = accq;
@@ -1136,6 +1175,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       if (empty) { if (--i < 1) running = false; else ev = EV_INIT; }
       else if (stop) running = false;
       else ev = 0;
+      if (lane == 0) C->ev_w[warp] = running ? ev : EV_STOP;
       if (tid == 0) { C->hst = h; C->i = i; }
       if (drive_on && running && warp == NW - 1) {
         if (ev == 0 && lane < 6) fill_drive(lane, -(s0 + h * tab.alpha[lane]));
@@ -1287,6 +1327,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       if (stop) running = false;
       else if (interval_done) { if (--i < 1) running = false; else ev = EV_INIT; }
       else ev = 0;
+      if (lane == 0) C->ev_w[warp] = running ? ev : EV_STOP;
       if (tid == 0) { C->hst = h_new; C->i = i; C->par = par; }
       if (drive_on && running && warp == NW - 1) {
         if (ev == 0 && lane < 6) fill_drive(lane, -(s_new + h_new * tab.alpha[lane]));

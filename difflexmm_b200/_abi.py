@@ -66,7 +66,8 @@ class DfxParamGrads(C.Structure):
 
 
 class DfxOptions(C.Structure):
-    _fields_ = [("init_step_variant", C.c_int32), ("threads", C.c_int32), ("max_steps", C.c_int64)]
+    _fields_ = [("init_step_variant", C.c_int32), ("threads", C.c_int32), ("max_steps", C.c_int64),
+                ("design_order", C.c_void_p)]
 
 
 class DfxGeometryDesc(C.Structure):

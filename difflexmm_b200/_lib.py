@@ -144,6 +144,19 @@ def forward(topo: Topology, ps: _abi.ParamSet, y0, ts, rtol, atol, options: _abi
     return ys, _Stats(stats)
 
 
+def longest_first(stats: "_Stats", options: _abi.DfxOptions, min_batch: int = 149):
+    """Options for the adjoint launch that follows a forward solve: the designs are launched in decreasing order of
+    their forward step count (a good predictor of the adjoint's), so that a launch with more designs than SMs does not end
+    with one long design on an otherwise idle GPU.  Returns (options, order tensor to keep alive); small batches (one
+    wave) keep the plain order.  No host synchronisation."""
+    steps = stats.steps_device()
+    if steps.numel() < min_batch:
+        return options, None
+    order = torch.argsort(steps, descending=True, stable=True).to(torch.int32)
+    opt = _abi.DfxOptions(options.init_step_variant, options.threads, options.max_steps, order.data_ptr())
+    return opt, order
+
+
 def adjoint_plan(topo: Topology, ps: _abi.ParamSet) -> str:
     """name of the adjoint kernel the library launches for this topology / these leaf forms / this batch (diagnostic)"""
     p = ps.to_struct()
@@ -265,6 +278,10 @@ class _Stats:
 
     def numpy(self):
         return self._raw.cpu().numpy().view(_abi.STATS_DTYPE).reshape(-1)
+
+    def steps_device(self):
+        """attempted step counts as an int64 tensor on the device (no synchronisation)"""
+        return self._raw.view(torch.int64)[:, 0]
 
     def __getitem__(self, k):
         return self.numpy()[k]

@@ -63,6 +63,7 @@ struct AdjArgs {
   // quadrature layout (entries)
   int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, nq;
   int group;  // CL = 2: CTAs per design
+  const int* order;  // DfxOptions.design_order
 };
 
 // Cotangent dJ/d ys[design][i][(is_v ? n_free : 0) + f] of the device objectives (include/dfx.h), w = weights[design]:
@@ -224,7 +225,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   const Tableau& tab = a.tab;
   const int ncta = CL == 1 ? (int)cluster_nctarank() : (CL == 2 ? a.group : 1);
   const int crank = CL == 1 ? (int)cluster_ctarank() : (CL == 2 ? (int)(blockIdx.x % ncta) : 0);
-  const int design = blockIdx.x / ncta;
+  const int design = a.order ? a.order[blockIdx.x / ncta] : (int)(blockIdx.x / ncta);
   const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
   const int lane = threadIdx.x & 31, cwarp = threadIdx.x >> 5, cnwarp = (blockDim.x + 31) >> 5;
   const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;

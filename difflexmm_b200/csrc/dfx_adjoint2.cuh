@@ -190,7 +190,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
   const AdjArgs& a = A.a;
   const DevTopo& T = a.topo;
   const Tableau& tab = a.tab;
-  const int design = blockIdx.x;
+  const int design = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int nthr = TT, nwarp = TT / 32;
   const int NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;

@@ -352,7 +352,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
   const AdjArgs& a = A.a;
   const DevTopo& T = a.topo;
   const Tableau& tab = a.tab;
-  const int design = blockIdx.x;
+  const int design = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
   const bool isD = tid >= TU;
   const int NB = T.n_blocks, NBONDS = T.n_bonds, nf = T.n_free;

@@ -499,6 +499,7 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
   a.rtol = rtol; a.atol = atol;
   a.init_step_variant = opt ? opt->init_step_variant : 0;
   a.max_steps = (opt && opt->max_steps > 0) ? opt->max_steps : (1LL << 40);
+  a.order = opt ? opt->design_order : nullptr;
   a.ys = ys; a.stats = stats;
   if (fp.ok) g = fp.scratch;
   a.scratch_per_design = g;
@@ -653,6 +654,7 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   a.aug_size = aug_size;
   a.init_step_variant = opt ? opt->init_step_variant : 0;
   a.max_steps = (opt && opt->max_steps > 0) ? opt->max_steps : (1LL << 40);
+  a.order = opt ? opt->design_order : nullptr;
   a.y0_bar = y0_bar; a.ts_bar = ts_bar;
   if (grads) a.grads = *grads;
   a.stats = stats;

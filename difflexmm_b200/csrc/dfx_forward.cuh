@@ -53,6 +53,7 @@ struct FwdArgs {
   double* ys; DfxStats* stats;
   double* scratch; long long scratch_per_design;  // doubles
   int group;  // CL = 2: CTAs per design
+  const int* order;  // DfxOptions.design_order
 };
 constexpr int kGroupReserveFwd = 8 + 2 * kMaxGroup;
 
@@ -112,7 +113,7 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
   const DevTopo& T = a.topo;
   const int ncta = CL == 1 ? (int)cluster_nctarank() : (CL == 2 ? a.group : 1);
   const int crank = CL == 1 ? (int)cluster_ctarank() : (CL == 2 ? (int)(blockIdx.x % ncta) : 0);
-  const int design = blockIdx.x / ncta;
+  const int design = a.order ? a.order[blockIdx.x / ncta] : (int)(blockIdx.x / ncta);
   const int tid = crank * blockDim.x + threadIdx.x, nthr = ncta * blockDim.x;
   const int NB = T.n_blocks, NN = T.n_nodes, ND = 3 * NB, NBONDS = T.n_bonds, npb = T.n_npb;
   double* red = smem;  // 40 doubles reserved at the start of shared memory

@@ -32,7 +32,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
   const FwdArgs& a = A.a;
   const DevTopo& T = a.topo;
   const Tableau& tab = a.tab;
-  const int design = blockIdx.x;
+  const int design = a.order ? a.order[blockIdx.x] : (int)blockIdx.x;
   const int tid = threadIdx.x, warp = tid >> 5;
   constexpr int nthr = TT;
   const int NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds, npb = T.n_npb, nf = T.n_free;

@@ -248,8 +248,9 @@ class _DeviceObjective(torch.autograd.Function):
     def backward(ctx, gJ):
         solver, meta, ps = ctx.solver, ctx.meta, ctx.ps
         ys, ts, y0, ibar, abar = ctx.saved_tensors
+        opt, order = solver._lib.longest_first(solver.last_forward_stats, solver.options)  # noqa: F841 (order kept alive)
         y0_bar, ts_bar, grads, stats = solver._lib.adjoint_objective(
-            solver.handle, ps, ys, ts, ctx.target_ids, gJ, solver.rtol, solver.atol, meta["aug_size"], solver.options,
+            solver.handle, ps, ys, ts, ctx.target_ids, gJ, solver.rtol, solver.atol, meta["aug_size"], opt,
             meta["kind"], ctx.arm)
         solver.last_adjoint_stats = stats
         grads["inertia"] = grads["inertia"] + gJ[:, None] * ibar  # explicit dependence of J on the masses

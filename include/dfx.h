@@ -141,6 +141,10 @@ typedef struct DfxOptions {
                                 1: h1 = (0.01/max(d1,d2))^(1/5) (later jax releases)     */
   int32_t threads;           /* CTA size override, 0 = choose                           */
   int64_t max_steps;         /* attempted-step cap per odeint call, 0 = 1<<40 (jax: inf)*/
+  const int32_t* design_order; /* device array [batch] or NULL: CTA (group) k of the launch works on design
+                                design_order[k].  A permutation of 0..batch-1 that puts the designs expected to take
+                                longest first (e.g. by the step counts of the forward solve) shortens the tail of a
+                                launch with more designs than SMs; the results do not depend on it.            */
 } DfxOptions;
 
 enum { DFX_OK = 0, DFX_ERR_INVALID = 1, DFX_ERR_CUDA = 2, DFX_ERR_UNSUPPORTED = 3 };

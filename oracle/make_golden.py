@@ -258,6 +258,37 @@ def static_pulse_case(name, n1, n2, *, n_t, rtol, atol):
              ts=ts, rtol=rtol, atol=atol, density_leaf=T(rho))
 
 
+def ramp_sech2_case(name, n1, n2, *, n_t, t_end, rtol, atol, seed=6):
+    """the two signal kinds no other fixture holds: constrained DOFs on a linear ramp to a plateau
+    (problems/hinge_characterization.py:134-139) and an external load with the sech^2 * tanh pulse of
+    scripts/pulse_RS.py:49-50 on the right-hand column; per-DOF damping, contact present but not entered."""
+    torch.manual_seed(seed)
+    geo = QuadGeometry(n1, n2, spacing=15., bond_length=2.25)
+    bc, cnvf, bonds, refv = geo.get_parametrization()
+    hs, vs = geo.get_design_from_rotated_square(25 * math.pi / 180)
+    hs = hs + 0.2 * torch.randn_like(hs)
+    vs = vs + 0.2 * torch.randn_like(vs)
+    cnv, cent = cnvf(hs, vs), bc(hs, vs)
+    mid = (n2 // 2) * n1
+    pairs = np.array([[mid, 0], [mid, 1], [mid, 2], [0, 0], [0, 1], [0, 2]])
+    cons = pairs[:, 0] * 3 + pairs[:, 1]
+    free, _, _ = DOFsInfo(geo.n_blocks, pairs)
+    lv = np.zeros(len(cons))
+    lv[0] = 1
+    rho = 6.18e-9
+    inertia = compute_inertia(cnv, rho).reshape(-1)[free]
+    damp = T(0.0186) * torch.ones(geo.n_blocks, 3, dtype=F64) * T(
+        [2 * (0.36125 * rho * 15 ** 2 * 1.19) ** .5] * 2 + [2 * (0.02175026 * rho * 15 ** 4 * 1.5) ** .5])
+    leaves = dict(centroid_node_vectors=cnv, reference_vector=refv(), k_stretch=T(120.), k_shear=T(1.19), k_rot=T(1.5),
+                  damping=damp, inertia=inertia, contact=T([-15 * math.pi / 180, -10 * math.pi / 180, 1.5]))
+    loaded = np.array([(j * n1 + n1 - 1) * 3 for j in range(n2)])  # x DOF of the right-hand column
+    run_case(name, n_blocks=geo.n_blocks, n_npb=4, bonds=bonds(), cons=cons, bond_energy=0, use_contact=True,
+             drive_kind=_abi.DFX_DRIVE_RAMP, drive_vec0=lv, drive_vec1=None,
+             drive_params=dict(amplitude=2.5, loading_rate=250.), load=dict(kind=_abi.DFX_LOAD_SECH2, dofs=loaded, consts=(2.0e-7, 0.0012)),
+             damped_blocks=np.arange(geo.n_blocks), leaves=leaves, block_centroids=cent,
+             ts=np.linspace(0, t_end, n_t), rtol=rtol, atol=atol, density_leaf=T(rho), g_mode="generic")
+
+
 def tensile_case(name, n1_cells, bond_energy, *, n_t, t_end):
     """tests/test_difflexmm.py:35-146 in miniature (loading_fn, explicit inertia, clamped x DOFs)."""
     geo = RotatedSquareGeometry(n1_cells=n1_cells, n2_cells=1, spacing=1.0)
@@ -293,6 +324,7 @@ CASES = {
     "static_pulse_4x4": lambda: static_pulse_case("static_pulse_4x4", 4, 4, n_t=3, rtol=1e-9, atol=1e-8),
     "tensile_linearized": lambda: tensile_case("tensile_linearized", 2, 1, n_t=4, t_end=60.),
     "tensile_ligament": lambda: tensile_case("tensile_ligament", 2, 0, n_t=4, t_end=60.),
+    "ramp_sech2_4x3": lambda: ramp_sech2_case("ramp_sech2_4x3", 4, 3, n_t=5, t_end=0.008, rtol=1e-9, atol=1e-8),
     "springs_4x3": lambda: spring_case("springs_4x3", 4, 3, n_t=4, t_end=0.02, rtol=1e-8, atol=1e-6),
 }
 

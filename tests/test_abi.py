@@ -35,7 +35,7 @@ def test_ctypes_struct_layout_matches_header_sizes():
     from difflexmm_b200 import _abi
     assert C.sizeof(_abi.DfxStats) == 40
     assert C.sizeof(_abi.DfxLeaf) == 16
-    assert C.sizeof(_abi.DfxOptions) == 16
+    assert C.sizeof(_abi.DfxOptions) == 24
     assert C.sizeof(_abi.DfxParamGrads) == 9 * 8
     # DfxParams: 5 leaves, int[3] (+pad), leaf, int (+pad), 3 leaves
     assert C.sizeof(_abi.DfxParams) == 5 * 16 + 16 + 16 + 8 + 3 * 16

@@ -613,3 +613,41 @@ def test_adjoint3_instances_match_cpp_oracle(lattice, contact, damping, drive, e
     for k in gr_h:
         if np.abs(gr_h[k]).max() > 1e-9:
             assert rel_l2(gr[k][0].cpu().numpy(), gr2[k][0].cpu().numpy()) <= GRAD_TOL, k
+
+
+@pytest.mark.parametrize("mode", ["default", "v2", "generic", "cluster4"])
+def test_design_order_does_not_change_results(mode, monkeypatch):
+    """DfxOptions.design_order only changes which CTA works on which design: forward and adjoint results are bit-identical
+    with and without it (fast kernels, generic kernel, generic kernel over a cluster)"""
+    for var in ("DFX_FORWARD_KERNEL", "DFX_ADJOINT_KERNEL"):
+        monkeypatch.delenv(var, raising=False)
+    monkeypatch.setenv("DFX_CLUSTER", "4" if mode == "cluster4" else "1")
+    if mode in ("generic", "cluster4"):
+        monkeypatch.setenv("DFX_FORWARD_KERNEL", "generic")
+        monkeypatch.setenv("DFX_ADJOINT_KERNEL", "generic")
+    elif mode == "v2":
+        monkeypatch.setenv("DFX_ADJOINT_KERNEL", "v2")
+    c = load_golden("quads_4x3_contact_active")
+    B = 5
+    rng = np.random.default_rng(5)
+    leaves = {}
+    for k, v in c.leaves.items():
+        v = np.asarray(v, dtype=np.float64)
+        if k == "centroid_node_vectors":
+            v = v[None] * (1 + 1e-3 * rng.standard_normal((B,) + v.shape))
+        leaves[k] = torch.as_tensor(v, device="cuda").contiguous()
+    lib, topo = _solver(c.spec)
+    ps = _abi.ParamSet(c.spec, B, leaves, c.per_bond, c.damping_per_dof)
+    y0, ts = torch.as_tensor(c.y0, device="cuda"), torch.as_tensor(c.ts, device="cuda")
+    order = torch.as_tensor([3, 0, 4, 2, 1], dtype=torch.int32, device="cuda")
+    plain, perm = _abi.DfxOptions(0, 0, 0), _abi.DfxOptions(0, 0, 0, order.data_ptr())
+    ys0, st0 = lib.forward(topo, ps, y0, ts, c.rtol, c.atol, plain)
+    ys1, st1 = lib.forward(topo, ps, y0, ts, c.rtol, c.atol, perm)
+    assert torch.equal(ys0, ys1) and (st0.numpy()["steps"] == st1.numpy()["steps"]).all()
+    g = torch.cos(ys0) + 0.1
+    a0 = lib.adjoint(topo, ps, ys0, ts, g, c.rtol, c.atol, c.aug_size, plain)
+    a1 = lib.adjoint(topo, ps, ys0, ts, g, c.rtol, c.atol, c.aug_size, perm)
+    assert torch.equal(a0[0], a1[0]) and torch.equal(a0[1], a1[1])
+    for k in a0[2]:
+        assert torch.equal(a0[2][k], a1[2][k]), k
+    assert len(set(st0.numpy()["steps"].tolist())) > 1  # the designs really differ

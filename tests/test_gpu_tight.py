@@ -86,3 +86,17 @@ def test_full_lattices_at_tight_tolerances():
     # the three lattice sizes exercise the three fast adjoint instances
     assert kernels["cfg3_member_0"].startswith("adjoint3_kernel<4,1,2>")
     assert kernels["cfg2_kagome_20x12"].startswith("adjoint2_kernel") and kernels["cfg4_strain_0.01"].startswith("adjoint2_kernel")
+
+
+@pytest.mark.slow
+@pytest.mark.skipif(os.environ.get("DFX_LONG_TESTS") != "1", reason="minutes of host CPU time: set DFX_LONG_TESTS=1 "
+                    "(recorded run: profiles/r02_parity_long.jsonl)")
+def test_full_horizons_at_tight_tolerances():
+    """the full horizons of cfg2, three cfg3 members and both cfg4 tasks (real static ramps), see tools/parity_long.py"""
+    sys.path.insert(0, os.path.join(os.path.dirname(os.path.dirname(os.path.abspath(__file__))), "tools"))
+    import parity_long
+    cs = parity_long.cases(quick=False)
+    with ThreadPoolExecutor(max_workers=len(cs)) as pool:
+        refs = list(pool.map(lambda c: oracle_job(c[1], c[2], c[3], c[4]), cs))
+    for (name, P, design, rtol, atol), ref in zip(cs, refs):
+        compare(name, P, ref, rtol, atol)

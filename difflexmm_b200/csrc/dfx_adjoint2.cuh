@@ -225,7 +225,21 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
   // lines are reused by every design the SM processes and stay in L2 (A.scratch_slots = %nsmid bound, else per design)
   unsigned smid;
   asm("mov.u32 %0, %%smid;" : "=r"(smid));
-  double* gbase = a.scratch + (long long)(A.scratch_slots > 0 && (int)smid < A.scratch_slots ? (int)smid : design) * A.tp_scratch_per_design;
+  if (A.scratch_slots > 0 && (int)smid >= A.scratch_slots) {
+    // the scratch has one slice per SM id (the host sized it for %nsmid of sm_100 parts); an id beyond it must not fall
+    // back to the design index (out of bounds / shared with another SM): fail this design loudly instead
+    if (tid == 0 && a.stats) {
+      DfxStats st; st.steps = 0; st.accepted = 0; st.rhs_evals = 0; st.status = DFX_STATUS_NONFINITE; st.reserved = 0; st.last_dt = 0.0;
+      a.stats[design] = st;
+    }
+    if (NT > 0) {
+      asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
+      __syncthreads();
+      if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base_sh), "r"(512));
+    }
+    return;
+  }
+  double* gbase = a.scratch + (long long)(A.scratch_slots > 0 ? (int)smid : design) * A.tp_scratch_per_design;
   tp.g = gbase + tid;
   tp.taddr = NT > 0 ? (tmem_base_sh + ((uint32_t)((warp & 3) * 32) << 16) + (uint32_t)((warp >> 2) * A.tmem_cols_per_warp)) : 0u;
   // quadrature arrays [NQA][NE][T] behind the constants-tier overflow

@@ -1,7 +1,9 @@
 // jax_ffi_shim.cc -- XLA FFI handlers that expose libdfx's C ABI (include/dfx.h) to JAX as custom calls.
 //
-// NOT compiled in this image: it needs the XLA FFI headers shipped with a modern jaxlib
-// (`jax.ffi.include_dir()`, jax >= 0.4.31) and neither jax nor its headers are installed here.
+// NOT built in this image: it needs the XLA FFI headers shipped with a modern jaxlib (`jax.ffi.include_dir()`,
+// jax >= 0.4.31) and neither jax nor its headers are installed here.  It IS type-checked by the CPU
+// test suite (tests/test_abi.py) against tests/stubs/xla/ffi/api/ffi.h, a stand-in for the FFI surface used here whose
+// handler macro verifies that every implementation matches the argument list of its binding.
 // Handlers: DfxForward, DfxAdjoint (the odeint call and its custom_vjp backward), DfxObjectiveValue, DfxAdjointObjective
 // (objective fused with the adjoint), DfxGeometryForward, DfxGeometryVjp (design maps).
 // It is kept in-tree, next to the kernels it binds, so that a maintainer with a JAX install can build it:
@@ -19,6 +21,8 @@
 // memory; the topology handle (created once per setup_dynamic_solver call) travels as an int64 attribute.
 
 #include <cstdint>
+
+#include <cuda_runtime_api.h>  // cudaStream_t
 
 #include "xla/ffi/api/ffi.h"
 

@@ -142,10 +142,24 @@ def lower_params(spec, drive, control_params: ControlParams, batch: Optional[int
         if d.dim() - (1 if (B is not None and d.dim() in (1, 3)) else 0) == 0:
             d, _, n = split(d, 0)
         else:
-            d, db, n = split(d, 2)
+            # the reference multiplies the leaf by ones((n_damped, 3)) (loading.py:93-101): anything that broadcasts against
+            # that shape is valid -- (3,), (1, 3), (n_damped, 1).  The leaf keeps its own size in the augmented state
+            # (aug_size counts its elements); the kernel receives the broadcast (n_damped, 3) array and autograd sums the
+            # cotangent back to the leaf's shape.
+            if B is None and n_damped and tuple(d.shape) != (n_damped, 3):
+                try:
+                    n = d.numel()
+                    d = d * torch.ones((n_damped, 3), dtype=_F64, device=d.device)
+                except RuntimeError:
+                    raise ValueError(f"damping must be a scalar or broadcast against (n_damped_blocks, 3) = ({n_damped}, 3); "
+                                     f"got {tuple(_as_t(mp.damping, device).shape)}") from None
+                if tuple(d.shape) != (n_damped, 3):
+                    raise ValueError(f"damping must be a scalar or broadcast against (n_damped_blocks, 3) = ({n_damped}, 3)")
+            else:
+                d, db, n = split(d, 2)
+                if n_damped and tuple(d.shape[-2:]) != (n_damped, 3):
+                    raise ValueError(f"damping must be a scalar or of shape (n_damped_blocks, 3) = ({n_damped}, 3)")
             damping_per_dof = True
-            if n_damped and tuple(d.shape[-2:]) != (n_damped, 3):
-                raise ValueError(f"damping must be a scalar or of shape (n_damped_blocks, 3) = ({n_damped}, 3)")
         n_entries += n
         if n_damped:
             leaves["damping"] = d

@@ -213,9 +213,9 @@ class OptimizationProblem:
                              upper_bound: Optional[float] = None):
         """Batched counterpart of `run_optimization_nlopt` without the angle / edge-length constraints: MMA, objective
         maximised, `n_iterations` evaluations per instance (`opt.set_maxeval`), scalar box bounds."""
-        x0 = self.flatten(initial_guesses)
-        if self.forward_problem.geometry is None:
+        if self.forward_problem.geometry is None:  # flatten() reads the design shapes of the lowered geometry
             self.forward_problem.lower()
+        x0 = self.flatten(initial_guesses)
         opt = BatchedMMA(self.objective_and_grad, x0, lower_bound, upper_bound, maximize=True)
         best_x, best_f = opt.run(n_iterations)
         self.objective_values = [h.numpy() for h in opt.history]

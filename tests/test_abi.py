@@ -70,3 +70,28 @@ def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
     sizes = dict(line.split() for line in subprocess.check_output([str(exe)], text=True).splitlines())
     for n in names:
         assert int(sizes[n]) == C.sizeof(getattr(_abi, n)), n
+
+
+def test_jax_ffi_shim_type_checks_against_the_ffi_surface():
+    """difflexmm_b200/csrc/jax_ffi_shim.cc (the XLA FFI handlers of the C ABI) cannot be built here -- no jaxlib headers --
+    but it must at least be valid C++ against the FFI surface it uses: tests/stubs/xla/ffi/api/ffi.h mirrors that surface
+    and its handler macro refuses bindings whose context / attribute / argument / result types do not match the
+    implementation's signature.  A deliberately broken binding must be rejected (the check has teeth)."""
+    import subprocess
+    import tempfile
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    shim = os.path.join(root, "difflexmm_b200", "csrc", "jax_ffi_shim.cc")
+    cmd = ["g++", "-std=c++17", "-fsyntax-only", "-Wall", "-I", os.path.join(root, "tests", "stubs"), "-I", os.path.join(root, "include"),
+           "-I", "/usr/local/cuda/include"]
+    ok = subprocess.run(cmd + [shim], capture_output=True, text=True)
+    assert ok.returncode == 0, ok.stderr[-3000:]
+    src = open(shim).read()
+    bad = src.replace(".Ret<ffi::Buffer<ffi::U8>>());", ".Ret<ffi::Buffer<ffi::F64>>());", 1)
+    assert bad != src
+    with tempfile.NamedTemporaryFile("w", suffix=".cc", delete=False) as f:
+        f.write(bad)
+    try:
+        r = subprocess.run(cmd + [f.name], capture_output=True, text=True)
+    finally:
+        os.unlink(f.name)
+    assert r.returncode != 0 and "static assertion" in r.stderr

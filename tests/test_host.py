@@ -370,3 +370,56 @@ def test_optimization_problem_flatten_unflatten_roundtrip():
         assert torch.equal(xb[1, :int(np.prod(shapes[0]))], batch[0][1].reshape(-1))
     with pytest.raises(ImportError):
         OptimizationProblem(P).run_optimization_nlopt(None, 1)
+
+
+def test_damping_leaf_broadcasts_like_the_reference():
+    """the reference multiplies the damping leaf by ones((n_damped, 3)) (loading.py:93-101), so (3,), (1, 3) and
+    (n_damped, 1) leaves are valid; the lowering hands the kernel the broadcast array, keeps the leaf's own element count
+    in the augmented-state size, and autograd sums the cotangent back to the leaf's shape"""
+    from difflexmm_b200.utils import ContactParams, ControlParams, GeometricalParams, LigamentParams, MechanicalParams
+    P = QuadsFocusing(n1_blocks=8, n2_blocks=7)
+    spec, drive = P.lower()
+    nb = spec.n_blocks
+    bc, cnvf, bonds, refv = P.geometry.get_parametrization()
+    hs, vs = P.initial_design()
+    cnv = cnvf(hs, vs)
+
+    def lower(damping):
+        cp = ControlParams(
+            geometrical_params=GeometricalParams(block_centroids=bc(hs, vs), centroid_node_vectors=cnv),
+            mechanical_params=MechanicalParams(bond_params=LigamentParams(k_stretch=120., k_shear=1.19, k_rot=1.5, reference_vector=refv()),
+                                               density=6.18e-9, damping=damping,
+                                               contact_params=ContactParams(min_angle=-0.26, cutoff_angle=-0.17, k_contact=1.5)),
+            constraint_params=dict(amplitude=7.5, loading_rate=30., input_delay=0.1 / 30))
+        return lower_params(spec, drive, cp, None, "cpu")
+
+    full = torch.rand(nb, 3, dtype=torch.float64)
+    leaves_full, _, dpd_full, aug_full = lower(full)
+    row = torch.tensor([1e-5, 2e-5, 3e-5], dtype=torch.float64, requires_grad=True)
+    leaves_row, _, dpd_row, aug_row = lower(row)
+    assert dpd_full and dpd_row and leaves_row["damping"].shape == (nb, 3)
+    assert torch.equal(leaves_row["damping"], row.detach().expand(nb, 3))
+    assert aug_full - aug_row == 3 * nb - 3  # the leaf counts with its own size
+    leaves_row["damping"].sum().backward()
+    assert torch.allclose(row.grad, torch.full((3,), float(nb), dtype=torch.float64))
+    col = torch.rand(nb, 1, dtype=torch.float64)
+    assert torch.equal(lower(col)[0]["damping"], col.expand(nb, 3))
+    with pytest.raises(ValueError):
+        lower(torch.rand(nb, 2, dtype=torch.float64))
+
+
+def test_run_optimization_mma_lowers_the_problem_first():
+    """a fresh OptimizationProblem (geometry not lowered yet) must reach the point where it needs the CUDA library, not
+    fail on `geometry is None` while flattening the initial guess"""
+    from difflexmm_b200.optimization import OptimizationProblem
+    P = QuadsFocusing(n1_blocks=8, n2_blocks=7)
+    assert P.geometry is None
+    opt = OptimizationProblem(P)
+    x = opt.flatten if False else None  # noqa: F841
+    try:
+        opt.run_optimization_mma(None, 1)
+    except AttributeError as e:  # 'NoneType' object has no attribute 'design_shapes' was the bug
+        assert "design_shapes" not in str(e), e
+    except Exception:
+        pass
+    assert P.geometry is not None

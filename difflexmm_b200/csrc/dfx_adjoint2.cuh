@@ -975,7 +975,7 @@ __global__ void __launch_bounds__(TT, 1) adjoint2_kernel(const __grid_constant__
           s_cur = s_cur + h;
         }
         const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
-        const double factor = fmin(10.0, fmax(pow(ratio, -0.2) * 0.9, dfactor));
+        const double factor = fmin(10.0, fmax(inv_fifth_root(ratio) * 0.9, dfactor));
         h = (ratio == 0.0) ? h * 10.0 : h * factor;
         __syncthreads();
         if (interval_done) {

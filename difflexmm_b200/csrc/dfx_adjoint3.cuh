@@ -292,18 +292,6 @@ __device__ __forceinline__ void scal_totals_warp(const double* accb, int which, 
     for (int m = 0; m < 5; ++m) out[m] += __shfl_xor_sync(0xffffffffu, out[m], o);
   }
 }
-// ratio^(-1/5) for the step-size controller: float estimate + two Newton steps on y^-5 = r (y <- y (6 - r y^5) / 5), ~1 ulp
-__device__ __forceinline__ double inv_fifth_root(double r) {
-  if (!(r > 1e-30)) return 1e6;  // the controller clamps the factor to 10
-  double y = (double)__powf((float)r, -0.2f);
-#pragma unroll
-  for (int it = 0; it < 2; ++it) {
-    const double y2 = y * y, y5 = y2 * y2 * y;
-    y = y * fma(-r, y5, 6.0) * 0.2;
-  }
-  return y;
-}
-
 // bond role, the modes that occur once per step or per interval (0, 2, 6, 7); out of line to keep the bond phase lean
 static __device__ __noinline__ double bond_quad_rare_nl(int mode, const QC& c, const Tableau& tab, double* qg, double* bq, double qb0,
                                                         double qb1) {
@@ -1104,11 +1092,17 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       }
       __syncthreads();
       // initial_step_size over the whole augmented vector
-#pragma unroll 1
-      for (int e = 0; e < NE3; ++e) {
-        const double q0 = __ldcg(&qg[(long long)(par * NE3 + e) * TT]), k1 = __ldcg(&qg[(long long)((2 + par) * NE3 + e) * TT]);
-        const double s = atol + fabs(q0) * rtol;
-        sd0 += (q0 / s) * (q0 / s); sd1 += (k1 / s) * (k1 / s);
+      {
+        double q0v[NE3], k1v[NE3];  // all loads in flight together (one L2 round trip instead of twelve)
+#pragma unroll
+        for (int e = 0; e < NE3; ++e) {
+          q0v[e] = __ldcg(&qg[(long long)(par * NE3 + e) * TT]); k1v[e] = __ldcg(&qg[(long long)((2 + par) * NE3 + e) * TT]);
+        }
+#pragma unroll
+        for (int e = 0; e < NE3; ++e) {
+          const double is = rcp_pos(atol + fabs(q0v[e]) * rtol);
+          sd0 = fma(q0v[e] * is, q0v[e] * is, sd0); sd1 = fma(k1v[e] * is, k1v[e] * is, sd1);
+        }
       }
       if (tid < NSCAL) {
         const double s = atol + fabs(Sq0[tid]) * rtol;

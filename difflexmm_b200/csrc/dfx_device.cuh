@@ -214,6 +214,18 @@ __device__ __forceinline__ void sincos_fast(double x, double* sn, double* cs) {
   *sn = (n & 2) ? -ss : ss;
   *cs = ((n + 1) & 2) ? -cc : cc;
 }
+// ratio^(-1/5) for the step-size controller: float estimate + two Newton steps on y^-5 = r (y <- y (6 - r y^5) / 5), ~1 ulp
+__device__ __forceinline__ double inv_fifth_root(double r) {
+  if (!(r > 1e-30)) return 1e6;  // the controller clamps the factor to 10
+  double y = (double)__powf((float)r, -0.2f);
+#pragma unroll
+  for (int it = 0; it < 2; ++it) {
+    const double y2 = y * y, y5 = y2 * y2 * y;
+    y = y * fma(-r, y5, 6.0) * 0.2;
+  }
+  return y;
+}
+
 // 1/sqrt(x) for positive normal x: hardware approximation + two Newton steps
 __device__ __forceinline__ double rsqrt_pos(double x) {
   double r;

@@ -373,7 +373,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
           if (it >= a.n_t) running = false;
         }
         const double dfactor = ratio < 1.0 ? 1.0 : 0.2;
-        const double factor = fmin(10.0, fmax(pow(ratio, -0.2) * 0.9, dfactor));
+        const double factor = fmin(10.0, fmax(inv_fifth_root(ratio) * 0.9, dfactor));
         dt = (ratio == 0.0) ? dt * 10.0 : dt * factor;
         if (running) {
           if (!(dt > 0.0)) { status |= DFX_STATUS_DT_UNDERFLOW; running = false; }

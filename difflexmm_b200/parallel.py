@@ -37,7 +37,7 @@ def allreduce_sum_(t: torch.Tensor) -> torch.Tensor:
 
 
 def multitask_value_and_grad(task_value_and_grad: Callable, design: Sequence[torch.Tensor], tasks: Sequence,
-                             weights: Sequence[float]):
+                             weights: Sequence[float], timings: dict = None):
     """weights @ [objective(design, task) for task in tasks] and its gradient w.r.t. the shared design.
 
     `task_value_and_grad(design, task, weight) -> (weight*value, [grad of weight*value per design tensor])`
@@ -45,20 +45,39 @@ def multitask_value_and_grad(task_value_and_grad: Callable, design: Sequence[tor
     reference where the cotangent entering each task's odeint backward is `weight_i * d objective_i / d ys`: the
     adjoint solve is adaptive with an absolute tolerance, so scaling its cotangent afterwards is not the same
     computation (the step sequence differs; results agree only to the integration tolerance).
-    Tasks are sharded over the ranks; the partial sums are packed into one flat f64 buffer and all-reduced once."""
+    Tasks are sharded over the ranks; the partial sums are packed into one flat f64 buffer and all-reduced once.
+
+    `timings` (CUDA devices only): a dict that receives `task_events` = [(task index, start, stop)] and
+    `allreduce_events` = (start, stop), torch.cuda.Event pairs recorded on the current stream around every task of this
+    rank and around the collective (read them with `start.elapsed_time(stop)` after a synchronisation)."""
     rank, nranks = world()
     b, e = shard_range(len(tasks), rank, nranks)
     dev = design[0].device
     sizes = [d.numel() for d in design]
     buf = torch.zeros(1 + sum(sizes), dtype=torch.float64, device=dev)
+    timed = timings is not None and dev.type == "cuda"
+
+    def mark():
+        ev = torch.cuda.Event(enable_timing=True)
+        ev.record()
+        return ev
+
+    if timed:
+        timings["task_events"] = []
     for i in range(b, e):
+        t0 = mark() if timed else None
         v, gs = task_value_and_grad(design, tasks[i], weights[i])
         buf[0] += v
         off = 1
         for g, n in zip(gs, sizes):
             buf[off:off + n] += g.reshape(-1).to(torch.float64)
             off += n
+        if timed:
+            timings["task_events"].append((i, t0, mark()))
+    t0 = mark() if timed else None
     allreduce_sum_(buf)
+    if timed:
+        timings["allreduce_events"] = (t0, mark())
     grads, off = [], 1
     for d, n in zip(design, sizes):
         grads.append(buf[off:off + n].reshape(d.shape))

@@ -72,14 +72,47 @@ struct Lay {  // shared-memory layout (doubles)
                        END = CTRL + (int)((sizeof(Ctrl) + 7) / 8);
 };
 
+// wide tensor-memory loads: NC consecutive 32-bit columns of the thread's lane with ONE instruction (x2 .. x32)
+template <int NC> __device__ __forceinline__ void tm_ld_cols(uint32_t taddr, uint32_t* r);
+template <> __device__ __forceinline__ void tm_ld_cols<2>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x2.b32 {%0, %1}, [%2];" : "=r"(r[0]), "=r"(r[1]) : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tm_ld_cols<4>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]) : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tm_ld_cols<8>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x8.b32 {%0, %1, %2, %3, %4, %5, %6, %7}, [%8];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]) : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tm_ld_cols<16>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]) : "r"(taddr));
+}
+template <> __device__ __forceinline__ void tm_ld_cols<32>(uint32_t taddr, uint32_t* r) {
+  asm volatile("tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, %16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];" : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]), "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15]), "=r"(r[16]), "=r"(r[17]), "=r"(r[18]), "=r"(r[19]), "=r"(r[20]), "=r"(r[21]), "=r"(r[22]), "=r"(r[23]), "=r"(r[24]), "=r"(r[25]), "=r"(r[26]), "=r"(r[27]), "=r"(r[28]), "=r"(r[29]), "=r"(r[30]), "=r"(r[31]) : "r"(taddr));
+}
+
+// N consecutive slots (doubles) with as few load instructions as possible and one wait
 template <int N>
-__device__ __forceinline__ void tm_ld(uint32_t taddr, double (&out)[N]) {  // N consecutive slots, one wait
-  uint32_t lo[N], hi[N];
+__device__ __forceinline__ void tm_ld(uint32_t taddr, double (&out)[N]) {
+  uint32_t r[2 * N];
+  constexpr int NC = 2 * N;
+  int c = 0;
 #pragma unroll
-  for (int i = 0; i < N; ++i) tmem_ld_issue(taddr + 2 * i, lo[i], hi[i]);
+  for (int w = 32; w >= 2; w >>= 1) {
+#pragma unroll
+    for (int rep_ = 0; rep_ < 2; ++rep_) {
+      if (NC - c >= w) {
+        if (w == 32) tm_ld_cols<32>(taddr + c, r + c);
+        else if (w == 16) tm_ld_cols<16>(taddr + c, r + c);
+        else if (w == 8) tm_ld_cols<8>(taddr + c, r + c);
+        else if (w == 4) tm_ld_cols<4>(taddr + c, r + c);
+        else tm_ld_cols<2>(taddr + c, r + c);
+        c += w;
+      }
+    }
+  }
   tmem_ld_wait();
 #pragma unroll
-  for (int i = 0; i < N; ++i) { tmem_pin(lo[i], hi[i]); out[i] = __hiloint2double(hi[i], lo[i]); }
+  for (int i = 0; i < N; ++i) { tmem_pin(r[2 * i], r[2 * i + 1]); out[i] = __hiloint2double(r[2 * i + 1], r[2 * i]); }
 }
 template <int N>
 __device__ __forceinline__ void tm_lds(uint32_t taddr, int stride, double (&out)[N]) {  // N slots `stride` apart, one wait
@@ -119,23 +152,16 @@ __device__ __forceinline__ void stage_P(uint32_t ta, const Tableau& tab, double 
 template <int ST, int L0, int L1>
 __device__ __forceinline__ void acc_D(uint32_t ta, const Tableau& tab, double (&alu)[3], double (&alv)[3]) {
   constexpr int N = 3 * (L1 - L0 + 1);
-  uint32_t lo[2 * N], hi[2 * N];
-#pragma unroll
-  for (int q = 0; q < N; ++q) {
-    tmem_ld_issue(ta + 2 * (D_KLU + 3 * L0 + q), lo[q], hi[q]);
-    tmem_ld_issue(ta + 2 * (D_KLV + 3 * L0 + q), lo[N + q], hi[N + q]);
-  }
-  tmem_ld_wait();
-#pragma unroll
-  for (int q = 0; q < 2 * N; ++q) tmem_pin(lo[q], hi[q]);
+  double ku[N], kw[N];
+  tm_ld<N>(ta + 2 * (D_KLU + 3 * L0), ku);
+  tm_ld<N>(ta + 2 * (D_KLV + 3 * L0), kw);
 #pragma unroll
   for (int l = L0; l <= L1; ++l) {
     const double b = tab.beta[ST][l];
 #pragma unroll
     for (int j = 0; j < 3; ++j) {
-      const int q = 3 * (l - L0) + j;
-      alu[j] = fma(b, __hiloint2double(hi[q], lo[q]), alu[j]);
-      alv[j] = fma(b, __hiloint2double(hi[N + q], lo[N + q]), alv[j]);
+      alu[j] = fma(b, ku[3 * (l - L0) + j], alu[j]);
+      alv[j] = fma(b, kw[3 * (l - L0) + j], alv[j]);
     }
   }
 }
@@ -1183,17 +1209,17 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       const double xq = C->x, s_cur = C->s_cur;
       double y1a[3], y1b[3];  // P: u, v at the end of the step; D: lambda_u, lambda_v
       if (!isD) {
-        double y0[6];
+        double y0[6], kvh[21];  // the whole velocity-derivative history with two wide loads
         tm_ld<6>(ta + 2 * P_U0, y0);
+        tm_ld<21>(ta + 2 * P_KV, kvh);
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
-          double kv[7];
-          tm_lds<7>(ta + 2 * (P_KV + j), 3, kv);
           double eu = 0.0, evv = 0.0, su = 0.0, sv = 0.0;
 #pragma unroll
           for (int l = 0; l < 7; ++l) {
-            eu = fma(tab.e2[l], kv[l], eu); evv = fma(tab.c_err[l], kv[l], evv);
-            su = fma(tab.s2[l], kv[l], su); sv = fma(tab.c_sol[l], kv[l], sv);
+            const double kvl = kvh[3 * l + j];
+            eu = fma(tab.e2[l], kvl, eu); evv = fma(tab.c_err[l], kvl, evv);
+            su = fma(tab.s2[l], kvl, su); sv = fma(tab.c_sol[l], kvl, sv);
           }
           y1a[j] = y0[j] - h * (tab.sum_sol * y0[3 + j] + h * su);
           y1b[j] = y0[3 + j] + h * sv;
@@ -1209,23 +1235,21 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         double y0[6];
         tm_ld<6>(ta + 2 * D_LU0, y0);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) {
-          double klu[7], klv[7];
-          tm_lds<7>(ta + 2 * (D_KLU + j), 3, klu);
-          tm_lds<7>(ta + 2 * (D_KLV + j), 3, klv);
-          double elu = 0.0, elv = 0.0, slu = 0.0, slv = 0.0;
+        for (int q = 0; q < 2; ++q) {  // lambda_u then lambda_v: one wide load of the 7 x 3 history each
+          double kh[21];
+          tm_ld<21>(ta + 2 * (q == 0 ? D_KLU : D_KLV), kh);
 #pragma unroll
-          for (int l = 0; l < 7; ++l) {
-            elu = fma(tab.c_err[l], klu[l], elu); elv = fma(tab.c_err[l], klv[l], elv);
-            slu = fma(tab.c_sol[l], klu[l], slu); slv = fma(tab.c_sol[l], klv[l], slv);
-          }
-          y1a[j] = y0[j] + h * slu;
-          y1b[j] = y0[3 + j] + h * slv;
-          elu *= h; elv *= h;
-          if (is_free(j)) {
-            const double r2 = elu / (atol + rtol * fmax(fabs(y0[j]), fabs(y1a[j])));
-            const double r3 = elv / (atol + rtol * fmax(fabs(y0[3 + j]), fabs(y1b[j])));
-            se += r2 * r2 + r3 * r3;
+          for (int j = 0; j < 3; ++j) {
+            double el = 0.0, sl = 0.0;
+#pragma unroll
+            for (int l = 0; l < 7; ++l) { el = fma(tab.c_err[l], kh[3 * l + j], el); sl = fma(tab.c_sol[l], kh[3 * l + j], sl); }
+            const double y0q = y0[3 * q + j], y1q = y0q + h * sl;
+            if (q == 0) y1a[j] = y1q; else y1b[j] = y1q;
+            el *= h;
+            if (is_free(j)) {
+              const double r = el / (atol + rtol * fmax(fabs(y0q), fabs(y1q)));
+              se += r * r;
+            }
           }
         }
       }

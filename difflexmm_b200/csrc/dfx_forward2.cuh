@@ -263,14 +263,29 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
     } else {
       const double ha = dt * tab.alpha[ev], h2 = dt * dt;
       double au[3] = {0, 0, 0}, av[3] = {0, 0, 0};
-#pragma unroll 1
-      for (int l = 0; l <= ev; ++l) {
-        const double b = tab.beta[ev][l], b2 = tab.a2[ev][l];
-        double kv[3];
-        tp.template ldn_below<21, 3>(F_KV + 3 * l, 1, kv);
+      // history stages 0..ev with compile-time tableau indices (constant-bank operands) and one TMEM wait per three stages
+      auto acc = [&](auto st_tag, auto l0_tag, auto l1_tag) {
+        constexpr int ST = decltype(st_tag)::value, L0 = decltype(l0_tag)::value, L1 = decltype(l1_tag)::value;
+        double kv[3 * (L1 - L0 + 1)];
+        tp.template ldn_below<21, 3 * (L1 - L0 + 1)>(F_KV + 3 * L0, 1, kv);
 #pragma unroll
-        for (int j = 0; j < 3; ++j) { au[j] = fma(b2, kv[j], au[j]); av[j] = fma(b, kv[j], av[j]); }
+        for (int l = L0; l <= L1; ++l) {
+          const double b = tab.beta[ST][l], b2 = tab.a2[ST][l];
+#pragma unroll
+          for (int j = 0; j < 3; ++j) { au[j] = fma(b2, kv[3 * (l - L0) + j], au[j]); av[j] = fma(b, kv[3 * (l - L0) + j], av[j]); }
+        }
+      };
+      using std::integral_constant;
+#define DFX_F2_ACC(ST, L0, L1) acc(integral_constant<int, ST>{}, integral_constant<int, L0>{}, integral_constant<int, L1>{})
+      switch (ev) {
+        case 0: DFX_F2_ACC(0, 0, 0); break;
+        case 1: DFX_F2_ACC(1, 0, 1); break;
+        case 2: DFX_F2_ACC(2, 0, 2); break;
+        case 3: DFX_F2_ACC(3, 0, 2); DFX_F2_ACC(3, 3, 3); break;
+        case 4: DFX_F2_ACC(4, 0, 2); DFX_F2_ACC(4, 3, 4); break;
+        default: DFX_F2_ACC(5, 0, 2); DFX_F2_ACC(5, 3, 5); break;
       }
+#undef DFX_F2_ACC
       double y0[6];
       tp.template ldn<6>(F_U0, 1, y0);
 #pragma unroll

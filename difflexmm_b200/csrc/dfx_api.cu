@@ -422,6 +422,9 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   cudaFuncSetAttribute(forward2_kernel<42, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(forward2_kernel<0, 512, 1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(forward2_kernel<42, 384, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(forward2_kernel<42, 384, 2, F_NSLOT - 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes / 2 - 1024);
+  cudaFuncSetAttribute(forward2_kernel<42, 384, 2, F_NSLOT - 42>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
+  cudaFuncSetAttribute(forward2_kernel<42, 512, 1, F_NSLOT - 42>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
   cudaFuncSetAttribute(forward2_kernel<0, 384, 2>, cudaFuncAttributePreferredSharedMemoryCarveout, 100);
   cudaFuncSetAttribute(adjoint_kernel<0>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes);
   cudaFuncSetAttribute(adjoint2_kernel<84, 32, 384>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)kSmemBytes - 1024);
@@ -522,8 +525,10 @@ int dfx_forward(const DfxTopology* t, const DfxParams* params, int batch, const 
     A2.ns_slots = fp.ns;
     A2.tmem_cols_per_warp = fp.cols_per_warp;
     A2.tmem_cols_alloc = fp.cols_alloc;
-    if (fp.threads == 384 && fp.nt == 42) forward2_kernel<42, 384, 2><<<batch, 384, fp.smem, stream>>>(A2);
+    if (fp.threads == 384 && fp.nt == 42 && fp.ns == F_NSLOT - 42) forward2_kernel<42, 384, 2, F_NSLOT - 42><<<batch, 384, fp.smem, stream>>>(A2);
+    else if (fp.threads == 384 && fp.nt == 42) forward2_kernel<42, 384, 2><<<batch, 384, fp.smem, stream>>>(A2);
     else if (fp.threads == 384) forward2_kernel<0, 384, 2><<<batch, 384, fp.smem, stream>>>(A2);
+    else if (fp.nt == 42 && fp.ns == F_NSLOT - 42) forward2_kernel<42, 512, 1, F_NSLOT - 42><<<batch, 512, fp.smem, stream>>>(A2);
     else if (fp.nt == 42) forward2_kernel<42, 512, 1><<<batch, 512, fp.smem, stream>>>(A2);
     else forward2_kernel<0, 512, 1><<<batch, 512, fp.smem, stream>>>(A2);
   } else {

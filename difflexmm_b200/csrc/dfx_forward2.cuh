@@ -25,8 +25,10 @@ struct Fwd2Args {
   int ns_slots, tmem_cols_per_warp, tmem_cols_alloc;
 };
 
-template <int NT, int TT, int CTAS>
-__global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
+// NS >= 0: the number of thread-private slots in shared memory is a compile-time constant (the tier tests of the store
+// disappear); NS < 0: read from the launch arguments.
+template <int NT, int TT, int CTAS, int NS = -1>
+__global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const __grid_constant__ Fwd2Args A) {
   extern __shared__ double smem[];
   __shared__ uint32_t tmem_base_sh;
   const FwdArgs& a = A.a;
@@ -56,7 +58,7 @@ __global__ void __launch_bounds__(TT, CTAS) forward2_kernel(const Fwd2Args A) {
     __syncthreads();
     asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
   }
-  TP<NT, -1, TT> tp;
+  TP<NT, NS, TT> tp;
   tp.ns = A.ns_slots;
   tp.s = tp_s + tid;
   tp.g = a.scratch + (long long)design * A.tp_scratch_per_design + tid;

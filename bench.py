@@ -54,21 +54,49 @@ def flops_model(spec, aug_size, n_t, fwd_steps, bwd_steps):
 
 
 class ClockSampler:
-    """nvidia-smi clocks / throttle reasons during the timed region (B200_PROFILING.md clocks line)."""
+    """SM clock, power and throttle reasons during the timed region (B200_PROFILING.md clocks line), sampled every 0.2 s
+    through NVML inside this process.  (Spawning `nvidia-smi` five times a second stalled CUDA API calls of the timed
+    end-to-end steps by hundreds of milliseconds now and then -- the unexplained outliers of round 1; nvidia-smi remains
+    the fallback when the NVML binding is missing.)"""
 
     def __init__(self, index):
         self.rows, self._stop, self.index = [], threading.Event(), index
         self._t = threading.Thread(target=self._run, daemon=True)
+        self._nvml = None
+        try:
+            import pynvml
+            pynvml.nvmlInit()
+            # CUDA_VISIBLE_DEVICES renumbers CUDA devices, NVML does not: map through the UUID-free common case
+            vis = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
+            self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+            self.source = "nvml"
+        except Exception:
+            self.source = "nvidia-smi"
+
+    def _sample_nvml(self):
+        n = self._nvml
+        sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
+        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
+        pw = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
+        flag = lambda bit: "Active" if r & bit else "Not Active"  # noqa: E731
+        return [str(sm), str(mx), f"{pw:.1f}", flag(n.nvmlClocksEventReasonHwSlowdown), flag(n.nvmlClocksEventReasonHwThermalSlowdown),
+                flag(n.nvmlClocksEventReasonSwThermalSlowdown), flag(n.nvmlClocksEventReasonSwPowerCap)]
 
     def _run(self):
         q = ("clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
              "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap")
         while not self._stop.is_set():
             try:
-                out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
-                                     capture_output=True, text=True, timeout=5).stdout.strip()
-                if out:
-                    self.rows.append([x.strip() for x in out.split(",")])
+                if self._nvml is not None:
+                    self.rows.append(self._sample_nvml())
+                else:
+                    out = subprocess.run(["nvidia-smi", f"--id={self.index}", f"--query-gpu={q}", "--format=csv,noheader,nounits"],
+                                         capture_output=True, text=True, timeout=5).stdout.strip()
+                    if out:
+                        self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
             self._stop.wait(0.2)
@@ -90,7 +118,7 @@ class ClockSampler:
                 if v.lower().startswith("active"):
                     reasons.add(name)
         return {"sm_mhz": float(np.median(sm)) if sm else None, "sm_max_mhz": max(mx) if mx else None,
-                "reasons": sorted(reasons), "samples": len(self.rows)}
+                "reasons": sorted(reasons), "samples": len(self.rows), "source": self.source}
 
 
 HORIZON_SCALE = 1.0  # < 1 only for profiling runs (ncu replays every launch dozens of times)

@@ -75,6 +75,12 @@ class DfxGeometryDesc(C.Structure):
                 ("base_nodes", C.c_void_p), ("node_design", C.c_void_p)]
 
 
+class DfxConstraintDesc(C.Structure):
+    _fields_ = [("n_bonds", C.c_int32), ("bonds", C.c_void_p), ("n_boundary", C.c_int32), ("boundary_nodes", C.c_void_p),
+                ("angles", C.c_int32), ("edges", C.c_int32),
+                ("min_void_angle", C.c_double), ("min_block_angle", C.c_double), ("min_edge_length", C.c_double)]
+
+
 DFX_OBJ_KINETIC, DFX_OBJ_ANGULAR = 0, 1
 
 

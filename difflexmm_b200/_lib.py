@@ -40,7 +40,9 @@ lib.dfx_adjoint_plan.restype = C.c_char_p
 EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free", "dfx_drive_n_params",
            "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
            "dfx_expand_fields", "dfx_objective", "dfx_adjoint_objective",
-           "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp", "dfx_fp64_peak", "dfx_math_selftest", "dfx_sincos_selftest", "dfx_adjoint_plan", "dfx_last_error", "dfx_version")
+           "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp",
+           "dfx_constraints_create", "dfx_constraints_destroy", "dfx_constraints_rows", "dfx_constraints_columns", "dfx_constraints_eval",
+           "dfx_fp64_peak", "dfx_math_selftest", "dfx_sincos_selftest", "dfx_adjoint_plan", "dfx_last_error", "dfx_version")
 
 
 def _check(rc, what):
@@ -80,6 +82,43 @@ class GeometryHandle:
         h, self._h = getattr(self, "_h", None), None
         if h:
             lib.dfx_geometry_destroy(h)
+
+
+class ConstraintsHandle:
+    """Owns one `DfxConstraints*`: angle / edge-length inequality rows of a lattice geometry and their column table."""
+
+    def __init__(self, geo: GeometryHandle, bonds, boundary_nodes, angles, edges, min_void_angle, min_block_angle, min_edge_length):
+        import numpy as np
+        self.geo = geo  # keeps the geometry alive
+        self._bonds = np.ascontiguousarray(bonds, dtype=np.int32).reshape(-1, 2)
+        self._boundary = np.ascontiguousarray(boundary_nodes if boundary_nodes is not None else [], dtype=np.int32).reshape(-1)
+        desc = _abi.DfxConstraintDesc(len(self._bonds), self._bonds.ctypes.data, len(self._boundary),
+                                      self._boundary.ctypes.data if len(self._boundary) else None, int(bool(angles)), int(bool(edges)),
+                                      float(min_void_angle), float(min_block_angle), float(min_edge_length))
+        self._h = C.c_void_p()
+        _check(lib.dfx_constraints_create(geo._h, C.byref(desc), C.byref(self._h)), "dfx_constraints_create")
+        n_angle = C.c_int32(0)
+        self.n_rows = int(lib.dfx_constraints_rows(self._h, C.byref(n_angle)))
+        self.n_angle_rows = int(n_angle.value)
+        self.columns = np.empty((self.n_rows, 4), dtype=np.int32)
+        _check(lib.dfx_constraints_columns(self._h, C.c_void_p(self.columns.ctypes.data)), "dfx_constraints_columns")
+
+    def __del__(self):
+        h, self._h = getattr(self, "_h", None), None
+        if h:
+            lib.dfx_constraints_destroy(h)
+
+
+def constraints_eval(con: ConstraintsHandle, design, want_jacobian=True):
+    """design (B, n_design, 2) -> values (B, rows), jac (B, rows, 4, 2) or None: one launch for the whole batch"""
+    dev, B = design.device, design.shape[0]
+    design = design.contiguous()
+    values = torch.empty((B, con.n_rows), dtype=torch.float64, device=dev)
+    jac = torch.empty((B, con.n_rows, 4, 2), dtype=torch.float64, device=dev) if want_jacobian else None
+    with torch.cuda.device(dev):
+        _check(lib.dfx_constraints_eval(con._h, B, C.c_void_p(design.data_ptr()), C.c_void_p(values.data_ptr()),
+                                        C.c_void_p(jac.data_ptr() if jac is not None else None), _stream_ptr(dev)), "dfx_constraints_eval")
+    return values, jac
 
 
 def geometry_forward(geo: GeometryHandle, design, density):

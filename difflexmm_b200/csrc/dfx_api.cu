@@ -846,6 +846,111 @@ int dfx_geometry_vjp(const DfxGeometry* g, int batch, const double* design, cons
 
 }  // extern "C"
 
+// ---- design constraints (dfx_geometry.cuh) -----------------------------------------------------------------------
+struct DfxConstraints {
+  const DfxGeometry* geo;
+  int m, m_angle;
+  ConstraintRow* rows;         // device
+  std::vector<int32_t> cols;   // host, [m][4]
+};
+
+extern "C" {
+
+int dfx_constraints_create(const DfxGeometry* g, const DfxConstraintDesc* d, DfxConstraints** out) {
+  if (!g || !d || !out) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (d->n_bonds < 0 || d->n_boundary < 0 || (d->n_bonds > 0 && !d->bonds) || (d->n_boundary > 0 && !d->boundary_nodes))
+    return fail(DFX_ERR_INVALID, "bad constraint tables");
+  const int npb = g->dev.n_npb, nn = g->dev.n_nodes;
+  std::vector<int> nd(nn);
+  int cur = 0;
+  cudaGetDevice(&cur);
+  if (cudaSetDevice(g->device) != cudaSuccess) return fail(DFX_ERR_CUDA, "cudaSetDevice(%d) failed", g->device);
+  cudaError_t e = cudaMemcpy(nd.data(), g->dev.node_design, nn * sizeof(int), cudaMemcpyDeviceToHost);
+  if (e != cudaSuccess) { cudaSetDevice(cur); return fail(DFX_ERR_CUDA, "constraint table download failed: %s", cudaGetErrorString(e)); }
+  auto next = [&](int n) { return (n / npb) * npb + (n % npb + 1) % npb; };
+  auto prev = [&](int n) { return (n / npb) * npb + (n % npb + npb - 1) % npb; };
+  std::vector<ConstraintRow> rows;
+  std::vector<int32_t> cols;
+  auto add = [&](int p0, int p1, int q0, int q1, double minimum) {
+    ConstraintRow R;
+    R.p0 = p0; R.p1 = p1; R.q0 = q0; R.q1 = q1; R.minimum = minimum;
+    const int v[4] = {p0, p1, q0, q1};
+    int32_t c[4] = {-1, -1, -1, -1};
+    int used = 0;
+    for (int s = 0; s < 4; ++s) {
+      const int col = v[s] >= 0 ? nd[v[s]] : -1;
+      R.slot[s] = -1;
+      if (col < 0) continue;
+      int t = 0;
+      while (t < used && c[t] != col) ++t;  // vertices fed by the same design 2-vector share one Jacobian slot
+      if (t == used) c[used++] = col;
+      R.slot[s] = t;
+    }
+    rows.push_back(R);
+    cols.insert(cols.end(), c, c + 4);
+  };
+  for (int b = 0; b < d->n_bonds; ++b)
+    for (int k = 0; k < 2; ++k)
+      if (d->bonds[2 * b + k] < 0 || d->bonds[2 * b + k] >= nn) { cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "bond %d: node id out of range", b); }
+  for (int i = 0; i < d->n_boundary; ++i)
+    if (d->boundary_nodes[i] < 0 || d->boundary_nodes[i] >= nn) { cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "boundary node %d out of range", i); }
+  if (d->angles) {
+    // compute_edge_angles (geometry.py:234-253): e1 = next - here, e2 = previous - here of each bond node
+    for (int b = 0; b < d->n_bonds; ++b) { const int n1 = d->bonds[2 * b], n2 = d->bonds[2 * b + 1]; add(n2, prev(n2), n1, next(n1), d->min_void_angle); }
+    for (int b = 0; b < d->n_bonds; ++b) { const int n1 = d->bonds[2 * b], n2 = d->bonds[2 * b + 1]; add(n1, prev(n1), n2, next(n2), d->min_void_angle); }
+    for (int b = 0; b < d->n_bonds; ++b) { const int n1 = d->bonds[2 * b]; add(n1, next(n1), n1, prev(n1), d->min_block_angle); }
+    for (int b = 0; b < d->n_bonds; ++b) { const int n2 = d->bonds[2 * b + 1]; add(n2, next(n2), n2, prev(n2), d->min_block_angle); }
+    for (int i = 0; i < d->n_boundary; ++i) { const int n = d->boundary_nodes[i]; add(n, next(n), n, prev(n), d->min_block_angle); }
+  }
+  const int m_angle = (int)rows.size();
+  if (d->edges)  // compute_edge_lengths (geometry.py:205-218): |vertex[l-1] - vertex[l]|
+    for (int n = 0; n < nn; ++n) add(n, prev(n), -1, -1, d->min_edge_length);
+  if (rows.empty()) { cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "no constraint rows requested"); }
+  DfxConstraints* h = new (std::nothrow) DfxConstraints();
+  if (!h) { cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "out of host memory"); }
+  h->geo = g; h->m = (int)rows.size(); h->m_angle = m_angle; h->rows = nullptr; h->cols = std::move(cols);
+  e = upload(rows, &h->rows);
+  cudaSetDevice(cur);
+  if (e != cudaSuccess) { delete h; return fail(DFX_ERR_CUDA, "constraint table upload failed: %s", cudaGetErrorString(e)); }
+  *out = h;
+  return DFX_OK;
+}
+
+void dfx_constraints_destroy(DfxConstraints* h) {
+  if (!h) return;
+  int cur = 0;
+  cudaGetDevice(&cur);
+  cudaSetDevice(h->geo->device);
+  if (h->rows) cudaFree(h->rows);
+  cudaSetDevice(cur);
+  delete h;
+}
+
+int dfx_constraints_rows(const DfxConstraints* h, int32_t* n_angle_rows) {
+  if (!h) return -1;
+  if (n_angle_rows) *n_angle_rows = h->m_angle;
+  return h->m;
+}
+
+int dfx_constraints_columns(const DfxConstraints* h, int32_t* cols) {
+  if (!h || !cols) return fail(DFX_ERR_INVALID, "NULL argument");
+  std::copy(h->cols.begin(), h->cols.end(), cols);
+  return DFX_OK;
+}
+
+int dfx_constraints_eval(const DfxConstraints* h, int batch, const double* design, double* values, double* jac, void* stream_) {
+  if (!h || !design || !values) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (batch <= 0) return fail(DFX_ERR_INVALID, "batch must be positive");
+  const int threads = 128;
+  dim3 grid((h->m + threads - 1) / threads, batch);
+  constraints_kernel<<<grid, threads, 0, (cudaStream_t)stream_>>>(h->geo->dev, h->rows, h->m, design, values, jac);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "constraints launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
+
+}  // extern "C"
+
 // ---- field reconstruction (dynamics.py:129-136, 169-182 without the dense Jacobian) ------------
 namespace {
 __global__ void expand_fields_kernel(DevTopo T, DfxLeaf drive, const double* ys, const double* ts, long long ts_bstride, int n_t,

@@ -150,3 +150,74 @@ __global__ void geometry_vjp_kernel(DevGeometry G, const double* design, const d
 }
 
 }  // namespace dfx
+
+// ---- inequality constraints of the design and their sparse Jacobian -------------------------------
+// Reference: OptimizationProblem.setup_angle_constraints / setup_edge_length_constraints
+// (problems/quads_focusing.py:473-544) and the jit(jacobian(...)) the nlopt callbacks evaluate (:585-588, :613-616).
+// Every row is a function of two polygon edges a = v[p1] - v[p0], b = v[q1] - v[q0] of the undeformed lattice
+// (vertex = base + design[node_design]; the polygon centroid cancels in an edge):
+//     angle row:  c = -(mod(atan2(a x b, a . b), 2 pi) - min)      (void angles, block angles, boundary block angles)
+//     edge row:   c = -(|a| - min)
+// so a Jacobian row has at most 4 design 2-vectors: fixed-width rows [4][2] with a shared column table.
+namespace dfx {
+
+struct ConstraintRow {
+  int p0, p1, q0, q1;  // vertex ids; q0 < 0: edge-length row
+  int slot[4];         // Jacobian slot that the gradient w.r.t. (p0, p1, q0, q1) is added to, or -1 (vertex has no design variable)
+  double minimum;
+};
+
+// grid (ceil(m / blockDim), batch)
+__global__ void constraints_kernel(DevGeometry G, const ConstraintRow* rows, int m, const double* design, double* values, double* jac) {
+  const int b = blockIdx.y, r = blockIdx.x * blockDim.x + threadIdx.x;
+  if (r >= m) return;
+  const ConstraintRow R = rows[r];
+  const double* dsg = design + (long long)b * G.n_design * 2;
+  auto vertex = [&](int n, double& x, double& y) {
+    const int d = G.node_design[n];
+    x = G.base_nodes[2 * n] + (d >= 0 ? dsg[2 * d] : 0.0);
+    y = G.base_nodes[2 * n + 1] + (d >= 0 ? dsg[2 * d + 1] : 0.0);
+  };
+  double x0, y0, x1, y1;
+  vertex(R.p0, x0, y0);
+  vertex(R.p1, x1, y1);
+  const double ax = x1 - x0, ay = y1 - y0;
+  double gax, gay, gbx = 0.0, gby = 0.0, c;  // dc/da, dc/db
+  if (R.q0 < 0) {
+    const double len = sqrt(ax * ax + ay * ay);
+    c = -(len - R.minimum);
+    gax = -ax / len;
+    gay = -ay / len;
+  } else {
+    double u0, v0, u1, v1;
+    vertex(R.q0, u0, v0);
+    vertex(R.q1, u1, v1);
+    const double bx = u1 - u0, by = v1 - v0;
+    double phi = atan2(ax * by - ay * bx, ax * bx + ay * by);
+    const double two_pi = 6.283185307179586476925286766559;
+    phi = phi - two_pi * floor(phi / two_pi);  // jnp.mod(phi, 2 pi)
+    c = -(phi - R.minimum);
+    const double ia = 1.0 / (ax * ax + ay * ay), ib = 1.0 / (bx * bx + by * by);
+    gax = -ay * ia;  // -d phi / d a,  d phi / d a = (a_y, -a_x) / |a|^2
+    gay = ax * ia;
+    gbx = by * ib;   // -d phi / d b,  d phi / d b = (-b_y, b_x) / |b|^2
+    gby = -bx * ib;
+  }
+  values[(long long)b * m + r] = c;
+  if (jac) {
+    double out[4][2] = {{0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}, {0.0, 0.0}};
+    const double gx[4] = {-gax, gax, -gbx, gbx}, gy[4] = {-gay, gay, -gby, gby};
+#pragma unroll
+    for (int s = 0; s < 4; ++s) {
+      const int t = R.slot[s];
+#pragma unroll
+      for (int k = 0; k < 4; ++k)
+        if (t == k) { out[k][0] += gx[s]; out[k][1] += gy[s]; }
+    }
+    double* o = jac + ((long long)b * m + r) * 8;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) { o[2 * k] = out[k][0]; o[2 * k + 1] = out[k][1]; }
+  }
+}
+
+}  // namespace dfx

@@ -91,3 +91,49 @@ class DeviceGeometry:
         if not batched:
             return cnv[0], cen[0], inertia[0]
         return cnv, cen, inertia
+
+
+class DeviceConstraints:
+    """Angle and edge-length inequality constraints of a lattice design (`<= 0` when satisfied) with their sparse
+    Jacobian, one kernel launch per batch of designs (libdfx `dfx_constraints_eval`; reference
+    `problems/quads_focusing.py:473-544` and the `jit(jacobian(...))` of the nlopt callbacks, `:585-588, :613-616`).
+
+    Rows: the reference's `angle_constraints` rows (when both `min_void_angle` and `min_block_angle` are given, as in
+    `run_optimization_nlopt`), then its `edge_length_constraints` rows (when `min_edge_length` is given).  A row depends
+    on at most 4 design 2-vectors: `jac[b, row, slot, xy]` belongs to the flat design variable `2 * columns[row, slot] + xy`
+    (flat design = the design arrays concatenated, as in `DeviceGeometry.flatten`); `columns < 0` marks an empty slot."""
+
+    def __init__(self, device_geometry: DeviceGeometry, min_void_angle=None, min_block_angle=None, min_edge_length=None,
+                 boundary_angle_constraint=False):
+        from . import _lib
+        geometry = device_geometry.geometry
+        angles = min_void_angle is not None and min_block_angle is not None
+        edges = min_edge_length is not None
+        if not angles and not edges:
+            raise ValueError("no constraint requested (give min_void_angle and min_block_angle, and / or min_edge_length)")
+        boundary = None
+        if angles and boundary_angle_constraint:
+            from .optimization import quad_boundary_node_ids
+            boundary = quad_boundary_node_ids(geometry.n1_blocks, geometry.n2_blocks)
+        self.dg = device_geometry
+        self.handle = _lib.ConstraintsHandle(device_geometry.handle, np.asarray(geometry.bond_connectivity()), boundary, angles, edges,
+                                             min_void_angle if angles else 0.0, min_block_angle if angles else 0.0,
+                                             min_edge_length if edges else 0.0)
+        self.n_rows, self.n_angle_rows = self.handle.n_rows, self.handle.n_angle_rows
+        self.columns = torch.from_numpy(self.handle.columns.astype(np.int64)).to(device_geometry.device)
+        # flat scalar column of every Jacobian entry; empty slots point at column 0 and carry exact zeros
+        col = self.columns.clamp_min(0)
+        self.scalar_columns = torch.stack([2 * col, 2 * col + 1], dim=-1).reshape(self.n_rows, 8)
+
+    def __call__(self, design_flat, want_jacobian=True):
+        """design_flat (B, n_design, 2) or (B, 2 n_design) on the device -> values (B, rows), jac (B, rows, 4, 2) | None"""
+        from . import _lib
+        x = torch.as_tensor(design_flat, dtype=_F64, device=self.dg.device).reshape(-1, self.dg.n_design, 2)
+        return _lib.constraints_eval(self.handle, x, want_jacobian)
+
+    def dense_jacobian(self, jac):
+        """(B, rows, 4, 2) -> (B, rows, 2 n_design) (tests, small lattices)"""
+        B = jac.shape[0]
+        out = torch.zeros((B, self.n_rows, 2 * self.dg.n_design), dtype=_F64, device=jac.device)
+        out.scatter_add_(2, self.scalar_columns.expand(B, -1, -1), jac.reshape(B, self.n_rows, 8))
+        return out

@@ -245,6 +245,32 @@ int dfx_geometry_vjp(const DfxGeometry* geo, int batch, const double* design, co
                      const double* inertia_bar /* or NULL */, double* design_bar /*[B][n_design][2]*/,
                      double* density_bar /*[B] or NULL*/, void* stream);
 
+/* ---- inequality constraints of the design and their Jacobian on the device ----------------------
+ * Replaces OptimizationProblem.setup_angle_constraints / setup_edge_length_constraints
+ * (problems/quads_focusing.py:473-544) and the jit(jacobian(...)) evaluated inside the nlopt callbacks (:585-588,
+ * :613-616) for the lattices a DfxGeometry describes.  Rows (all <= 0 when satisfied), in the reference's order:
+ *   angles: -(void_angle_1 - min_void) per bond, -(void_angle_2 - min_void) per bond, -(block_angle_1 - min_block),
+ *           -(block_angle_2 - min_block), then -(block angle - min_block) of each boundary node; angles mod 2 pi
+ *   edges:  -(edge length - min_edge_length) per polygon vertex (edge to the previous vertex), block-major
+ * A row depends on at most 4 design 2-vectors: jac[b][row][slot][xy] with the shared column table
+ * columns[row][slot] = design 2-vector index or -1 (empty slot). */
+typedef struct DfxConstraintDesc {
+  int32_t n_bonds;
+  const int32_t* bonds;           /* host, [n_bonds][2] node ids */
+  int32_t n_boundary;
+  const int32_t* boundary_nodes;  /* host, [n_boundary] or NULL */
+  int32_t angles, edges;          /* which row families to build */
+  double min_void_angle, min_block_angle, min_edge_length;
+} DfxConstraintDesc;
+typedef struct DfxConstraints DfxConstraints;
+
+int dfx_constraints_create(const DfxGeometry* geo, const DfxConstraintDesc* desc, DfxConstraints** out); /* geo must outlive it */
+void dfx_constraints_destroy(DfxConstraints* con);
+int dfx_constraints_rows(const DfxConstraints* con, int32_t* n_angle_rows /* or NULL */); /* -> number of rows */
+int dfx_constraints_columns(const DfxConstraints* con, int32_t* columns /* host, [rows][4] */);
+int dfx_constraints_eval(const DfxConstraints* con, int batch, const double* design /*[B][n_design][2]*/,
+                         double* values /*[B][rows]*/, double* jac /*[B][rows][4][2] or NULL*/, void* stream);
+
 /* fields[b][i][0][blk][dof] = displacement, fields[b][i][1][blk][dof] = velocity of every
  * block DOF (constrained DOFs follow the drive and its time derivative). */
 int dfx_expand_fields(const DfxTopology* topo, const DfxParams* params, int batch,

@@ -61,7 +61,7 @@ def test_header_is_plain_c_and_struct_sizes_match_ctypes(tmp_path):
     difflexmm_b200/_abi.py must have the sizes the C compiler gives the structs"""
     import subprocess
     from difflexmm_b200 import _abi
-    names = ["DfxTopologyDesc", "DfxLeaf", "DfxParams", "DfxParamGrads", "DfxOptions", "DfxStats", "DfxObjective", "DfxGeometryDesc"]
+    names = ["DfxTopologyDesc", "DfxLeaf", "DfxParams", "DfxParamGrads", "DfxOptions", "DfxStats", "DfxObjective", "DfxGeometryDesc", "DfxConstraintDesc"]
     src = tmp_path / "sizes.c"
     src.write_text('#include <stdio.h>\n#include "dfx.h"\nint main(void) {\n' +
                    "".join(f'  printf("{n} %zu\\n", sizeof({n}));\n' for n in names) + "  return 0;\n}\n")

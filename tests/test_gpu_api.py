@@ -346,6 +346,94 @@ def test_device_geometry_matches_the_torch_design_maps(lattice):
     assert cnv1.shape == cnv_r.shape[1:] and torch.equal(cnv1, cnv[0].detach())
 
 
+@pytest.mark.parametrize("lattice", ["quads", "quads_boundary", "kagome"])
+def test_device_constraints_match_the_torch_constraints_and_their_jacobian(lattice):
+    """dfx_constraints_eval (values + fixed-width sparse Jacobian, one launch per batch) against the torch
+    restatement of the reference's angle / edge-length constraints (problems/quads_focusing.py:473-544) and its autograd
+    Jacobian (the reference: jit(jacobian(...)), :585-588, :613-616), to 1e-12"""
+    from difflexmm_b200.geometry import KagomeGeometry, QuadGeometry
+    from difflexmm_b200.geometry_device import DeviceConstraints, DeviceGeometry
+    from difflexmm_b200.optimization import angle_constraints, edge_length_constraints
+    rng = np.random.default_rng(11)
+    if lattice.startswith("quads"):
+        geo = QuadGeometry(6, 4, spacing=15.0, bond_length=2.25)
+        geo.compute_geometry()
+        base = geo.get_design_from_rotated_square(25 * math.pi / 180)
+    else:
+        geo = KagomeGeometry(4, 3, direct_basis=20.0 * np.array([[1, 0], [math.cos(math.pi / 3), math.sin(math.pi / 3)]]),
+                             bond_length=2.25)
+        geo.compute_geometry()
+        base = [torch.zeros(s, dtype=torch.float64) for s in geo.design_shapes]
+    boundary = lattice == "quads_boundary"
+    min_void, min_block, min_edge = 5 * math.pi / 180, 30 * math.pi / 180, 3.0
+    B = 3
+    designs = [torch.stack([b + torch.from_numpy(rng.uniform(-0.8, 0.8, b.shape)) for _ in range(B)]) for b in base]
+    dg = DeviceGeometry(geo, "cuda")
+    dc = DeviceConstraints(dg, min_void, min_block, min_edge, boundary_angle_constraint=boundary)
+    flat, _ = dg.flatten(designs)
+    c, jac = dc(flat)
+    dense = dc.dense_jacobian(jac).cpu()
+    ang, edg = angle_constraints(geo, min_void, min_block, boundary), edge_length_constraints(geo, min_edge)
+    n_bonds = len(np.asarray(geo.bond_connectivity()))
+    assert dc.n_angle_rows == 4 * n_bonds + (2 * (geo.n1_blocks + geo.n2_blocks) if boundary else 0)
+    assert dc.n_rows == dc.n_angle_rows + geo.n_blocks * geo.n_npb
+    sizes = [int(np.prod(s)) for s in geo.design_shapes]
+    for b in range(B):
+        def both(x):
+            parts, o = [], 0
+            for s, n in zip(geo.design_shapes, sizes):
+                parts.append(x[o:o + n].reshape(tuple(s)))
+                o += n
+            return torch.cat([ang(parts), edg(parts)])
+        x = flat[b].reshape(-1).cpu()
+        ref = both(x)
+        J_ref = torch.autograd.functional.jacobian(both, x)
+        assert (c[b].cpu() - ref).abs().max() <= 1e-12 * max(1.0, float(ref.abs().max()))
+        assert (dense[b] - J_ref).abs().max() <= 1e-12 * max(1.0, float(J_ref.abs().max()))
+    # values only
+    c2, none = dc(flat, want_jacobian=False)
+    assert none is None and torch.equal(c2, c)
+
+
+def test_constrained_batched_mma_gives_a_feasible_ascent():
+    """run_optimization_mma with min_void_angle / min_block_angle / min_edge_length set (the switches of the
+    reference's run_optimization_nlopt, problems/quads_focusing.py:546-652): every best design is feasible to the
+    reference's tolerance (1e-8), no worse than its feasible start, and the constraints are active for some instance"""
+    from difflexmm_b200.optimization import OptimizationProblem
+    P = _problem()
+    P.setup()
+    B = 3
+    guesses = P.random_ensemble(B, noise=0.03)
+    opt = OptimizationProblem(P)
+    x0 = opt.flatten(guesses).cuda()
+    dc0 = opt.device_constraints(0.0, 0.0, 0.0)
+    bounds = dict(lower_bound=float(x0.min()) - 1.0, upper_bound=float(x0.max()) + 1.0)
+
+    def family_minima(x):  # smallest void angle, block angle, edge length over the batch
+        c, _ = dc0(x)
+        na = dc0.n_angle_rows
+        return float((-c[:, :na // 2]).min()), float((-c[:, na // 2:na]).min()), float((-c[:, na:]).min())
+
+    # the unconstrained run tells which quantities the objective wants to shrink; thresholds halfway between the start
+    # and that design make the start feasible and the unconstrained optimum infeasible
+    opt_free = OptimizationProblem(P)
+    best_free, best_f_free = opt_free.run_optimization_mma([g.cuda() for g in guesses], n_iterations=8, **bounds)
+    start, free = family_minima(x0), family_minima(opt_free.flatten(best_free).cuda())
+    assert any(f < s * (1 - 1e-6) for s, f in zip(start, free))
+    void_t, block_t, edge_t = [0.5 * (s + f) if f < s * (1 - 1e-6) else 0.97 * s for s, f in zip(start, free)]
+    mins = dict(min_void_angle=void_t, min_block_angle=block_t, min_edge_length=edge_t)
+    dc = opt.device_constraints(**mins)
+    assert float(dc(x0)[0].max()) < 0 < float(dc(opt_free.flatten(best_free).cuda())[0].max())
+    J0, _ = opt.objective_and_grad(x0)
+    best, best_f = opt.run_optimization_mma([g.cuda() for g in guesses], n_iterations=8, **bounds, **mins)
+    assert len(opt.objective_values) == 8 and len(opt.constraints_violation["angles"]) >= 8
+    assert len(opt.constraints_violation["edge_lengths"]) >= 8
+    c_best, _ = dc(opt.flatten(best).cuda())
+    assert float(c_best.max()) <= 1e-8
+    assert (opt.optimizer.best_violation <= 1e-8).all()
+    assert (best_f >= J0 * (1 - 1e-12)).all() and (best_f > J0 * 1.001).any()
+
+
 def test_batched_mma_improves_an_ensemble_of_designs():
     """several MMA instances advanced in lock-step, one batched forward + adjoint per iteration"""
     from difflexmm_b200.optimization import OptimizationProblem

@@ -206,6 +206,51 @@ def test_batched_mma_converges_and_instances_are_independent():
     assert bx.abs().max() < 1e-4 and (bf <= 0).all()
 
 
+def test_batched_mma_with_inequality_constraints_reaches_the_constrained_minimum():
+    """inequality constraints inside the batched MMA (reference: nlopt LD_MMA + add_inequality_mconstraint,
+    problems/quads_focusing.py:578-627): linear pair constraints and one dense quadratic row through the fixed-width sparse
+    Jacobian interface, against scipy SLSQP on every instance; every recorded best design is feasible to the tolerance"""
+    import numpy as np
+    import torch
+    from scipy.optimize import minimize
+    from difflexmm_b200.optimization import BatchedMMA
+    torch.manual_seed(0)
+    B, n = 4, 6
+    t = torch.randn(B, n, dtype=torch.float64) * 2
+    cols = torch.zeros(n, n, dtype=torch.int64)
+    for j in range(n - 1):
+        cols[j, 0], cols[j, 1] = j, j + 1
+    cols[n - 1] = torch.arange(n)
+
+    def con(x):
+        c = torch.zeros(x.shape[0], n, dtype=torch.float64)
+        J = torch.zeros(x.shape[0], n, n, dtype=torch.float64)
+        c[:, :n - 1] = x[:, :-1] + x[:, 1:] - 0.5
+        J[:, :n - 1, 0] = 1.0
+        J[:, :n - 1, 1] = 1.0
+        c[:, n - 1] = (x ** 2).sum(1) - 4.0
+        J[:, n - 1, :] = 2 * x
+        return c, J, cols
+
+    opt = BatchedMMA(lambda x: (((x - t) ** 2).sum(1), 2 * (x - t)), torch.zeros(B, n, dtype=torch.float64), -3.0, 3.0,
+                     maximize=False, constraints=con)
+    bx, bf = opt.run(60)
+    assert opt.n_evals == 60 and len(opt.history) == 60 and len(opt.violation_history) == 60
+    assert (opt.best_violation <= 1e-8).all() and (con(bx)[0] <= 1e-8).all()
+    for b in range(B):
+        tb = t[b].numpy()
+        ref = minimize(lambda x: ((x - tb) ** 2).sum(), np.zeros(n), jac=lambda x: 2 * (x - tb), method="SLSQP", bounds=[(-3, 3)] * n,
+                       constraints=[{"type": "ineq", "fun": lambda x, j=j: 0.5 - x[j] - x[j + 1]} for j in range(n - 1)]
+                       + [{"type": "ineq", "fun": lambda x: 4 - (x ** 2).sum()}], options={"ftol": 1e-14, "maxiter": 500})
+        assert abs(float(bf[b]) - ref.fun) <= 1e-5 * abs(ref.fun) and np.abs(bx[b].numpy() - ref.x).max() <= 1e-3
+    # an infeasible start is driven into the feasible set
+    opt = BatchedMMA(lambda x: (((x - t) ** 2).sum(1), 2 * (x - t)), torch.full((B, n), 2.5, dtype=torch.float64), -3.0, 3.0,
+                     maximize=False, constraints=con)
+    assert (con(opt.x)[0] > 0).any()
+    opt.run(40)
+    assert (opt.best_violation <= 1e-8).all()
+
+
 def test_constraints_match_a_per_bond_restatement():
     """angle / edge-length constraints (reference problems/quads_focusing.py:473-544) against a literal per-bond loop
     over the reference's compute_edge_unit_vectors / angle_between_unit_vectors (geometry.py:181-253)"""

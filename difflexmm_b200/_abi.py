@@ -55,14 +55,14 @@ class DfxParams(C.Structure):
         ("k_stretch", DfxLeaf), ("k_shear", DfxLeaf), ("k_rot", DfxLeaf),
         ("k_per_bond", C.c_int32 * 3),
         ("damping", DfxLeaf), ("damping_per_dof", C.c_int32),
-        ("inertia", DfxLeaf), ("contact", DfxLeaf), ("drive", DfxLeaf),
+        ("inertia", DfxLeaf), ("contact", DfxLeaf), ("drive", DfxLeaf), ("block_centroids", DfxLeaf),
     ]
 
 
 class DfxParamGrads(C.Structure):
     _fields_ = [(n, C.c_void_p) for n in (
         "centroid_node_vectors", "reference_vector", "k_stretch", "k_shear", "k_rot",
-        "damping", "inertia", "contact", "drive")]
+        "damping", "inertia", "contact", "drive", "block_centroids")]
 
 
 class DfxOptions(C.Structure):
@@ -82,6 +82,7 @@ class DfxConstraintDesc(C.Structure):
 
 
 DFX_OBJ_KINETIC, DFX_OBJ_ANGULAR = 0, 1
+DFX_CONTACT_NONE, DFX_CONTACT_ANGLE, DFX_CONTACT_DISTANCE = 0, 1, 2
 
 
 class DfxObjective(C.Structure):
@@ -111,7 +112,10 @@ class TopologySpec:
         self.n_blocks, self.n_npb = int(n_blocks), int(n_npb)
         self.bond_nodes = np.ascontiguousarray(np.asarray(bond_nodes, dtype=np.int32).reshape(-1, 2))
         self.constrained_dofs = np.ascontiguousarray(np.asarray(constrained_dofs, dtype=np.int32).reshape(-1))
-        self.bond_energy, self.contact, self.drive_kind = int(bond_energy), bool(contact), int(drive_kind)
+        # contact: False / True (angle-based) or DFX_CONTACT_* (2 = distance-based between the void edges)
+        self.bond_energy, self.contact, self.drive_kind = int(bond_energy), int(contact), int(drive_kind)
+        if self.contact not in (DFX_CONTACT_NONE, DFX_CONTACT_ANGLE, DFX_CONTACT_DISTANCE):
+            raise ValueError(f"unknown contact kind {contact}")
         nc = len(self.constrained_dofs)
 
         def vec(v):
@@ -174,7 +178,7 @@ class TopologySpec:
 
 
 LEAF_NAMES = ("centroid_node_vectors", "reference_vector", "k_stretch", "k_shear", "k_rot",
-              "damping", "inertia", "contact", "drive")
+              "damping", "inertia", "contact", "drive", "block_centroids")
 
 
 def _ptr(a):
@@ -210,13 +214,15 @@ class ParamSet:
             "inertia": (spec.n_free,),
             "contact": (3,),
             "drive": (spec.n_drive_params,),
+            "block_centroids": (spec.n_blocks, 2),
         }
         self.leaves, self.batched = {}, {}
         for name in LEAF_NAMES:
             a = leaves.get(name)
             needed = not ((name == "contact" and not spec.contact) or
                           (name == "drive" and spec.n_drive_params == 0) or
-                          (name == "damping" and len(spec.damped_blocks) == 0))
+                          (name == "damping" and len(spec.damped_blocks) == 0) or
+                          (name == "block_centroids" and spec.contact != DFX_CONTACT_DISTANCE))
             if a is None:
                 if needed:
                     raise ValueError(f"missing parameter leaf '{name}'")

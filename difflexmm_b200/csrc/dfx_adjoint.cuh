@@ -61,7 +61,7 @@ struct AdjArgs {
   DfxStats* stats;
   double* scratch; long long scratch_per_design;
   // quadrature layout (entries)
-  int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, nq;
+  int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, qo_cen, nq;
   int group;  // CL = 2: CTAs per design
   const int* order;  // DfxOptions.design_order
 };
@@ -257,8 +257,9 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   double *invm = P(AA_INVM), *cd = P(AA_CD);
   double *u0 = P(AA_U0), *v0 = P(AA_V0), *lu0 = P(AA_LU0), *lv0 = P(AA_LV0);
   double *kv = P(AA_KV), *klu = P(AA_KLU), *klv = P(AA_KLV);
-  double *bondc = P(AA_BONDC), *cnv = P(AA_CNV), *alpha = T.contact ? P(AA_ALPHA) : nullptr;
-  double* edged = T.contact ? P(AA_EDGED) : nullptr;  // [4][NN] d atan2(edge)/d(edge) of the next / previous edge of every node
+  const bool c_angle = T.contact == DFX_CONTACT_ANGLE, c_dist = T.contact == DFX_CONTACT_DISTANCE;
+  double *bondc = P(AA_BONDC), *cnv = P(AA_CNV), *alpha = c_angle ? P(AA_ALPHA) : nullptr;
+  double* edged = c_angle ? P(AA_EDGED) : nullptr;  // [4][NN] d atan2(edge)/d(edge) of the next / previous edge of every node
   QuadCtx qc;
   qc.ks[0] = P(AA_QK3); qc.ks[1] = P(AA_QK4); qc.ks[2] = P(AA_QK5); qc.ks[3] = P(AA_QK6); qc.tab = &a.tab;
   qc.k1 = P(AA_QK1); qc.k7 = P(AA_QK7); qc.q0 = P(AA_Q0); qc.qnew = P(AA_QNEW);
@@ -273,6 +274,7 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
   const double* g_ksh = leaf_ptr(a.p.k_shear, design);
   const double* g_kr = leaf_ptr(a.p.k_rot, design);
   const double* g_contact = leaf_ptr(a.p.contact, design);
+  const double* g_cen = leaf_ptr(a.p.block_centroids, design);  // distance-based contact only
   const double* g_drive = leaf_ptr(a.p.drive, design);
   const double* ts = a.ts + (long long)design * a.ts_bstride;
   const double* ys = a.ys + (long long)design * a.n_t * 2 * nf;
@@ -297,7 +299,8 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     }
   }
   for (int i = tid; i < 3 * NN; i += nthr) { Fs[i] = 0.0; Hs[i] = 0.0; }
-  for (int i = tid; i < 2 * NN; i += nthr) { Gs[i] = 0.0; if (Ga) Ga[i] = 0.0; }
+  for (int i = tid; i < 2 * NN; i += nthr) Gs[i] = 0.0;
+  if (Ga) for (int i = tid; i < (c_dist ? 6 : 2) * NN; i += nthr) Ga[i] = 0.0;
   for (int i = tid; i < NQ; i += nthr) { qc.q0[i] = 0.0; qc.k1[i] = 0.0; qc.k7[i] = 0.0; qc.qnew[i] = 0.0; qc.ks[0][i] = 0.0; qc.ks[1][i] = 0.0; qc.ks[2][i] = 0.0; qc.ks[3][i] = 0.0; }
   for (int i = threadIdx.x; i < kScalDoubles; i += blockDim.x) SC[i] = 0.0;
   double cmin = 0, ccut = 0, ckc = 0;
@@ -326,7 +329,34 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       BondOut<Dual> o;
       if (want_q) bond_gradient<Dual, true, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
       else bond_gradient<Dual, false, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
-      if (T.contact) {
+      Dual dgr1[2] = {Dual(0.0), Dual(0.0)}, dgr2[2] = {Dual(0.0), Dual(0.0)};  // distance contact: d/d(cnv) of the bond's own nodes
+      if (c_dist) {
+        double r6[6][2];
+        const int ends[2] = {nd.x, nd.y};
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int n = ends[side], blk = n / npb, l = n - blk * npb;
+          const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
+          r6[3 * side][0] = cnv[n]; r6[3 * side][1] = cnv[NN + n];
+          r6[3 * side + 1][0] = cnv[nn]; r6[3 * side + 1][1] = cnv[NN + nn];
+          r6[3 * side + 2][0] = cnv[np]; r6[3 * side + 2][1] = cnv[NN + np];
+        }
+        DistanceContactOut<Dual> dc;
+        distance_contact<Dual>(s1, s2, g_cen + 2 * bl.x, g_cen + 2 * bl.y, r6, cmin, ccut, ckc, dc);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { o.f1[j] = o.f1[j] + dc.f1[j]; o.f2[j] = o.f2[j] + dc.f2[j]; }
+        if (want_q) {
+          // integrand of a leaf p: -(dual part of dE/dp).  Vertex cotangents of the next / previous vertex go to slots
+          // indexed by the bond node (each node belongs to one bond: no conflicts); block centroids see the contact
+          // part of the force pair.
+          dgr1[0] = dc.gr[0][0]; dgr1[1] = dc.gr[0][1]; dgr2[0] = dc.gr[3][0]; dgr2[1] = dc.gr[3][1];
+          Ga[nd.x] = -dc.gr[1][0].d; Ga[NN + nd.x] = -dc.gr[1][1].d; Ga[2 * NN + nd.x] = -dc.gr[2][0].d; Ga[3 * NN + nd.x] = -dc.gr[2][1].d;
+          Ga[nd.y] = -dc.gr[4][0].d; Ga[NN + nd.y] = -dc.gr[4][1].d; Ga[2 * NN + nd.y] = -dc.gr[5][0].d; Ga[3 * NN + nd.y] = -dc.gr[5][1].d;
+          Ga[4 * NN + nd.x] = -dc.f1[0].d; Ga[5 * NN + nd.x] = -dc.f1[1].d;
+          Ga[4 * NN + nd.y] = -dc.f2[0].d; Ga[5 * NN + nd.y] = -dc.f2[1].d;
+          p_c0 -= dc.gmin.d; p_c1 -= dc.gcut.d; p_c2 -= dc.gkc.d;
+        }
+      } else if (c_angle) {
         Dual psi1 = wrapT(s1.th - s2.th + (alpha[nd.x] - alpha[NN + nd.y]));
         Dual psi2 = wrapT(s2.th - s1.th + (alpha[nd.y] - alpha[NN + nd.x]));
         Dual e1, e2, m1, m2, c1, c2, k1, k2;
@@ -346,8 +376,8 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
       Hs[nd.y] = o.f2[0].d; Hs[NN + nd.y] = o.f2[1].d; Hs[2 * NN + nd.y] = o.f2[2].d;
       if (want_q) {
         // d(w.F)/dp = -(dual part of dE/dp)
-        Gs[nd.x] = -o.gr1[0].d; Gs[NN + nd.x] = -o.gr1[1].d;
-        Gs[nd.y] = -o.gr2[0].d; Gs[NN + nd.y] = -o.gr2[1].d;
+        Gs[nd.x] = -(o.gr1[0].d + dgr1[0].d); Gs[NN + nd.x] = -(o.gr1[1].d + dgr1[1].d);
+        Gs[nd.y] = -(o.gr2[0].d + dgr2[0].d); Gs[NN + nd.y] = -(o.gr2[1].d + dgr2[1].d);
         quad_update(qc, a.qo_ref + b, -o.gr0[0].d, probe);
         quad_update(qc, a.qo_ref + NBONDS + b, -o.gr0[1].d, probe);
         if (ks_pb) quad_update(qc, a.qo_ks + b, -o.gks.d, probe); else p_ks -= o.gks.d;
@@ -411,11 +441,15 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
           if (l < npb) {
             const int n = blk * npb + l;
             double val = Gs[j * NN + n];
-            if (T.contact) {
+            if (c_angle) {
               const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
               const double d1 = edged[j * NN + n], d2 = edged[(2 + j) * NN + n];
               // own edges: d/dr_n = -d/de ; as far end of nn's previous edge (e = r_n - r_nn = -e1): also -d1
               val += -Ga[n] * d1 - Ga[NN + n] * d2 - Ga[NN + nn] * d1 - Ga[np] * d2;
+            } else if (c_dist) {
+              // this vertex is the "next" of its previous vertex and the "previous" of its next vertex
+              const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
+              val += Ga[j * NN + np] + Ga[(2 + j) * NN + nn];
             }
             vals[l] = val;
           }
@@ -426,12 +460,19 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
         for (int l = 4; l < npb; ++l) {  // polygons with more than 4 vertices
           const int n = blk * npb + l;
           double val = Gs[j * NN + n];
-          if (T.contact) {
-            const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = n - 1;
+          const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = n - 1;
+          if (c_angle) {
             const double d1 = edged[j * NN + n], d2 = edged[(2 + j) * NN + n];
             val += -Ga[n] * d1 - Ga[NN + n] * d2 - Ga[NN + nn] * d1 - Ga[np] * d2;
+          } else if (c_dist) {
+            val += Ga[j * NN + np] + Ga[(2 + j) * NN + nn];
           }
           quad_update(qc, a.qo_cnv + j * NN + n, val, probe);
+        }
+        if (c_dist) {  // block_centroids leaf: contact part of the force on this block, component j
+          double cb = 0.0;
+          for (int l = 0; l < npb; ++l) cb += Ga[(4 + j) * NN + blk * npb + l];
+          quad_update(qc, a.qo_cen + j * NB + blk, cb, probe);
         }
       }
     }
@@ -712,6 +753,11 @@ __global__ void __launch_bounds__(512, 1) adjoint_kernel(const __grid_constant__
     for (int n = tid; n < NN; n += nthr) {
       a.grads.centroid_node_vectors[((long long)design * NN + n) * 2] = bad ? nanv : qc.q0[a.qo_cnv + n];
       a.grads.centroid_node_vectors[((long long)design * NN + n) * 2 + 1] = bad ? nanv : qc.q0[a.qo_cnv + NN + n];
+    }
+  if (a.grads.block_centroids && c_dist)
+    for (int k = tid; k < NB; k += nthr) {
+      a.grads.block_centroids[((long long)design * NB + k) * 2] = bad ? nanv : qc.q0[a.qo_cen + k];
+      a.grads.block_centroids[((long long)design * NB + k) * 2 + 1] = bad ? nanv : qc.q0[a.qo_cen + NB + k];
     }
   if (a.grads.reference_vector)
     FOR_B(b) {

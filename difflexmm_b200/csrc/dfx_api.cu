@@ -100,10 +100,10 @@ void forward_sizes(const DevTopo& T, long long (&sz)[FA_COUNT]) {
   const long long NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds;
   sz[FA_US] = 5 * NB; sz[FA_VS] = 3 * NB; sz[FA_FS] = 3 * NN; sz[FA_U0] = 3 * NB; sz[FA_V0] = 3 * NB;
   sz[FA_KV] = 21 * NB; sz[FA_INVM] = 3 * NB; sz[FA_CD] = 3 * NB; sz[FA_BONDC] = 4 * NBONDS; sz[FA_CNV] = 2 * NN;
-  sz[FA_ALPHA] = T.contact ? 2 * NN : 0;
+  sz[FA_ALPHA] = T.contact == DFX_CONTACT_ANGLE ? 2 * NN : 0;
 }
 
-struct QuadLayout { int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, nq; };
+struct QuadLayout { int qo_cnv, qo_ref, qo_ks, qo_ksh, qo_kr, qo_damp, qo_inertia, qo_cen, nq; };
 
 QuadLayout quad_layout(const DevTopo& T, const DfxParams& p) {
   QuadLayout q;
@@ -115,6 +115,7 @@ QuadLayout quad_layout(const DevTopo& T, const DfxParams& p) {
   q.qo_kr = o; o += p.k_per_bond[2] ? T.n_bonds : 0;
   q.qo_damp = o; o += (T.n_damped > 0 && p.damping_per_dof) ? 3 * T.n_blocks : 0;
   q.qo_inertia = o; o += 3 * T.n_blocks;
+  q.qo_cen = o; o += T.contact == DFX_CONTACT_DISTANCE ? 2 * T.n_blocks : 0;  // block_centroids leaf [2][NB]
   q.nq = o;
   return q;
 }
@@ -122,13 +123,16 @@ QuadLayout quad_layout(const DevTopo& T, const DfxParams& p) {
 void adjoint_sizes(const DevTopo& T, const QuadLayout& q, long long (&sz)[AA_COUNT], int cluster = 1) {
   const long long NB = T.n_blocks, NN = T.n_nodes, NBONDS = T.n_bonds;
   sz[AA_US] = 5 * NB; sz[AA_WS] = 3 * NB; sz[AA_VS] = 3 * NB; sz[AA_LUS] = 3 * NB; sz[AA_LVS] = 3 * NB;
-  sz[AA_FS] = 3 * NN; sz[AA_HS] = 3 * NN; sz[AA_GS] = 2 * NN; sz[AA_GA] = T.contact ? 2 * NN : 0;
+  sz[AA_FS] = 3 * NN; sz[AA_HS] = 3 * NN; sz[AA_GS] = 2 * NN;
+  // angle contact: d/d(alpha_next, alpha_prev) per node; distance contact: cotangents of the next / previous vertex (x, y each)
+  // and the contact part of the force pair [2][NN] for the block_centroids leaf
+  sz[AA_GA] = T.contact == DFX_CONTACT_ANGLE ? 2 * NN : (T.contact == DFX_CONTACT_DISTANCE ? 6 * NN : 0);
   sz[AA_SC] = cluster > 1 ? 0 : kScalDoubles;  // cluster mode keeps it in each CTA's shared memory
   sz[AA_INVM] = 3 * NB; sz[AA_CD] = 3 * NB;
   sz[AA_U0] = 3 * NB; sz[AA_V0] = 3 * NB; sz[AA_LU0] = 3 * NB; sz[AA_LV0] = 3 * NB;
   sz[AA_KV] = 21 * NB; sz[AA_KLU] = 21 * NB; sz[AA_KLV] = 21 * NB;
-  sz[AA_BONDC] = 4 * NBONDS; sz[AA_CNV] = 2 * NN; sz[AA_ALPHA] = T.contact ? 2 * NN : 0;
-  sz[AA_EDGED] = T.contact ? 4 * NN : 0;
+  sz[AA_BONDC] = 4 * NBONDS; sz[AA_CNV] = 2 * NN; sz[AA_ALPHA] = T.contact == DFX_CONTACT_ANGLE ? 2 * NN : 0;
+  sz[AA_EDGED] = T.contact == DFX_CONTACT_ANGLE ? 4 * NN : 0;
   for (int i = AA_QK3; i <= AA_QNEW; ++i) sz[i] = q.nq;
 }
 
@@ -226,7 +230,7 @@ FastPlan plan_fast_adjoint(const DevTopo& T) {
   FastPlan f = {};
   const char* mode = getenv("DFX_ADJOINT_KERNEL");  // "generic" | "notmem" | unset (fast + TMEM)
   if (mode && !strcmp(mode, "generic")) return f;
-  if (T.bond_energy == DFX_BOND_SPRING) return f;  // generic kernels only
+  if (T.bond_energy == DFX_BOND_SPRING || T.contact == DFX_CONTACT_DISTANCE) return f;  // generic kernels only
   int t = T.n_blocks > (T.n_bonds + 1) / 2 ? T.n_blocks : (T.n_bonds + 1) / 2;
   t = t <= 384 ? 384 : 512;  // the CTA size is a compile-time constant of the kernel (addresses become immediates)
   if (const char* e = getenv("DFX_ADJOINT_THREADS")) { if (atoi(e) == 512) t = 512; }  // experiment: 16 warps at <= 128 registers
@@ -267,7 +271,7 @@ Fast3Plan plan_adjoint3(const DevTopo& T, const DfxParams& p, int n_cons_units) 
   const char* mode = getenv("DFX_ADJOINT_KERNEL");
   if (mode && (!strcmp(mode, "generic") || !strcmp(mode, "notmem") || !strcmp(mode, "v2"))) return f;
   if (getenv("DFX_ADJOINT_THREADS")) return f;
-  if (T.bond_energy != DFX_BOND_LIGAMENT || T.load_kind != DFX_LOAD_NONE) return f;
+  if (T.bond_energy != DFX_BOND_LIGAMENT || T.load_kind != DFX_LOAD_NONE || T.contact == DFX_CONTACT_DISTANCE) return f;
   if (p.k_per_bond[0] || p.k_per_bond[1] || p.k_per_bond[2]) return f;
   if (T.n_blocks > k3::TU || T.n_bonds > k3::TT || T.n_blocks < 1 || T.n_bonds < 1) return f;
   if (n_cons_units > k3::NCU) return f;  // the drive vectors of the constrained units are cached in shared memory
@@ -284,7 +288,7 @@ FastFwdPlan plan_fast_forward(const DevTopo& T) {
   FastFwdPlan f = {};
   const char* mode = getenv("DFX_FORWARD_KERNEL");  // "generic" | "notmem" | unset (fast + TMEM)
   if (mode && !strcmp(mode, "generic")) return f;
-  if (T.bond_energy == DFX_BOND_SPRING) return f;  // generic kernels only
+  if (T.bond_energy == DFX_BOND_SPRING || T.contact == DFX_CONTACT_DISTANCE) return f;  // generic kernels only
   int t = T.n_blocks > (T.n_bonds + 1) / 2 ? T.n_blocks : (T.n_bonds + 1) / 2;
   t = t <= 384 ? 384 : 512;
   if (T.n_npb > 4 || T.n_blocks > t || T.n_bonds > 2 * t) return f;
@@ -313,6 +317,8 @@ int check_params(const DevTopo& T, const DfxParams* p) {
       !p->inertia.ptr)
     return fail(DFX_ERR_INVALID, "a required parameter leaf is NULL");
   if (T.contact && !p->contact.ptr) return fail(DFX_ERR_INVALID, "topology has contact but params.contact is NULL");
+  if (T.contact == DFX_CONTACT_DISTANCE && !p->block_centroids.ptr)
+    return fail(DFX_ERR_INVALID, "distance-based contact needs params.block_centroids");
   if (T.n_drive_params > 0 && !p->drive.ptr) return fail(DFX_ERR_INVALID, "drive signal needs params.drive");
   return DFX_OK;
 }
@@ -383,7 +389,7 @@ int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out)
   std::memset(&D, 0, sizeof(D));
   D.n_blocks = d->n_blocks; D.n_npb = d->n_npb; D.n_bonds = d->n_bonds; D.n_nodes = n_nodes; D.n_dof = n_dof;
   D.n_free = (int)free_dofs.size(); D.n_cons = d->n_constrained;
-  D.bond_energy = d->bond_energy; D.contact = d->contact ? 1 : 0; D.drive_kind = d->drive_kind;
+  D.bond_energy = d->bond_energy; D.contact = d->contact; D.drive_kind = d->drive_kind;
   D.load_kind = d->load_kind; D.n_drive_params = n_drive_params_of(d->drive_kind); D.n_damped = d->n_damped;
   for (int i = 0; i < DFX_MAX_LOAD_CONSTS; ++i) D.load_consts[i] = d->load_consts[i];
   int2 *dbn, *dbb; int *dfo, *dcs, *dds, *dfd, *dnb; double *dv0, *dv1, *dlm, *dtt = nullptr, *dtv = nullptr;
@@ -631,7 +637,7 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
   a.topo = T; a.p = *params; a.tab = make_tableau();
   QuadLayout q = quad_layout(T, *params);
   a.qo_cnv = q.qo_cnv; a.qo_ref = q.qo_ref; a.qo_ks = q.qo_ks; a.qo_ksh = q.qo_ksh; a.qo_kr = q.qo_kr;
-  a.qo_damp = q.qo_damp; a.qo_inertia = q.qo_inertia; a.nq = q.nq;
+  a.qo_damp = q.qo_damp; a.qo_inertia = q.qo_inertia; a.qo_cen = q.qo_cen; a.nq = q.nq;
   long long sz[AA_COUNT], g;
   size_t smem;
   const FastPlan fp = plan_fast_adjoint(T);
@@ -653,6 +659,7 @@ int adjoint_impl(const DfxTopology* t, const DfxParams* params, int batch, const
     for (int k = 0; k < 3; ++k) n += params->k_per_bond[k] ? T.n_bonds : 1;
     if (T.n_damped > 0 && params->damping.ptr) n += params->damping_per_dof ? 3LL * T.n_damped : 1;
     if (T.contact) n += 3;
+    if (T.contact == DFX_CONTACT_DISTANCE) n += 2LL * T.n_blocks;
     n += T.n_drive_params;
     aug_size = n;
   }

@@ -266,6 +266,104 @@ __device__ __forceinline__ bool contact_term(T psi, double tmin, double tcut, do
   return false;
 }
 
+// ---- distance-based contact between the void edges of a bond (reference energy.py:222-330, build_contact_energy with
+// angle_based=False at :364-407).  The six polygon vertices involved are
+//     P[k] = block centroid + block displacement + R(theta) * centroid_node_vector,  k = node, next, previous of block 1, then of block 2,
+// the two gaps are edges_distance((P0,P1),(P3,P5)) and edges_distance((P0,P2),(P3,P4)), each the smallest of four
+// point-to-segment distances (branches decided on values: jnp.where / jnp.min), and each gap enters the same 1/x-type
+// energy as a void angle (contact_term; min / cutoff are lengths here).  Output: dE/d(block DOFs) (whose x, y entries
+// are also dE/d(block centroid)), dE/d(centroid_node_vector) of the six vertices and dE/d(contact parameters).
+template <class T>
+struct DistanceContactOut {
+  T f1[3], f2[3];
+  T gr[6][2];
+  T gmin, gcut, gkc;
+};
+
+__device__ __forceinline__ double point_segment_value(double px, double py, double x0, double y0, double x1, double y1) {
+  const double ex = x1 - x0, ey = y1 - y0, rx = px - x0, ry = py - y0;
+  const double t = (rx * ex + ry * ey) / (ex * ex + ey * ey);
+  if (t >= 0.0 && t <= 1.0) return sqrt((rx * rx - (t * ex) * (t * ex)) + (ry * ry - (t * ey) * (t * ey)));
+  if (t < 0.0) return sqrt(rx * rx + ry * ry);
+  const double sx = px - x1, sy = py - y1;
+  return sqrt(sx * sx + sy * sy);
+}
+
+// d = distance of P[ip] to the segment (P[i0], P[i1]); adds scale(d) * dd/dP to the vertex gradients G.  On the segment
+// d^2 = |r|^2 - (r.e)^2 / |e|^2 with foot parameter t: dd/dp = n, dd/dx1 = -t n, dd/dx0 = (t - 1) n, n = (r - t e) / d.
+template <class T, class F>
+__device__ __forceinline__ void point_segment_accumulate(const T (*P)[2], int ip, int i0, int i1, T (*G)[2], F&& scale) {
+  const T ex = P[i1][0] - P[i0][0], ey = P[i1][1] - P[i0][1], rx = P[ip][0] - P[i0][0], ry = P[ip][1] - P[i0][1];
+  const T t = (rx * ex + ry * ey) * recipT(ex * ex + ey * ey);
+  const double tv = val(t);
+  if (tv >= 0.0 && tv <= 1.0) {
+    const T tex = t * ex, tey = t * ey;
+    const T d = sqrtT((rx * rx - tex * tex) + (ry * ry - tey * tey));
+    const T w = scale(d) * recipT(d);
+    const T nx = (rx - tex) * w, ny = (ry - tey) * w;
+    G[ip][0] = G[ip][0] + nx; G[ip][1] = G[ip][1] + ny;
+    G[i1][0] = G[i1][0] - t * nx; G[i1][1] = G[i1][1] - t * ny;
+    const T tm = t - 1.0;
+    G[i0][0] = G[i0][0] + tm * nx; G[i0][1] = G[i0][1] + tm * ny;
+  } else {
+    const int iq = tv < 0.0 ? i0 : i1;  // nearest end of the segment
+    const T sx = P[ip][0] - P[iq][0], sy = P[ip][1] - P[iq][1];
+    const T d = sqrtT(sx * sx + sy * sy);
+    const T w = scale(d) * recipT(d);
+    G[ip][0] = G[ip][0] + sx * w; G[ip][1] = G[ip][1] + sy * w;
+    G[iq][0] = G[iq][0] - sx * w; G[iq][1] = G[iq][1] - sy * w;
+  }
+}
+
+// cen: block centroids of block 1, 2; r[k]: centroid_node_vectors of the six vertices
+template <class T>
+__device__ __noinline__ void distance_contact(const BlockState<T>& b1, const BlockState<T>& b2, const double* cen1, const double* cen2,
+                                              const double (*r)[2], double dmin, double dcut, double kc, DistanceContactOut<T>& o) {
+  T P[6][2], G[6][2];
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const BlockState<T>& b = k < 3 ? b1 : b2;
+    const double* cen = k < 3 ? cen1 : cen2;
+    P[k][0] = b.x + (b.c * r[k][0] - b.s * r[k][1]) + cen[0];
+    P[k][1] = b.y + (b.s * r[k][0] + b.c * r[k][1]) + cen[1];
+    G[k][0] = make_T<T>(0.0, 0.0); G[k][1] = make_T<T>(0.0, 0.0);
+  }
+  o.gmin = make_T<T>(0.0, 0.0); o.gcut = make_T<T>(0.0, 0.0); o.gkc = make_T<T>(0.0, 0.0);
+#pragma unroll
+  for (int side = 0; side < 2; ++side) {
+    const int a0 = 0, a1 = side == 0 ? 1 : 2, c0 = 3, c1 = side == 0 ? 5 : 4;
+    // candidates in the reference's order: ends of the second edge onto the first, ends of the first onto the second
+    const int cand[4][3] = {{c0, a0, a1}, {c1, a0, a1}, {a0, c0, c1}, {a1, c0, c1}};
+    int best = 0;
+    double dbest = 0.0;
+#pragma unroll
+    for (int k = 0; k < 4; ++k) {
+      const double dv = point_segment_value(val(P[cand[k][0]][0]), val(P[cand[k][0]][1]), val(P[cand[k][1]][0]), val(P[cand[k][1]][1]),
+                                            val(P[cand[k][2]][0]), val(P[cand[k][2]][1]));
+      if (k == 0 || dv < dbest) { dbest = dv; best = k; }
+    }
+    point_segment_accumulate<T>(P, cand[best][0], cand[best][1], cand[best][2], G, [&](T d) {
+      T e, m, u, kk;
+      contact_term<T>(d, dmin, dcut, kc, e, m, u, kk);
+      o.gmin = o.gmin + m; o.gcut = o.gcut + u; o.gkc = o.gkc + kk;
+      return e;
+    });
+  }
+#pragma unroll
+  for (int j = 0; j < 3; ++j) { o.f1[j] = make_T<T>(0.0, 0.0); o.f2[j] = make_T<T>(0.0, 0.0); }
+#pragma unroll
+  for (int k = 0; k < 6; ++k) {
+    const BlockState<T>& b = k < 3 ? b1 : b2;
+    T* f = k < 3 ? o.f1 : o.f2;
+    f[0] = f[0] + G[k][0];
+    f[1] = f[1] + G[k][1];
+    // d(R r)/d theta = (-s r_x - c r_y, c r_x - s r_y)
+    f[2] = f[2] + G[k][1] * (b.c * r[k][0] - b.s * r[k][1]) - G[k][0] * (b.s * r[k][0] + b.c * r[k][1]);
+    o.gr[k][0] = b.c * G[k][0] + b.s * G[k][1];
+    o.gr[k][1] = b.c * G[k][1] - b.s * G[k][0];
+  }
+}
+
 // EXT: also compile the bond kinds that only the generic kernels support (DFX_BOND_SPRING)
 template <class T, bool PARAMS, bool EXT = false>
 __device__ __forceinline__ void bond_gradient(int energy_kind, const BlockState<T>& b1, const BlockState<T>& b2,

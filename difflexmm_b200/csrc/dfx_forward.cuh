@@ -140,12 +140,13 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
   double* cd = placed(a.place, FA_CD, smem, scratch);      // [3][NB]
   double* bondc = placed(a.place, FA_BONDC, smem, scratch);  // [4][NBONDS]
   double* cnv = placed(a.place, FA_CNV, smem, scratch);    // [2][NN]
-  double* alpha = T.contact ? placed(a.place, FA_ALPHA, smem, scratch) : nullptr;  // [2][NN]
+  double* alpha = T.contact == DFX_CONTACT_ANGLE ? placed(a.place, FA_ALPHA, smem, scratch) : nullptr;  // [2][NN]
 
   const double* g_ks = leaf_ptr(a.p.k_stretch, design);
   const double* g_ksh = leaf_ptr(a.p.k_shear, design);
   const double* g_kr = leaf_ptr(a.p.k_rot, design);
   const double* g_contact = leaf_ptr(a.p.contact, design);
+  const double* g_cen = leaf_ptr(a.p.block_centroids, design);  // distance-based contact only
   const double* g_drive = leaf_ptr(a.p.drive, design);
   const double* ts = a.ts + (long long)design * a.ts_bstride;
   const double* y0g = a.y0 + (long long)design * a.y0_bstride;
@@ -179,7 +180,22 @@ __global__ void __launch_bounds__(512, 1) forward_kernel(const __grid_constant__
       const double ks = g_ks[a.p.k_per_bond[0] ? b : 0], ksh = g_ksh[a.p.k_per_bond[1] ? b : 0], kr = g_kr[a.p.k_per_bond[2] ? b : 0];
       BondOut<double> o;
       bond_gradient<double, false, true>(T.bond_energy, s1, s2, cnv[nd.x], cnv[NN + nd.x], cnv[nd.y], cnv[NN + nd.y], bc, ks, ksh, kr, o);
-      if (T.contact) {
+      if (T.contact == DFX_CONTACT_DISTANCE) {
+        double r6[6][2];
+        const int ends[2] = {nd.x, nd.y};
+#pragma unroll
+        for (int side = 0; side < 2; ++side) {
+          const int n = ends[side], blk = n / npb, l = n - blk * npb;
+          const int nn = blk * npb + (l + 1 == npb ? 0 : l + 1), np = blk * npb + (l == 0 ? npb - 1 : l - 1);
+          r6[3 * side][0] = cnv[n]; r6[3 * side][1] = cnv[NN + n];
+          r6[3 * side + 1][0] = cnv[nn]; r6[3 * side + 1][1] = cnv[NN + nn];
+          r6[3 * side + 2][0] = cnv[np]; r6[3 * side + 2][1] = cnv[NN + np];
+        }
+        DistanceContactOut<double> dc;
+        distance_contact<double>(s1, s2, g_cen + 2 * bl.x, g_cen + 2 * bl.y, r6, cmin, ccut, ckc, dc);
+#pragma unroll
+        for (int j = 0; j < 3; ++j) { o.f1[j] += dc.f1[j]; o.f2[j] += dc.f2[j]; }
+      } else if (T.contact) {
         // void angles depend on the two rotations only
         const double psi1 = wrap_value(alpha[nd.x] - alpha[NN + nd.y] + s1.th - s2.th);
         const double psi2 = wrap_value(alpha[nd.y] - alpha[NN + nd.x] + s2.th - s1.th);

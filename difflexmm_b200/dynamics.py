@@ -113,7 +113,12 @@ def lower_params(spec, drive, control_params: ControlParams, batch: Optional[int
     leaves["centroid_node_vectors"] = cnv
     n_entries += n
     if gp.block_centroids is not None:
-        n_entries += split(gp.block_centroids, 2)[2]
+        cen, _, n = split(gp.block_centroids, 2)
+        n_entries += n
+        if spec.contact == _abi.DFX_CONTACT_DISTANCE:  # the only energy that reads block positions (energy.py:395-405)
+            leaves["block_centroids"] = cen
+    elif spec.contact == _abi.DFX_CONTACT_DISTANCE:
+        raise ValueError("distance-based contact needs geometrical_params.block_centroids")
     spring = spec.bond_energy == _abi.DFX_BOND_SPRING
     if spring != (not hasattr(bp, "reference_vector")):
         raise TypeError("stretching_torsional_spring_energy takes StretchingTorsionalSpringParams, the ligament energies "

@@ -50,12 +50,13 @@ class StrainEnergy(BlockEnergy):
 
 
 class ContactEnergy(BlockEnergy):
+    """angle-based (reference `energy.py:204-219`) or distance-based between the two void edges of every bond
+    (`energy.py:222-330`; `contact_params.min_angle` / `cutoff_angle` are lengths then, and the block centroids become a
+    differentiable leaf; runs on the generic kernels)"""
+
     def __init__(self, bond_connectivity, angle_based=True):
-        if not angle_based:
-            raise NotImplementedError("distance-based contact (reference energy.py:222-330) has no call "
-                                      "site in the reference problems and is not lowered to CUDA")
         self.bond_connectivity = np.asarray(bond_connectivity, dtype=np.int64).reshape(-1, 2)
-        self.contact = True
+        self.contact = _abi.DFX_CONTACT_ANGLE if angle_based else _abi.DFX_CONTACT_DISTANCE
 
 
 class CombinedEnergy(BlockEnergy):
@@ -68,7 +69,7 @@ class CombinedEnergy(BlockEnergy):
         if contact:
             if not np.array_equal(contact[0].bond_connectivity, self.bond_connectivity):
                 raise ValueError("strain and contact energies must share the bond connectivity")
-            self.contact = True
+            self.contact = contact[0].contact
 
 
 def build_strain_energy(bond_connectivity, bond_energy_fn=ligament_energy_linearized):

@@ -75,6 +75,8 @@ enum {
 };
 #define DFX_MAX_LOAD_CONSTS 4
 
+enum { DFX_CONTACT_NONE = 0, DFX_CONTACT_ANGLE = 1, DFX_CONTACT_DISTANCE = 2 };
+
 /* ---- static topology --------------------------------------------------------------- */
 typedef struct DfxTopologyDesc {
   int32_t n_blocks;          /* rigid units                                            */
@@ -85,7 +87,8 @@ typedef struct DfxTopologyDesc {
   const int32_t* constrained_dofs; /* [n_constrained] global DOF ids block*3+dof, in the
                                       order of constrained_block_DOF_pairs               */
   int32_t bond_energy;       /* DFX_BOND_*                                              */
-  int32_t contact;           /* 1 = angle-based contact energy (energy.py:364-407)      */
+  int32_t contact;           /* DFX_CONTACT_*: 0 none, 1 angle-based (energy.py:204-219, 364-407),
+                                2 distance-based between the void edges (energy.py:222-330; generic kernels) */
   int32_t drive_kind;        /* DFX_DRIVE_*                                             */
   const double* drive_vec0;  /* [n_constrained] or NULL (= zeros)                       */
   const double* drive_vec1;  /* [n_constrained] or NULL                                 */
@@ -119,6 +122,8 @@ typedef struct DfxParams {
   DfxLeaf inertia;               /* [n_free]  (reduced to the free DOFs, dynamics.py:157-163) */
   DfxLeaf contact;               /* [3] = (min_angle, cutoff_angle, k_contact); NULL if contact==0 */
   DfxLeaf drive;                 /* [n_drive_params(kind)]                              */
+  DfxLeaf block_centroids;       /* [n_blocks*2]; read by DFX_CONTACT_DISTANCE only (the other energies depend on
+                                    displacements, not positions), NULL otherwise          */
 } DfxParams;
 
 /* cotangent outputs of dfx_adjoint, one slice per design (no sharing), same leaf shapes.
@@ -134,6 +139,7 @@ typedef struct DfxParamGrads {
   double* inertia;               /* [B][n_free]           */
   double* contact;               /* [B][3]                */
   double* drive;                 /* [B][n_drive_params]   */
+  double* block_centroids;       /* [B][n_blocks*2]; written with DFX_CONTACT_DISTANCE only (zero otherwise: leave NULL) */
 } DfxParamGrads;
 
 typedef struct DfxOptions {

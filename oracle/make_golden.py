@@ -106,7 +106,7 @@ def run_case(name, *, n_blocks, n_npb, bonds, cons, bond_energy, use_contact, dr
     aug_size = 4 * nf + 1 + sum(int(torch.as_tensor(x).numel()) for x in flat)  # = length of the literal run's augmented vector
     out = dict(
         n_blocks=n_blocks, n_npb=n_npb, bond_nodes=np.asarray(bonds, dtype=np.int32), constrained_dofs=np.asarray(cons, dtype=np.int32),
-        bond_energy=bond_energy, contact=int(use_contact), drive_kind=drive_kind,
+        bond_energy=bond_energy, contact=2 if use_contact == "distance" else int(bool(use_contact)), drive_kind=drive_kind,
         drive_vec0=np.zeros(0) if drive_vec0 is None else np.asarray(drive_vec0, dtype=np.float64),
         drive_vec1=np.zeros(0) if drive_vec1 is None else np.asarray(drive_vec1, dtype=np.float64),
         load_kind=0 if load is None else load["kind"], loaded_dofs=np.zeros(0, dtype=np.int32) if load is None else np.asarray(load["dofs"], dtype=np.int32),
@@ -126,17 +126,21 @@ def run_case(name, *, n_blocks, n_npb, bonds, cons, bond_energy, use_contact, dr
             out["grad_" + k] = gb[src].numpy()
     if use_contact:
         out["grad_contact"] = np.array([gb["min_angle"].item(), gb["cutoff_angle"].item(), gb["k_contact"].item()])
+    if use_contact == "distance":  # the only energy that reads block positions (energy.py:395-405)
+        out["leaf_block_centroids"] = np.asarray(block_centroids.detach().numpy(), dtype=np.float64)
+        out["grad_block_centroids"] = gb["block_centroids"].numpy()
     out["grad_drive"] = np.array([gb["constraint_params." + n].item() for n in names])
     os.makedirs(OUT, exist_ok=True)
     np.savez_compressed(os.path.join(OUT, name + ".npz"), **out)
     print(f"{name}: n_free={nf} fwd {st_f} {t1 - t0:.0f}s  bwd {st_b} {t2 - t1:.0f}s  aug_size={aug_size}", flush=True)
 
 
-def quad_case(name, n1, n2, *, contact_window, noise, n_t, t_end, rtol, atol, seed=0, g_mode="kinetic"):
+def quad_case(name, n1, n2, *, contact_window, noise, n_t, t_end, rtol, atol, seed=0, g_mode="kinetic", use_contact=True, angle=25.,
+              initial_rotation=0.0):
     torch.manual_seed(seed)
     geo = QuadGeometry(n1, n2, spacing=15., bond_length=2.25)
     bc, cnvf, bonds, refv = geo.get_parametrization()
-    hs, vs = geo.get_design_from_rotated_square(25 * math.pi / 180)
+    hs, vs = geo.get_design_from_rotated_square(angle * math.pi / 180)
     hs = hs + noise * torch.randn_like(hs)
     vs = vs + noise * torch.randn_like(vs)
     cnv, cent = cnvf(hs, vs), bc(hs, vs)
@@ -152,11 +156,21 @@ def quad_case(name, n1, n2, *, contact_window, noise, n_t, t_end, rtol, atol, se
         [2 * (0.36125 * rho * 15 ** 2 * 1.19) ** .5] * 2 + [2 * (0.02175026 * rho * 15 ** 4 * 1.5) ** .5])
     leaves = dict(centroid_node_vectors=cnv, reference_vector=refv(), k_stretch=T(120.), k_shear=T(1.19), k_rot=T(1.5),
                   damping=damp, inertia=inertia, contact=T([contact_window[0], contact_window[1], 1.5]))
-    run_case(name, n_blocks=geo.n_blocks, n_npb=4, bonds=bonds(), cons=cons, bond_energy=0, use_contact=True,
+    run_case(name, n_blocks=geo.n_blocks, n_npb=4, bonds=bonds(), cons=cons, bond_energy=0, use_contact=use_contact,
              drive_kind=_abi.DFX_DRIVE_PULSE, drive_vec0=lv, drive_vec1=None,
              drive_params=dict(amplitude=7.5, loading_rate=30., input_delay=0.1 / 30), load=None,
              damped_blocks=np.arange(geo.n_blocks), leaves=leaves, block_centroids=cent,
-             ts=np.linspace(0, t_end, n_t), rtol=rtol, atol=atol, density_leaf=T(rho), g_mode=g_mode)
+             ts=np.linspace(0, t_end, n_t), rtol=rtol, atol=atol, density_leaf=T(rho), g_mode=g_mode,
+             y0=_counter_rotated_state(geo, free, initial_rotation) if initial_rotation else None)
+
+
+def _counter_rotated_state(geo, free, angle):
+    """initial state with neighbouring blocks rotated by +-angle (the rotating-squares mechanism): voids close on one side,
+    so that the distance-based contact takes its point-on-edge branch, not only the hinge-to-hinge distance"""
+    u = np.zeros((geo.n_blocks, 3))
+    ids = np.arange(geo.n_blocks)
+    u[:, 2] = angle * (-1.0) ** (ids % geo.n1_blocks + ids // geo.n1_blocks)
+    return np.concatenate([u.reshape(-1)[free], np.zeros(len(free))])
 
 
 def spring_case(name, n1, n2, *, n_t, t_end, rtol, atol, seed=4):
@@ -325,6 +339,9 @@ CASES = {
     "tensile_linearized": lambda: tensile_case("tensile_linearized", 2, 1, n_t=4, t_end=60.),
     "tensile_ligament": lambda: tensile_case("tensile_ligament", 2, 0, n_t=4, t_end=60.),
     "ramp_sech2_4x3": lambda: ramp_sech2_case("ramp_sech2_4x3", 4, 3, n_t=5, t_end=0.008, rtol=1e-9, atol=1e-8),
+    # distance-based contact (energy.py:222-330, angle_based=False): window in length units around the hinge length 2.25
+    "quads_4x3_distance_contact": lambda: quad_case("quads_4x3_distance_contact", 4, 3, contact_window=(0.5, 3.0), noise=0.3, n_t=3, t_end=0.0004,
+                                                    rtol=1e-9, atol=1e-7, seed=5, g_mode="generic", use_contact="distance", initial_rotation=0.12),
     "springs_4x3": lambda: spring_case("springs_4x3", 4, 3, n_t=4, t_end=0.02, rtol=1e-8, atol=1e-6),
 }
 

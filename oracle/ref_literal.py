@@ -121,6 +121,34 @@ def void_angles(current_block_nodes, bond_connectivity):
 
 
 # ------------------------------------------------------------------ energy.py:333-361
+# energy.py:222-251, vectorised over a leading axis like the reference's vmap
+def point_to_edge_distance(point, edge):
+    x0, x1 = edge[..., 0, :], edge[..., 1, :]
+    t = ((point - x0) * (x1 - x0)).sum(-1) / ((x1 - x0) * (x1 - x0)).sum(-1)
+    inside = torch.sum((point - x0) ** 2 - (t[..., None] * (x1 - x0)) ** 2, -1) ** 0.5
+    return torch.where((t >= 0) & (t <= 1), inside,
+                       torch.where(t < 0, torch.sum((point - x0) ** 2, -1) ** 0.5, torch.sum((point - x1) ** 2, -1) ** 0.5))
+
+
+# energy.py:255-275 (jnp.min: the cotangent is shared equally among tied minima, as torch.amin does)
+def edges_distance(edge_1, edge_2):
+    d = [point_to_edge_distance(edge_2[..., 0, :], edge_1), point_to_edge_distance(edge_2[..., 1, :], edge_1),
+         point_to_edge_distance(edge_1[..., 0, :], edge_2), point_to_edge_distance(edge_1[..., 1, :], edge_2)]
+    return torch.amin(torch.stack(d, -1), -1)
+
+
+# energy.py:282-328
+def void_edge_distance(current_block_nodes, bond_connectivity):
+    npb = current_block_nodes.shape[1]
+    n1, n2 = bond_connectivity[:, 0], bond_connectivity[:, 1]
+    at = lambda n, shift: current_block_nodes[n // npb, (n + shift) % npb]  # noqa: E731
+    pts1, pts1_prev, pts1_next = at(n1, 0), at(n1, -1), at(n1, 1)
+    pts2, pts2_prev, pts2_next = at(n2, 0), at(n2, -1), at(n2, 1)
+    d1 = edges_distance(torch.stack((pts1, pts1_next), 1), torch.stack((pts2, pts2_prev), 1))
+    d2 = edges_distance(torch.stack((pts1, pts1_prev), 1), torch.stack((pts2, pts2_next), 1))
+    return torch.cat((d1, d2))
+
+
 def contact_energy(current_void_angles, min_angle, cutoff_angle, k_contact):
     x = (current_void_angles - cutoff_angle) / (cutoff_angle - min_angle)
     inner = k_contact / 4 * (cutoff_angle - min_angle) ** 2 * ((x + 1) ** -1 - (x - 1) ** -1 - 2)
@@ -184,8 +212,8 @@ class Problem:
                                     reference_vector=P["reference_vector"])
         if self.use_contact:
             current = P["block_centroids"][:, None] + cnv + node_disp[:, :, :2]
-            E = E + contact_energy(void_angles(current, self.bonds), P["min_angle"], P["cutoff_angle"],
-                                   P["k_contact"]).sum()
+            gaps = void_edge_distance(current, self.bonds) if self.use_contact == "distance" else void_angles(current, self.bonds)
+            E = E + contact_energy(gaps, P["min_angle"], P["cutoff_angle"], P["k_contact"]).sum()
         return E
 
     # dynamics.py:33-55 ; loading.py:36-45, 96-104

@@ -28,7 +28,7 @@ def load_golden(name) -> Case:
     z = np.load(os.path.join(GOLDEN, name + ".npz"))
     spec = _abi.TopologySpec(
         int(z["n_blocks"]), int(z["n_npb"]), z["bond_nodes"], z["constrained_dofs"], int(z["bond_energy"]),
-        bool(z["contact"]), int(z["drive_kind"]),
+        int(z["contact"]), int(z["drive_kind"]),
         z["drive_vec0"] if z["drive_vec0"].size else None, z["drive_vec1"] if z["drive_vec1"].size else None,
         int(z["load_kind"]), z["loaded_dofs"], None, tuple(z["load_consts"]), z["damped_blocks"])
     leaves = {n: z["leaf_" + n] for n in LEAVES if "leaf_" + n in z.files}

@@ -36,9 +36,9 @@ def test_ctypes_struct_layout_matches_header_sizes():
     assert C.sizeof(_abi.DfxStats) == 40
     assert C.sizeof(_abi.DfxLeaf) == 16
     assert C.sizeof(_abi.DfxOptions) == 24
-    assert C.sizeof(_abi.DfxParamGrads) == 9 * 8
+    assert C.sizeof(_abi.DfxParamGrads) == 10 * 8
     # DfxParams: 5 leaves, int[3] (+pad), leaf, int (+pad), 3 leaves
-    assert C.sizeof(_abi.DfxParams) == 5 * 16 + 16 + 16 + 8 + 3 * 16
+    assert C.sizeof(_abi.DfxParams) == 5 * 16 + 16 + 16 + 8 + 4 * 16
 
 
 def test_topology_create_reports_errors_instead_of_crashing():

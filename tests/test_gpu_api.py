@@ -46,6 +46,61 @@ def test_setup_dynamic_solver_matches_oracle_fields():
     assert rel_l2(fields.cpu().numpy(), ref) <= 1e-6
 
 
+def test_distance_based_contact_through_the_api_matches_the_oracle():
+    """build_contact_energy(bonds, angle_based=False) (reference energy.py:222-330, 364-407) through setup_dynamic_solver:
+    fields and the gradient of a functional w.r.t. block_centroids / centroid_node_vectors / contact parameters against
+    the C++ oracle (itself pinned to torch autograd of the literal energy in tests/test_oracle.py)"""
+    from difflexmm_b200 import _abi
+    from difflexmm_b200.dynamics import setup_dynamic_solver
+    from difflexmm_b200.energy import build_contact_energy, build_strain_energy, combine_block_energies, ligament_energy
+    from difflexmm_b200.geometry import QuadGeometry
+    from difflexmm_b200.utils import ContactParams
+    from oracle import Oracle
+    P = _problem(simulation_time=0.003, n_timepoints=4, rtol=1e-9, atol=1e-8)
+    spec0, drive = P.lower()
+    geo = QuadGeometry(P.n1_blocks, P.n2_blocks, spacing=P.spacing, bond_length=P.bond_length)
+    bonds = geo.get_parametrization()[2]()
+    energy = combine_block_energies(build_strain_energy(bonds, ligament_energy), build_contact_energy(bonds, angle_based=False))
+    assert energy.contact == _abi.DFX_CONTACT_DISTANCE
+    solve_dynamics = setup_dynamic_solver(geo, energy, constrained_block_DOF_pairs=P.constrained_block_DOF_pairs,
+                                          constrained_DOFs_fn=drive, damped_blocks=np.arange(geo.n_blocks), rtol=P.rtol, atol=P.atol)
+    design = P.initial_design()
+    cp = P.control_params(design, "cuda")
+    # contact window in length units around the hinge length (the gap never exceeds it): contact always active
+    window = ContactParams(min_angle=torch.tensor(0.25 * P.bond_length, dtype=torch.float64),
+                           cutoff_angle=torch.tensor(1.5 * P.bond_length, dtype=torch.float64),
+                           k_contact=cp.mechanical_params.contact_params.k_contact)
+    cen = cp.geometrical_params.block_centroids.clone().requires_grad_(True)
+    cnv = cp.geometrical_params.centroid_node_vectors.clone().requires_grad_(True)
+    kc = torch.tensor(float(window.k_contact), dtype=torch.float64, device="cuda", requires_grad=True)
+    cp = cp._replace(geometrical_params=cp.geometrical_params._replace(block_centroids=cen, centroid_node_vectors=cnv),
+                     mechanical_params=cp.mechanical_params._replace(contact_params=window._replace(k_contact=kc)))
+    fields = solve_dynamics(torch.zeros(2, geo.n_blocks, 3, dtype=torch.float64), P.timepoints(), cp)
+    w = torch.linspace(0.5, 1.5, fields.numel(), dtype=torch.float64, device="cuda").reshape(fields.shape)
+    (w * torch.sin(fields)).sum().backward()
+    assert cen.grad is not None and float(cen.grad.abs().max()) > 0
+    # the same solve on the oracle, at the solver boundary
+    solver = solve_dynamics.solver if hasattr(solve_dynamics, "solver") else solve_dynamics
+    spec = solver.spec
+    assert spec.contact == _abi.DFX_CONTACT_DISTANCE
+    from difflexmm_b200.dynamics import lower_params
+    leaves, pb, dpd, aug = lower_params(spec, drive, cp, None, "cuda", inertia_full=None)
+    orc = Oracle(spec)
+    lv = {k: v.detach().cpu().numpy() for k, v in leaves.items()}
+    ps = orc.params(1, lv, pb, dpd)
+    ts = P.timepoints().numpy()
+    ys, st = orc.forward(ps, np.zeros(2 * spec.n_free), ts, P.rtol, P.atol)
+    ref = orc.expand_fields(ps, ys, ts)[0]
+    assert rel_l2(fields.detach().cpu().numpy(), ref) <= 1e-6
+    # cotangent of the free-DOF trajectory: constrained DOFs follow the drive, whose parameters are not differentiated here
+    gf = (w * torch.cos(fields)).detach().cpu().numpy()
+    free = np.asarray(spec.free_dofs)
+    g = np.concatenate([gf[:, 0].reshape(len(ts), -1)[:, free], gf[:, 1].reshape(len(ts), -1)[:, free]], axis=1)
+    _, _, gr, sb = orc.adjoint(ps, ys, ts, g[None], P.rtol, P.atol, aug)
+    assert rel_l2(cen.grad.cpu().numpy(), gr["block_centroids"][0]) <= 1e-5
+    assert abs(kc.grad.item() - gr["contact"][0][2]) <= 1e-5 * abs(gr["contact"][0][2])
+
+
 def test_design_gradient_through_the_solver_matches_finite_differences():
     """value_and_grad(target kinetic energy)(design) -- the hot call of the reference's optimisation loop
     (problems/quads_focusing.py:565-569) -- against central differences of the forward solve"""

@@ -69,7 +69,9 @@ def test_forward_matches_golden(name, forward_kernel_mode):
     st = stats.numpy()[0]
     assert st["status"] == 0
     assert rel_l2(ys[0].cpu().numpy(), c.ref["ys"]) <= TRAJ_TOL
-    assert abs(int(st["steps"]) - int(c.ref["fwd_steps"])) <= max(2, int(0.01 * c.ref["fwd_steps"]))
+    # distance-based contact has a discontinuous force (min over vertex / edge pairs): rejected steps depend on round-off
+    slack = 0.10 if c.spec.contact == _abi.DFX_CONTACT_DISTANCE else 0.01
+    assert abs(int(st["steps"]) - int(c.ref["fwd_steps"])) <= max(2, int(slack * c.ref["fwd_steps"]))
 
 
 @pytest.fixture(params=["fast_tmem", "v2", "notmem", "generic", "cluster4", "cluster16", "group40"])
@@ -92,7 +94,8 @@ def test_adjoint_matches_golden(name, adjoint_kernel_mode):
     st = stats.numpy()[0]
     assert st["status"] == 0
     # step counts are a diagnostic: at tight tolerances borderline accept/reject decisions flip on round-off
-    assert abs(int(st["steps"]) - int(c.ref["bwd_steps"])) <= max(2, int(0.03 * c.ref["bwd_steps"]))
+    slack = 0.10 if c.spec.contact == _abi.DFX_CONTACT_DISTANCE else 0.03
+    assert abs(int(st["steps"]) - int(c.ref["bwd_steps"])) <= max(2, int(slack * c.ref["bwd_steps"]))
     assert rel_l2(y0_bar[0].cpu().numpy(), c.ref["y0_bar"]) <= GRAD_TOL
     assert rel_l2(ts_bar[0].cpu().numpy(), c.ref["ts_bar"]) <= GRAD_TOL
     for k, v in grads.items():
@@ -119,6 +122,7 @@ def test_default_adjoint_kernel_choice(monkeypatch):
     assert seen["quads_5x4_tight"].startswith("adjoint3_kernel<4,"), seen
     assert seen["kagome_3x2_perbond"].startswith("adjoint2_kernel"), seen
     assert seen["springs_4x3"].startswith("adjoint_kernel"), seen
+    assert seen["quads_4x3_distance_contact"].startswith("adjoint_kernel"), seen
     monkeypatch.setenv("DFX_ADJOINT_KERNEL", "v2")
     c = load_golden("quads_4x3_contact_active")
     lib, topo = _solver(c.spec)

@@ -24,18 +24,98 @@ def test_oracle_matches_literal_golden(name):
     ps = orc.params(1, c.leaves, c.per_bond, c.damping_per_dof)
     ys, st = orc.forward(ps, c.y0, c.ts, c.rtol, c.atol)
     assert st["status"][0] == 0
-    assert int(st["steps"][0]) == int(c.ref["fwd_steps"]) and int(st["accepted"][0]) == int(c.ref["fwd_accepted"])
-    assert rel_l2(ys[0], c.ref["ys"]) < 1e-9
+    # distance-based contact: the force jumps where the closest vertex / edge pair of a void changes (the gap is a min of
+    # four distances, energy.py:255-275), so the step-size controller rejects steps there and the rejections depend on
+    # round-off: same accepted steps, a few more or fewer rejected ones, results equal at the integration tolerance
+    # (the two RHS themselves agree to 1e-15: test_distance_contact_rhs_matches_the_literal_restatement)
+    nonsmooth = c.spec.contact == _abi.DFX_CONTACT_DISTANCE
+    traj_tol, grad_tol = (1e-6, 1e-6) if nonsmooth else (1e-9, 1e-7)
+    if nonsmooth:
+        assert abs(int(st["steps"][0]) - int(c.ref["fwd_steps"])) <= 0.05 * c.ref["fwd_steps"]
+        assert abs(int(st["accepted"][0]) - int(c.ref["fwd_accepted"])) <= 0.02 * c.ref["fwd_accepted"]
+    else:
+        assert int(st["steps"][0]) == int(c.ref["fwd_steps"]) and int(st["accepted"][0]) == int(c.ref["fwd_accepted"])
+    assert rel_l2(ys[0], c.ref["ys"]) < traj_tol
     y0b, tsb, gr, sb = orc.adjoint(ps, c.ref["ys"][None], c.ts, c.g[None], c.rtol, c.atol, aug_size=c.aug_size)
     assert sb["status"][0] == 0
     # borderline accept / reject decisions flip on round-off: the count is a diagnostic, the cotangents are the check
-    assert abs(int(sb["steps"][0]) - int(c.ref["bwd_steps"])) <= max(3, int(0.005 * c.ref["bwd_steps"]))
-    assert rel_l2(y0b[0], c.ref["y0_bar"]) < 1e-7
+    assert abs(int(sb["steps"][0]) - int(c.ref["bwd_steps"])) <= max(3, int((0.05 if nonsmooth else 0.005) * c.ref["bwd_steps"]))
+    assert rel_l2(y0b[0], c.ref["y0_bar"]) < grad_tol
     assert rel_l2(tsb[0], c.ref["ts_bar"]) < 1e-6
     for k, v in gr.items():
         key = "grad_" + k
         if key in c.ref and np.abs(c.ref[key]).max() > 1e-9:
-            assert rel_l2(v[0], c.ref[key]) < 1e-7, k
+            assert rel_l2(v[0], c.ref[key]) < grad_tol, k
+
+
+def test_distance_contact_rhs_matches_the_literal_restatement():
+    """distance-based contact (reference energy.py:222-330, build_contact_energy(angle_based=False)): the closed-form
+    force of the C++ oracle against torch autograd of the literal energy, at the fixture's counter-rotated start and at
+    random states (point-on-edge and end-point branches both occur), and the augmented RHS (H w and every parameter
+    cotangent, block_centroids included) against the literal vector-Jacobian product"""
+    import torch
+    from oracle import ref_literal as L
+    c = load_golden("quads_4x3_distance_contact")
+    orc = Oracle(c.spec)
+    ps = orc.params(1, c.leaves, c.per_bond, c.damping_per_dof)
+    T = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64)  # noqa: E731
+    lv = c.leaves
+    prob = L.Problem(c.spec.n_blocks, c.spec.n_npb, c.spec.bond_nodes, c.spec.constrained_dofs, bond_energy="ligament",
+                     use_contact="distance", constrained_DOFs_fn=None, damped_blocks=c.spec.damped_blocks)
+    P = dict(block_centroids=T(lv["block_centroids"]), centroid_node_vectors=T(lv["centroid_node_vectors"]), k_stretch=T(lv["k_stretch"]),
+             k_shear=T(lv["k_shear"]), k_rot=T(lv["k_rot"]), reference_vector=T(lv["reference_vector"]), inertia=T(lv["inertia"]),
+             damping=T(lv["damping"]), min_angle=T(lv["contact"][0]), cutoff_angle=T(lv["contact"][1]), k_contact=T(lv["contact"][2]),
+             constraint_params={}, loading_params={})
+    rng = np.random.default_rng(0)
+    nf = c.spec.n_free
+    branches = set()
+    for trial in range(4):
+        y = c.y0.copy() if trial == 0 else c.y0 + np.concatenate([0.3 * rng.standard_normal(nf), rng.standard_normal(nf)])
+        a = orc.rhs(ps, y, 0.0)
+        with torch.enable_grad():
+            b = prob.rhs(T(y), torch.tensor(0.0, dtype=torch.float64), P, create_graph=False).detach().numpy()
+        assert np.abs(a - b).max() <= 1e-13 * np.abs(b).max()
+        # which branch the gaps take: below the hinge-to-hinge distance = a point-on-edge (or far-end) candidate won
+        U = np.zeros(3 * c.spec.n_blocks)
+        U[c.spec.free_dofs] = y[:nf]
+        disp = T(U.reshape(-1, 3))
+        cnv = P["centroid_node_vectors"]
+        cur = P["block_centroids"][:, None] + cnv + L.block_to_node_kinematics(disp, cnv)[:, :, :2]
+        bonds = torch.as_tensor(np.asarray(c.spec.bond_nodes), dtype=torch.int64)
+        gaps = L.void_edge_distance(cur, bonds)
+        flat = cur.reshape(-1, 2)
+        hinge = (flat[bonds[:, 0]] - flat[bonds[:, 1]]).norm(dim=1).repeat(2)
+        branches |= {"hinge"} if bool((gaps >= hinge - 1e-12).any()) else set()
+        branches |= {"edge"} if bool((gaps < hinge - 1e-9).any()) else set()
+        # augmented RHS: z = [y | y_bar | t0_bar | leaves], literal vjp through torch autograd
+        names, leaves = L.flatten_leaves(P)
+        ybar = rng.standard_normal(2 * nf)
+        with torch.enable_grad():
+            yy = T(y).requires_grad_(True)
+            ll = [T(x).clone().requires_grad_(True) for x in leaves]
+            ydot = prob.rhs(yy, torch.tensor(0.0, dtype=torch.float64), L._rebuild(P, names, ll), create_graph=True)
+            grads = torch.autograd.grad(ydot, [yy] + ll, grad_outputs=T(ybar), allow_unused=True)
+        lit = {n: (np.zeros(tuple(x.shape)) if gq is None else gq.numpy()) for n, gq, x in zip(names, grads[1:], ll)}
+        z = np.zeros(orc.aug_size(ps))
+        z[:2 * nf], z[2 * nf:4 * nf] = y, ybar
+        out = orc.aug_rhs(ps, z, 0.0)
+        assert np.abs(out[2 * nf:4 * nf] - grads[0].numpy()).max() <= 1e-12 * np.abs(grads[0].numpy()).max()
+        # layout of the oracle's quadratures (oracle/dfx_oracle.cpp aug_layout): cnv, ref, ks, ksh, kr, damping, inertia, contact, drive, centroids
+        o = 4 * nf + 1
+        nn, nb = c.spec.n_blocks * c.spec.n_npb, c.spec.n_bonds
+        for name, size in (("centroid_node_vectors", 2 * nn), ("reference_vector", 2 * nb), ("k_stretch", 1), ("k_shear", 1), ("k_rot", 1),
+                           ("damping", 3 * len(c.spec.damped_blocks)), ("inertia", nf)):
+            ref = lit[name].reshape(-1)
+            if name == "damping":  # entries on constrained DOFs have no equation
+                ref = ref.copy()
+            assert np.abs(out[o:o + size] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max()), name
+            o += size
+        ref = np.array([lit["min_angle"], lit["cutoff_angle"], lit["k_contact"]]).reshape(-1)
+        assert np.abs(out[o:o + 3] - ref).max() <= 1e-11 * max(1.0, np.abs(ref).max())
+        o += 3 + c.spec.n_drive_params
+        ref = lit["block_centroids"].reshape(-1)
+        assert np.abs(ref).max() > 0 and np.abs(out[o:o + ref.size] - ref).max() <= 1e-11 * np.abs(ref).max()
+    assert branches == {"hinge", "edge"}
 
 
 def _rotated_square_chain(n1_cells):

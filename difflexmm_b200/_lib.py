@@ -41,6 +41,7 @@ EXPORTS = ("dfx_topology_create", "dfx_topology_destroy", "dfx_topology_n_free",
            "dfx_forward_workspace_bytes", "dfx_adjoint_workspace_bytes", "dfx_forward", "dfx_adjoint",
            "dfx_expand_fields", "dfx_objective", "dfx_adjoint_objective",
            "dfx_geometry_create", "dfx_geometry_destroy", "dfx_geometry_forward", "dfx_geometry_vjp",
+           "dfx_rotated_square_forward", "dfx_rotated_square_vjp",
            "dfx_constraints_create", "dfx_constraints_destroy", "dfx_constraints_rows", "dfx_constraints_columns", "dfx_constraints_eval",
            "dfx_fp64_peak", "dfx_math_selftest", "dfx_sincos_selftest", "dfx_adjoint_plan", "dfx_last_error", "dfx_version")
 
@@ -82,6 +83,35 @@ class GeometryHandle:
         h, self._h = getattr(self, "_h", None), None
         if h:
             lib.dfx_geometry_destroy(h)
+
+
+def rotated_square_forward(n1_blocks, n2_blocks, half_side, angle, density):
+    """angle (B,), density (B,) or () -> cnv (B, n_blocks, 4, 2), inertia (B, n_blocks, 3)"""
+    dev, B, nb = angle.device, angle.shape[0], n1_blocks * n2_blocks
+    angle, density = angle.contiguous(), density.contiguous()
+    cnv = torch.empty((B, nb, 4, 2), dtype=torch.float64, device=dev)
+    inertia = torch.empty((B, nb, 3), dtype=torch.float64, device=dev)
+    with torch.cuda.device(dev):
+        _check(lib.dfx_rotated_square_forward(int(n1_blocks), int(n2_blocks), C.c_double(half_side), B, C.c_void_p(angle.data_ptr()),
+                                              C.c_void_p(density.data_ptr()), C.c_int64(1 if density.dim() == 1 else 0),
+                                              C.c_void_p(cnv.data_ptr()), C.c_void_p(inertia.data_ptr()), _stream_ptr(dev)),
+               "dfx_rotated_square_forward")
+    return cnv, inertia
+
+
+def rotated_square_vjp(n1_blocks, n2_blocks, half_side, angle, density, cnv_bar, inertia_bar, want_density_bar=False):
+    dev, B = angle.device, angle.shape[0]
+    angle, density = angle.contiguous(), density.contiguous()
+    cnv_bar, inertia_bar = [None if t is None else t.contiguous() for t in (cnv_bar, inertia_bar)]
+    ptr = lambda t: C.c_void_p(t.data_ptr()) if t is not None else C.c_void_p(None)
+    angle_bar = torch.empty((B,), dtype=torch.float64, device=dev)
+    density_bar = torch.empty((B,), dtype=torch.float64, device=dev) if want_density_bar else None
+    with torch.cuda.device(dev):
+        _check(lib.dfx_rotated_square_vjp(int(n1_blocks), int(n2_blocks), C.c_double(half_side), B, C.c_void_p(angle.data_ptr()),
+                                          C.c_void_p(density.data_ptr()), C.c_int64(1 if density.dim() == 1 else 0), ptr(cnv_bar),
+                                          ptr(inertia_bar), C.c_void_p(angle_bar.data_ptr()), ptr(density_bar), _stream_ptr(dev)),
+               "dfx_rotated_square_vjp")
+    return angle_bar, density_bar
 
 
 class ConstraintsHandle:

@@ -185,11 +185,13 @@ MultiCta pick_multi_cta(const DevTopo& T, int batch, int sm_count) {
     if (n > 1) return {2, n};
     return {0, 1};
   }
-  if (!std::getenv("DFX_CLUSTER") && T.n_bonds >= kGroupMinBonds && 2LL * kMaxCluster * batch <= sm_count) {
-    // a lattice this large keeps more SMs busy than a cluster can span
+  if (!std::getenv("DFX_CLUSTER") && T.n_bonds >= kGroupMinBonds && 8LL * batch <= sm_count) {
+    // a lattice this large keeps more SMs busy than a cluster can span; for a small batch of them a group of
+    // SMs / batch CTAs also beats 16-CTA clusters, of which only a few fit the GPCs at a time (8 lattices of 100 x 100:
+    // 2.1 lattices/s with groups of 18 against 1.26 with clusters of 16, profiles/r02_lattice_timing.jsonl)
     int n = kGroupDefault;
     if ((long long)n * batch > sm_count) n = sm_count / batch;
-    if (n > kMaxCluster) return {2, n};
+    if (n >= 8) return {2, n};
   }
   const int cl = pick_cluster(T, batch, sm_count);
   return {cl > 1 ? 1 : 0, cl};
@@ -848,6 +850,35 @@ int dfx_geometry_vjp(const DfxGeometry* g, int batch, const double* design, cons
   cudaError_t e = cudaGetLastError();
   cudaFreeAsync(node_bar, stream);
   if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "geometry_vjp launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
+
+}  // extern "C"
+
+// ---- RotatedSquareGeometry design map (dfx_geometry.cuh) -----------------------------------------------------------
+extern "C" {
+
+int dfx_rotated_square_forward(int n1_blocks, int n2_blocks, double half_side, int batch, const double* angle, const double* density,
+                               int64_t density_bstride, double* cnv, double* inertia, void* stream_) {
+  if (!angle || !cnv || (inertia && !density)) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (n1_blocks <= 0 || n2_blocks <= 0 || batch <= 0 || !(half_side > 0.0)) return fail(DFX_ERR_INVALID, "bad rotated-square sizes");
+  const int nb = n1_blocks * n2_blocks, threads = 128;
+  dim3 grid((nb + threads - 1) / threads, batch);
+  rotated_square_forward_kernel<<<grid, threads, 0, (cudaStream_t)stream_>>>(n1_blocks, nb, half_side, angle, density, density_bstride, cnv, inertia);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "rotated_square_forward launch failed: %s", cudaGetErrorString(e));
+  return DFX_OK;
+}
+
+int dfx_rotated_square_vjp(int n1_blocks, int n2_blocks, double half_side, int batch, const double* angle, const double* density,
+                           int64_t density_bstride, const double* cnv_bar, const double* inertia_bar, double* angle_bar,
+                           double* density_bar, void* stream_) {
+  if (!angle || !angle_bar || (inertia_bar && !density)) return fail(DFX_ERR_INVALID, "NULL argument");
+  if (n1_blocks <= 0 || n2_blocks <= 0 || batch <= 0 || !(half_side > 0.0)) return fail(DFX_ERR_INVALID, "bad rotated-square sizes");
+  rotated_square_vjp_kernel<<<batch, 256, 0, (cudaStream_t)stream_>>>(n1_blocks, n1_blocks * n2_blocks, half_side, angle, density,
+                                                                     density_bstride, cnv_bar, inertia_bar, angle_bar, density_bar);
+  cudaError_t e = cudaGetLastError();
+  if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "rotated_square_vjp launch failed: %s", cudaGetErrorString(e));
   return DFX_OK;
 }
 

@@ -221,3 +221,78 @@ __global__ void constraints_kernel(DevGeometry G, const ConstraintRow* rows, int
 }
 
 }  // namespace dfx
+
+// ---- RotatedSquareGeometry: one design angle per lattice (reference geometry.py:354-443) --------------------------
+// Block k = (i1, i2) of the n1 x n2 grid (i1 fastest) is a square whose half-diagonal direction is rotated by
+// parity * angle, parity = (-1)^(i1 + i2):  vertex_l = R(l * pi/2) * half * (1, tan(parity * angle)),  l = 0..3
+// (the polygon centroid is the block centre, so these are the centroid_node_vectors), inertia = density * (A, A, J).
+namespace dfx {
+
+template <class T>
+__device__ __forceinline__ void rotated_square_vertices(T a, double half, T* vx, T* vy) {
+  T sn, cs;
+  if constexpr (sizeof(T) == sizeof(double)) { double s_, c_; sincos(val(a), &s_, &c_); sn = make_T<T>(s_, 0.0); cs = make_T<T>(c_, 0.0); }
+  else { double s_, c_; sincos(val(a), &s_, &c_); sn = make_T<T>(s_, c_ * dot_part(a)); cs = make_T<T>(c_, -s_ * dot_part(a)); }
+  const T x = make_T<T>(half, 0.0), y = sn * recipT(cs) * half;
+  vx[0] = x; vy[0] = y;          // quarter turns: (x, y) -> (-y, x) -> (-x, -y) -> (y, -x)
+  vx[1] = -y; vy[1] = x;
+  vx[2] = -x; vy[2] = -y;
+  vx[3] = y; vy[3] = -x;
+}
+
+// grid (ceil(n_blocks / blockDim), batch)
+__global__ void rotated_square_forward_kernel(int n1, int n_blocks, double half, const double* angle, const double* density,
+                                              long long density_bstride, double* cnv, double* inertia) {
+  const int b = blockIdx.y, k = blockIdx.x * blockDim.x + threadIdx.x;
+  if (k >= n_blocks) return;
+  const double parity = ((k % n1 + k / n1) & 1) ? -1.0 : 1.0;
+  double vx[4], vy[4];
+  rotated_square_vertices<double>(parity * angle[b], half, vx, vy);
+  double* o = cnv + ((long long)b * n_blocks + k) * 8;
+#pragma unroll
+  for (int l = 0; l < 4; ++l) { o[2 * l] = vx[l]; o[2 * l + 1] = vy[l]; }
+  if (inertia) {
+    double cx, cy, A, J;
+    polygon_props<double>(vx, vy, 4, cx, cy, A, J);
+    const double rho = density[(long long)b * density_bstride];
+    double* q = inertia + ((long long)b * n_blocks + k) * 3;
+    q[0] = rho * A; q[1] = rho * A; q[2] = rho * J;
+  }
+}
+
+// one CTA per design: angle_bar = sum_blocks parity * d/da (<cnv_bar, cnv> + <inertia_bar, rho (A, A, J)>), one dual pass per block
+__global__ void rotated_square_vjp_kernel(int n1, int n_blocks, double half, const double* angle, const double* density,
+                                          long long density_bstride, const double* cnv_bar, const double* inertia_bar,
+                                          double* angle_bar, double* density_bar) {
+  __shared__ double red[40];
+  const int b = blockIdx.x;
+  const double rho = density ? density[(long long)b * density_bstride] : 0.0;
+  double ga = 0.0, grho = 0.0;
+  for (int k = threadIdx.x; k < n_blocks; k += blockDim.x) {
+    const double parity = ((k % n1 + k / n1) & 1) ? -1.0 : 1.0;
+    Dual vx[4], vy[4];
+    rotated_square_vertices<Dual>(Dual(parity * angle[b], parity), half, vx, vy);
+    double s = 0.0;
+    if (cnv_bar) {
+      const double* g = cnv_bar + ((long long)b * n_blocks + k) * 8;
+#pragma unroll
+      for (int l = 0; l < 4; ++l) s += g[2 * l] * vx[l].d + g[2 * l + 1] * vy[l].d;
+    }
+    if (inertia_bar) {
+      Dual cx, cy, A, J;
+      polygon_props<Dual>(vx, vy, 4, cx, cy, A, J);
+      const double* g = inertia_bar + ((long long)b * n_blocks + k) * 3;
+      s += rho * ((g[0] + g[1]) * A.d + g[2] * J.d);
+      grho += (g[0] + g[1]) * A.v + g[2] * J.v;
+    }
+    ga += s;
+  }
+  const double ta = block_sum(ga, red);
+  if (threadIdx.x == 0) angle_bar[b] = ta;
+  if (density_bar) {
+    const double tr = block_sum(grho, red);
+    if (threadIdx.x == 0) density_bar[b] = tr;
+  }
+}
+
+}  // namespace dfx

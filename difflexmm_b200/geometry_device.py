@@ -93,6 +93,52 @@ class DeviceGeometry:
         return cnv, cen, inertia
 
 
+class _AngleToParams(torch.autograd.Function):
+    @staticmethod
+    def forward(ctx, drs, angle, density):
+        from . import _lib
+        cnv, inertia = _lib.rotated_square_forward(drs.n1_blocks, drs.n2_blocks, drs.half_side, angle, density)
+        ctx.drs = drs
+        ctx.save_for_backward(angle, density)
+        return cnv, inertia
+
+    @staticmethod
+    def backward(ctx, cnv_bar, inertia_bar):
+        angle, density = ctx.saved_tensors
+        want_rho = ctx.needs_input_grad[2]
+        from . import _lib
+        d = ctx.drs
+        angle_bar, rho_bar = _lib.rotated_square_vjp(d.n1_blocks, d.n2_blocks, d.half_side, angle, density, cnv_bar, inertia_bar, want_rho)
+        if want_rho and density.dim() == 0:
+            rho_bar = rho_bar.sum()
+        return None, angle_bar, rho_bar
+
+
+class DeviceRotatedSquare:
+    """Device-side design map of `RotatedSquareGeometry` (reference `geometry.py:354-443`): the design is one angle per
+    lattice (libdfx `dfx_rotated_square_forward` / `_vjp`); the block centroids do not depend on it."""
+
+    def __init__(self, geometry, device="cuda"):
+        from . import _lib  # noqa: F401  (raises if the CUDA library is missing)
+        if not hasattr(geometry, "_computed"):
+            geometry.compute_geometry()
+        self.geometry, self.device = geometry, torch.device(device)
+        self.n1_blocks, self.n2_blocks, self.n_blocks = geometry.n1_blocks, geometry.n2_blocks, geometry.n_blocks
+        self.half_side = (geometry.spacing - geometry.bond_length) / 2
+        self.centroids = geometry.block_centroids().to(self.device)
+
+    def __call__(self, angle, density):
+        """angle () or (B,) -> centroid_node_vectors ([B,] n_blocks, 4, 2), block_centroids (n_blocks, 2), inertia ([B,] n_blocks, 3);
+        differentiable w.r.t. the angle and the density"""
+        a = torch.as_tensor(angle, dtype=_F64, device=self.device)
+        batched = a.dim() == 1
+        rho = torch.as_tensor(density, dtype=_F64, device=self.device)
+        cnv, inertia = _AngleToParams.apply(self, a.reshape(-1), rho)
+        if not batched:
+            return cnv[0], self.centroids, inertia[0]
+        return cnv, self.centroids, inertia
+
+
 class DeviceConstraints:
     """Angle and edge-length inequality constraints of a lattice design (`<= 0` when satisfied) with their sparse
     Jacobian, one kernel launch per batch of designs (libdfx `dfx_constraints_eval`; reference

@@ -251,6 +251,17 @@ int dfx_geometry_vjp(const DfxGeometry* geo, int batch, const double* design, co
                      const double* inertia_bar /* or NULL */, double* design_bar /*[B][n_design][2]*/,
                      double* density_bar /*[B] or NULL*/, void* stream);
 
+/* RotatedSquareGeometry (geometry.py:354-443): the design is ONE angle per lattice.  Block (i1, i2) of the
+ * n1_blocks x n2_blocks grid (i1 fastest) has vertices R(l pi/2) * half_side * (1, tan(+-angle)), sign (-1)^(i1+i2),
+ * half_side = (spacing - bond_length) / 2; inertia = density * (area, area, polar moment) (geometry.py:71-160).
+ * The VJP returns angle_bar[b] = <cnv_bar, d cnv/d angle> + <inertia_bar, d inertia/d angle> (and density_bar). */
+int dfx_rotated_square_forward(int n1_blocks, int n2_blocks, double half_side, int batch, const double* angle /*[B]*/,
+                               const double* density, int64_t density_bstride /* 0 = shared */,
+                               double* cnv /*[B][n_blocks][4][2]*/, double* inertia /*[B][n_blocks][3] or NULL*/, void* stream);
+int dfx_rotated_square_vjp(int n1_blocks, int n2_blocks, double half_side, int batch, const double* angle, const double* density,
+                           int64_t density_bstride, const double* cnv_bar /* or NULL */, const double* inertia_bar /* or NULL */,
+                           double* angle_bar /*[B]*/, double* density_bar /*[B] or NULL*/, void* stream);
+
 /* ---- inequality constraints of the design and their Jacobian on the device ----------------------
  * Replaces OptimizationProblem.setup_angle_constraints / setup_edge_length_constraints
  * (problems/quads_focusing.py:473-544) and the jit(jacobian(...)) evaluated inside the nlopt callbacks (:585-588,

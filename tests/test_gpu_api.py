@@ -489,6 +489,36 @@ def test_constrained_batched_mma_gives_a_feasible_ascent():
     assert (best_f >= J0 * (1 - 1e-12)).all() and (best_f > J0 * 1.001).any()
 
 
+def test_device_rotated_square_map_matches_the_torch_design_map():
+    """rest of SURVEY 8 f1: RotatedSquareGeometry (reference geometry.py:354-443), design = one angle per lattice, on the
+    device (dfx_rotated_square_forward / _vjp) against the torch map + compute_inertia: values 1e-14, VJP 1e-12"""
+    from difflexmm_b200.geometry import RotatedSquareGeometry, compute_inertia
+    from difflexmm_b200.geometry_device import DeviceRotatedSquare
+    geo = RotatedSquareGeometry(3, 2, spacing=15.0, bond_length=2.25)
+    geo.compute_geometry()
+    rho = 6.18e-9
+    angles = torch.tensor([0.35, -0.2, 0.05], dtype=torch.float64)
+    a_ref = angles.clone().requires_grad_(True)
+    cnv_r = torch.stack([geo.centroid_node_vectors(a_ref[i]) for i in range(3)])
+    ine_r = compute_inertia(cnv_r, torch.tensor(rho, dtype=torch.float64))
+    drs = DeviceRotatedSquare(geo, "cuda")
+    a_dev = angles.clone().cuda().requires_grad_(True)
+    rho_dev = torch.tensor(rho, dtype=torch.float64, device="cuda", requires_grad=True)
+    cnv, cen, ine = drs(a_dev, rho_dev)
+    assert cnv.shape == cnv_r.shape and rel_l2(cnv.detach().cpu().numpy(), cnv_r.detach().numpy()) <= 1e-14
+    assert rel_l2(ine.detach().cpu().numpy(), ine_r.detach().numpy()) <= 1e-13
+    assert torch.equal(cen.cpu(), geo.block_centroids())
+    rng = np.random.default_rng(2)
+    w_cnv = torch.from_numpy(rng.standard_normal(cnv_r.shape))
+    w_ine = torch.from_numpy(rng.standard_normal(ine_r.shape)) / ine_r.detach().abs()
+    ((cnv_r * w_cnv).sum() + (ine_r * w_ine).sum()).backward()
+    ((cnv * w_cnv.cuda()).sum() + (ine * w_ine.cuda()).sum()).backward()
+    assert rel_l2(a_dev.grad.cpu().numpy(), a_ref.grad.numpy()) <= 1e-12
+    assert abs(rho_dev.grad.item() - float((ine_r.detach() * w_ine).sum() / rho)) <= 1e-10 * abs(rho_dev.grad.item())
+    cnv1, _, ine1 = drs(angles[0], rho)  # unbatched call
+    assert cnv1.shape == cnv_r.shape[1:] and torch.equal(cnv1, cnv[0].detach())
+
+
 def test_batched_mma_improves_an_ensemble_of_designs():
     """several MMA instances advanced in lock-step, one batched forward + adjoint per iteration"""
     from difflexmm_b200.optimization import OptimizationProblem

@@ -340,6 +340,17 @@ static __device__ __noinline__ int target_index_nl(const AdjArgs& a, int f) { re
 
 // one row of the drive table (out of line: several call sites, none of them inside the RHS phases)
 static __device__ __noinline__ void drive_row_nl(int kind, double t, const double* g_drive, DriveTable table, double* r) {
+  if (kind == DFX_DRIVE_PULSE || kind == DFX_DRIVE_HARMONIC) {
+    // one channel, three parameters (amplitude, loading rate, delay): no DriveEval round trip through local memory
+    // (this row is on the critical path of every step: the whole CTA waits for it at the barrier that ends the step)
+    double s, dtau, dA, df;
+    pulse_eval(t - g_drive[2], g_drive[0], g_drive[1], kind == DFX_DRIVE_PULSE, true, s, dtau, dA, df);
+    r[0] = s; r[1] = 0.0; r[2] = dtau; r[3] = 0.0;
+    r[4] = dA; r[5] = df; r[6] = -dtau; r[7] = 0.0; r[8] = 0.0;
+#pragma unroll
+    for (int q = 0; q < DFX_MAX_DRIVE_PARAMS; ++q) r[9 + q] = 0.0;
+    return;
+  }
   DriveEval de;
   drive_eval(kind, t, g_drive, true, de, table);
   r[0] = de.s[0]; r[1] = de.s[1]; r[2] = de.sdot[0]; r[3] = de.sdot[1];
@@ -866,7 +877,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
 
 #ifdef DFX_PHASE_TIMERS
   // cycles of lane 0 of every warp: A | wait A->B | B | wait B->C | C | what follows (DFX_PHASE_TIMERS builds only)
-  long long pt_acc[6] = {0, 0, 0, 0, 0, 0}, pt_mark = clock64();
+  long long pt_acc[10] = {0, 0, 0, 0, 0, 0, 0, 0, 0, 0}, pt_mark = clock64();  // 6..9: parts of the step end (see the marks)
 #define PT_MARK(k) do { const long long now_ = clock64(); pt_acc[k] += now_ - pt_mark; pt_mark = now_; } while (0)
 #else
 #define PT_MARK(k) do { } while (0)
@@ -1203,6 +1214,10 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       }
       __syncthreads();
     } else {
+#ifndef DFX_A3_OLD_STEP_END
+      __syncthreads();  // scalar running sums of the last stage complete (taken first: the thread's own error terms and the
+                        // scalar totals below are then one block of independent instruction streams)
+#endif
       double se = accq;
       const double h = hst;
       const bool crossing = C->crossing != 0;
@@ -1226,8 +1241,8 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
           eu = -h * (tab.sum_err * y0[3 + j] + h * eu);
           evv *= h;
           if (is_free(j)) {
-            const double r0 = eu / (atol + rtol * fmax(fabs(y0[j]), fabs(y1a[j])));
-            const double r1 = evv / (atol + rtol * fmax(fabs(y0[3 + j]), fabs(y1b[j])));
+            const double r0 = eu * rcp_pos(atol + rtol * fmax(fabs(y0[j]), fabs(y1a[j])));
+            const double r1 = evv * rcp_pos(atol + rtol * fmax(fabs(y0[3 + j]), fabs(y1b[j])));
             se += r0 * r0 + r1 * r1;
           }
         }
@@ -1247,25 +1262,29 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
             if (q == 0) y1a[j] = y1q; else y1b[j] = y1q;
             el *= h;
             if (is_free(j)) {
-              const double r = el / (atol + rtol * fmax(fabs(y0q), fabs(y1q)));
+              const double r = el * rcp_pos(atol + rtol * fmax(fabs(y0q), fabs(y1q)));
               se += r * r;
             }
           }
         }
       }
+      PT_MARK(6);  // error contributions of the thread's own state
+#ifdef DFX_A3_OLD_STEP_END
       __syncthreads();  // scalar running sums of the last stage complete
+#endif
       if (warp < NSCAL) {  // warp k: scalar leaf k
         double tot[5];
         scal_totals_warp(accb, warp, lane, tot);
         if (lane == 0) {
           const double q0 = Sq0[warp];
           const double q1 = q0 + h * tot[2];
-          const double r = h * tot[3] / (atol + rtol * fmax(fabs(q0), fabs(q1)));
+          const double r = h * tot[3] * rcp_pos(atol + rtol * fmax(fabs(q0), fabs(q1)));
           se += r * r;
           Sqnew[warp] = crossing ? interp_eval(q0, q1, q0 + h * tot[4], h * tot[0], h * tot[1], xq) : q1;
         }
       }
       const double ratio = sqrt(block_sum(se, red) * inv_n);
+      PT_MARK(7);  // barrier + scalar totals + norm
       const long long istep = C->istep + 1;
       const double s_target = C->s_target;
       bool interval_done = false, stop = false;
@@ -1347,11 +1366,13 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       else ev = 0;
       if (lane == 0) C->ev_w[warp] = running ? ev : EV_STOP;
       if (tid == 0) { C->hst = h_new; C->i = i; C->par = par; }
+      PT_MARK(8);  // accept / reject bookkeeping
       if (drive_on && running && warp == NW - 1) {
         if (ev == 0 && lane < 6) fill_drive(lane, -(s_new + h_new * tab.alpha[lane]));
         else if (ev == EV_INIT && lane == EV_INIT) fill_drive(EV_INIT, ts[i]);
       }
       __syncthreads();
+      PT_MARK(9);  // drive table of the next step (last warp) + closing barrier
     }
   }
 
@@ -1360,7 +1381,9 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
     const double n_ = (double)C->n_rhs;
     printf("warp %2d cycles/eval: A %.0f | wait A->B %.0f | B %.0f | wait B->C %.0f | C %.0f | post %.0f | total %.0f | evaluations %.0f\n", warp,
            pt_acc[0] / n_, pt_acc[1] / n_, pt_acc[2] / n_, pt_acc[3] / n_, pt_acc[4] / n_, pt_acc[5] / n_,
-           (pt_acc[0] + pt_acc[1] + pt_acc[2] + pt_acc[3] + pt_acc[4] + pt_acc[5]) / n_, n_);
+           (pt_acc[0] + pt_acc[1] + pt_acc[2] + pt_acc[3] + pt_acc[4] + pt_acc[5] + pt_acc[6] + pt_acc[7] + pt_acc[8] + pt_acc[9]) / n_, n_);
+    printf("warp %2d step end, cycles/step: own error terms %.0f | barrier + scalar totals + norm %.0f | accept / reject %.0f | drive table + barrier %.0f | steps %lld\n",
+           warp, (double)pt_acc[6] / C->n_steps, (double)pt_acc[7] / C->n_steps, (double)pt_acc[8] / C->n_steps, (double)pt_acc[9] / C->n_steps, C->n_steps);
   }
 #endif
   // ---- outputs ----------------------------------------------------------------------------------------------

@@ -128,8 +128,9 @@ def test_vocabulary_is_closed_and_loud():
         lower_topology(g, energy, constrained_block_DOF_pairs=[[0, 0]], constrained_DOFs_fn=lambda t: 0.0)
     with pytest.raises(TypeError):
         build_strain_energy(bonds, lambda *a, **k: 0.0)
-    with pytest.raises(NotImplementedError):
-        build_contact_energy(bonds, angle_based=False)
+    dist = combine_block_energies(build_strain_energy(bonds, ligament_energy), build_contact_energy(bonds, angle_based=False))
+    assert dist.contact == _abi.DFX_CONTACT_DISTANCE and energy.contact == _abi.DFX_CONTACT_ANGLE  # both contact models lower
+    assert lower_topology(g, dist)[0].contact == _abi.DFX_CONTACT_DISTANCE
     with pytest.raises(ValueError):
         lower_topology(g, energy, constrained_block_DOF_pairs=[[0, 0], [0, 0]], constrained_DOFs_fn=pulse_drive([1, 0]))
     spec, drive = lower_topology(g, build_strain_energy(bonds, ligament_energy_linearized), [[11, 0]], ramp_load(0.2, 1e-3),

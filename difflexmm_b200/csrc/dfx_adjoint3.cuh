@@ -1214,10 +1214,6 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
       }
       __syncthreads();
     } else {
-#ifndef DFX_A3_OLD_STEP_END
-      __syncthreads();  // scalar running sums of the last stage complete (taken first: the thread's own error terms and the
-                        // scalar totals below are then one block of independent instruction streams)
-#endif
       double se = accq;
       const double h = hst;
       const bool crossing = C->crossing != 0;
@@ -1227,6 +1223,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         double y0[6], kvh[21];  // the whole velocity-derivative history with two wide loads
         tm_ld<6>(ta + 2 * P_U0, y0);
         tm_ld<21>(ta + 2 * P_KV, kvh);
+
 #pragma unroll
         for (int j = 0; j < 3; ++j) {
           double eu = 0.0, evv = 0.0, su = 0.0, sv = 0.0;
@@ -1269,9 +1266,7 @@ __global__ void __launch_bounds__(k3::TT, 1) adjoint3_kernel(const __grid_consta
         }
       }
       PT_MARK(6);  // error contributions of the thread's own state
-#ifdef DFX_A3_OLD_STEP_END
       __syncthreads();  // scalar running sums of the last stage complete
-#endif
       if (warp < NSCAL) {  // warp k: scalar leaf k
         double tot[5];
         scal_totals_warp(accb, warp, lane, tot);

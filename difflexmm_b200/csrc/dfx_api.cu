@@ -886,7 +886,8 @@ int dfx_rotated_square_vjp(int n1_blocks, int n2_blocks, double half_side, int b
 
 // ---- design constraints (dfx_geometry.cuh) -----------------------------------------------------------------------
 struct DfxConstraints {
-  const DfxGeometry* geo;
+  int device;       // copies: the handle must stay destroyable after its geometry (finalisers run in any order)
+  DevGeometry dev;  // device tables owned by the geometry, which must be alive for dfx_constraints_eval
   int m, m_angle;
   ConstraintRow* rows;         // device
   std::vector<int32_t> cols;   // host, [m][4]
@@ -946,7 +947,7 @@ int dfx_constraints_create(const DfxGeometry* g, const DfxConstraintDesc* d, Dfx
   if (rows.empty()) { cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "no constraint rows requested"); }
   DfxConstraints* h = new (std::nothrow) DfxConstraints();
   if (!h) { cudaSetDevice(cur); return fail(DFX_ERR_INVALID, "out of host memory"); }
-  h->geo = g; h->m = (int)rows.size(); h->m_angle = m_angle; h->rows = nullptr; h->cols = std::move(cols);
+  h->device = g->device; h->dev = g->dev; h->m = (int)rows.size(); h->m_angle = m_angle; h->rows = nullptr; h->cols = std::move(cols);
   e = upload(rows, &h->rows);
   cudaSetDevice(cur);
   if (e != cudaSuccess) { delete h; return fail(DFX_ERR_CUDA, "constraint table upload failed: %s", cudaGetErrorString(e)); }
@@ -958,7 +959,7 @@ void dfx_constraints_destroy(DfxConstraints* h) {
   if (!h) return;
   int cur = 0;
   cudaGetDevice(&cur);
-  cudaSetDevice(h->geo->device);
+  cudaSetDevice(h->device);
   if (h->rows) cudaFree(h->rows);
   cudaSetDevice(cur);
   delete h;
@@ -981,7 +982,7 @@ int dfx_constraints_eval(const DfxConstraints* h, int batch, const double* desig
   if (batch <= 0) return fail(DFX_ERR_INVALID, "batch must be positive");
   const int threads = 128;
   dim3 grid((h->m + threads - 1) / threads, batch);
-  constraints_kernel<<<grid, threads, 0, (cudaStream_t)stream_>>>(h->geo->dev, h->rows, h->m, design, values, jac);
+  constraints_kernel<<<grid, threads, 0, (cudaStream_t)stream_>>>(h->dev, h->rows, h->m, design, values, jac);
   cudaError_t e = cudaGetLastError();
   if (e != cudaSuccess) return fail(DFX_ERR_CUDA, "constraints launch failed: %s", cudaGetErrorString(e));
   return DFX_OK;

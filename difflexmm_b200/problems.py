@@ -44,8 +44,8 @@ class _ProblemBase:
     def lower(self):
         """-> (TopologySpec, DriveSignal): everything static, on the host."""
         geo = self.make_geometry()
-        self.geometry = geo
         geo.compute_geometry()
+        self.geometry = geo  # published only when complete: lower() may be called again from another thread
         pairs, drive = self.constraints(geo)
         self.constrained_block_DOF_pairs = pairs
         spec, drive = lower_topology(geo, self.energy(geo.bond_connectivity()), None, None, pairs, drive,

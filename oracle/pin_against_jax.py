@@ -104,8 +104,8 @@ def main():
 
         bond_fn = {0: ligament_energy, 1: ligament_energy_linearized, 2: stretching_torsional_spring_energy}[energy_kind]
         energy = build_strain_energy(bond_connectivity=bonds, bond_energy_fn=bond_fn)
-        if int(z["contact"]):
-            energy = combine_block_energies(energy, build_contact_energy(bond_connectivity=bonds))
+        if int(z["contact"]):  # 1: angle-based, 2: distance-based between the void edges (energy.py:364-407)
+            energy = combine_block_energies(energy, build_contact_energy(bond_connectivity=bonds, angle_based=int(z["contact"]) == 1))
         geo = Geo(nb)
         kin = build_constrained_kinematics(geometry=geo, constrained_block_DOF_pairs=pairs, constrained_DOFs_fn=cfn)
         cenergy = constrain_energy(energy_fn=energy, constrained_kinematics=kin)
@@ -138,7 +138,8 @@ def main():
             contact = ContactParams(min_angle=lv["contact"][0], cutoff_angle=lv["contact"][1], k_contact=lv["contact"][2]) \
                 if "contact" in lv else None
             cp = ControlParams(
-                geometrical_params=GeometricalParams(block_centroids=jnp.zeros((nb, 2)),
+                geometrical_params=GeometricalParams(block_centroids=lv["block_centroids"].reshape(nb, 2) if "block_centroids" in lv
+                                                     else jnp.zeros((nb, 2)),
                                                      centroid_node_vectors=lv["centroid_node_vectors"].reshape(nb, npb, 2)),
                 mechanical_params=MechanicalParams(bond_params=bond, density=1.0, inertia=None,
                                                    damping=lv.get("damping", 0.0), contact_params=contact),

@@ -3,7 +3,10 @@
 (0.01 and 0.08 strain, the real static ramps of 0.04 s and 0.32 s) against the C++ oracle at tight tolerances.  Writes one
 JSON line per case to profiles/r02_parity_long.jsonl (minutes of host CPU time; the oracle jobs run on host threads).
 
-  python tools/parity_long.py [--quick]"""
+  python tools/parity_long.py [--quick] [--cfg5]
+
+--cfg5 runs one more case alone: the 100 x 100 lattice with active contact (BASELINE.json cfg5) over two drive periods, generic
+kernels spread over all SMs, against the single-threaded C++ oracle (ten minutes of host time) -> r02_parity_cfg5.jsonl."""
 import json
 import os
 import sys
@@ -32,14 +35,22 @@ def cases(quick):
     return out
 
 
+def cfg5_case():
+    import math
+    from difflexmm_b200.problems import QuadsFocusing
+    P = QuadsFocusing(n1_blocks=100, n2_blocks=100, simulation_time=2 / 30.0, n_timepoints=9, target_shift=(2, 2),
+                      min_angle=15 * math.pi / 180, cutoff_angle=45 * math.pi / 180)
+    return [("cfg5 quads 100x100, contact active, 2 drive periods (n_t 9)", P, P.initial_design(), 1e-8, 1e-8)]
+
+
 def main():
     quick = "--quick" in sys.argv
-    cs = cases(quick)
+    cs = cfg5_case() if "--cfg5" in sys.argv else cases(quick)
     t0 = time.time()
     with ThreadPoolExecutor(max_workers=len(cs)) as pool:
         refs = list(pool.map(lambda c: T.oracle_job(c[1], c[2], c[3], c[4]), cs))
     t_oracle = time.time() - t0
-    path = os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "profiles", "r02_parity_long.jsonl")
+    path = os.path.join(ROOT, "gpurun_out" if os.path.isdir(os.path.join(ROOT, "gpurun_out")) else "profiles", "r02_parity_cfg5.jsonl" if "--cfg5" in sys.argv else "r02_parity_long.jsonl")
     with open(path, "w") as f:
         for (name, P, design, rtol, atol), ref in zip(cs, refs):
             try:

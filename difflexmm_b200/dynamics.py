@@ -309,7 +309,13 @@ class DynamicSolver:
 
     # -- raw launches (device tensors) -------------------------------------------------------
     def lib_forward(self, ps, y0, ts):
-        return self._lib.forward(self.handle, ps, y0, ts, self.rtol, self.atol, self.options)
+        # a batch with more designs than forward slots (2 CTAs per SM) that was solved before -- the next iteration of an
+        # optimisation loop -- is launched longest-first by the step counts of that previous solve (results do not depend
+        # on the launch order; it only shortens the tail of the launch)
+        opt, order, prev = self.options, None, self.last_forward_stats  # noqa: F841 (order kept alive until the launch is queued)
+        if prev is not None and prev.steps_device().numel() == ps.batch:
+            opt, order = self._lib.longest_first(prev, self.options, min_batch=297)
+        return self._lib.forward(self.handle, ps, y0, ts, self.rtol, self.atol, opt)
 
     def lib_adjoint(self, ps, ys, ts, g, aug_size):
         return self._lib.adjoint(self.handle, ps, ys, ts, g, self.rtol, self.atol, aug_size, self.options)

@@ -267,7 +267,7 @@ class _DeviceObjective(torch.autograd.Function):
     def backward(ctx, gJ):
         solver, meta, ps = ctx.solver, ctx.meta, ctx.ps
         ys, ts, y0, ibar, abar = ctx.saved_tensors
-        opt, order = solver._lib.longest_first(solver.last_forward_stats, solver.options)  # noqa: F841 (order kept alive)
+        opt, order = solver.adjoint_launch_options(ps.batch)  # noqa: F841 (order kept alive until the launch is queued)
         y0_bar, ts_bar, grads, stats = solver._lib.adjoint_objective(
             solver.handle, ps, ys, ts, ctx.target_ids, gJ, solver.rtol, solver.atol, meta["aug_size"], opt,
             meta["kind"], ctx.arm)
@@ -317,8 +317,21 @@ class DynamicSolver:
             opt, order = self._lib.longest_first(prev, self.options, min_batch=297)
         return self._lib.forward(self.handle, ps, y0, ts, self.rtol, self.atol, opt)
 
+    def adjoint_launch_options(self, batch):
+        """Launch order of the adjoint of `batch` designs: longest first, so that a launch with more designs than SMs does
+        not end with a few long designs on an otherwise idle GPU (one CTA per SM; attempted steps vary by a factor of two
+        over an ensemble).  Predictor of a design's length: the adjoint step count of the PREVIOUS evaluation of the same
+        batch when there is one -- the next iteration of an optimisation loop, where designs move little -- else the step
+        count of the forward solve just done (a weak predictor: correlation 0.15 on the cfg3 ensemble, the tail then costs
+        10 % of the launch, `tools/tail_analysis.py`).  The results do not depend on the order.  -> (options, order tensor)"""
+        for prev in (self.last_adjoint_stats, self.last_forward_stats):
+            if prev is not None and prev.steps_device().numel() == batch:
+                return self._lib.longest_first(prev, self.options)
+        return self.options, None
+
     def lib_adjoint(self, ps, ys, ts, g, aug_size):
-        return self._lib.adjoint(self.handle, ps, ys, ts, g, self.rtol, self.atol, aug_size, self.options)
+        opt, order = self.adjoint_launch_options(ps.batch)  # noqa: F841 (order kept alive until the launch is queued)
+        return self._lib.adjoint(self.handle, ps, ys, ts, g, self.rtol, self.atol, aug_size, opt)
 
     # -- differentiable odeint ------------------------------------------------------------
     def odeint(self, y0, ts, leaves, batch, per_bond=(), damping_per_dof=False, aug_size=0):

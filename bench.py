@@ -54,10 +54,12 @@ def flops_model(spec, aug_size, n_t, fwd_steps, bwd_steps):
 
 
 class ClockSampler:
-    """SM clock, power and throttle reasons during the timed region (B200_PROFILING.md clocks line), sampled every 0.2 s
-    through NVML inside this process.  (Spawning `nvidia-smi` five times a second stalled CUDA API calls of the timed
-    end-to-end steps by hundreds of milliseconds now and then -- the unexplained outliers of round 1; nvidia-smi remains
-    the fallback when the NVML binding is missing.)"""
+    """SM clock and throttle reasons during the timed region (B200_PROFILING.md clocks line), sampled once a second through
+    NVML inside this process; the maximum clock is read once (that query alone takes up to 75 ms, tools/nvml_probe.py) and
+    the power every fourth sample.  Management queries share driver locks with the CUDA calls of the measured thread:
+    spawning `nvidia-smi` five times a second stalled timed end-to-end steps by hundreds of milliseconds (round 1), four NVML
+    queries every 0.2 s still did now and then (tools/e2e_jitter.py: the device time of a step is constant to 0.1 %, the
+    waits are on the host).  nvidia-smi remains the fallback when the NVML binding is missing."""
 
     def __init__(self, index):
         self.rows, self._stop, self.index = [], threading.Event(), index
@@ -71,6 +73,8 @@ class ClockSampler:
             phys = int(vis.split(",")[index]) if vis and all(x.strip().isdigit() for x in vis.split(",")) else index
             self._h = pynvml.nvmlDeviceGetHandleByIndex(phys)
             self._nvml = pynvml
+            self._max = pynvml.nvmlDeviceGetMaxClockInfo(self._h, pynvml.NVML_CLOCK_SM)
+            self._power, self._k = "", 0
             self.source = "nvml"
         except Exception:
             self.source = "nvidia-smi"
@@ -78,11 +82,12 @@ class ClockSampler:
     def _sample_nvml(self):
         n = self._nvml
         sm = n.nvmlDeviceGetClockInfo(self._h, n.NVML_CLOCK_SM)
-        mx = n.nvmlDeviceGetMaxClockInfo(self._h, n.NVML_CLOCK_SM)
-        pw = n.nvmlDeviceGetPowerUsage(self._h) / 1000.0
+        if self._k % 4 == 0:
+            self._power = f"{n.nvmlDeviceGetPowerUsage(self._h) / 1000.0:.1f}"
+        self._k += 1
         r = n.nvmlDeviceGetCurrentClocksEventReasons(self._h)
         flag = lambda bit: "Active" if r & bit else "Not Active"  # noqa: E731
-        return [str(sm), str(mx), f"{pw:.1f}", flag(n.nvmlClocksEventReasonHwSlowdown), flag(n.nvmlClocksEventReasonHwThermalSlowdown),
+        return [str(sm), str(self._max), self._power, flag(n.nvmlClocksEventReasonHwSlowdown), flag(n.nvmlClocksEventReasonHwThermalSlowdown),
                 flag(n.nvmlClocksEventReasonSwThermalSlowdown), flag(n.nvmlClocksEventReasonSwPowerCap)]
 
     def _run(self):
@@ -99,7 +104,7 @@ class ClockSampler:
                         self.rows.append([x.strip() for x in out.split(",")])
             except Exception:
                 pass
-            self._stop.wait(0.2)
+            self._stop.wait(1.0 if self._nvml is not None else 2.0)
 
     def __enter__(self):
         self._t.start()
@@ -443,12 +448,20 @@ def main():
             for o, d in zip(grad_pinned, design):
                 o.copy_(d.grad, non_blocking=True)
             obj_pinned.copy_(obj.detach(), non_blocking=True)
-            torch.cuda.synchronize()
+            # wait for the results by polling an event: on these hosts a blocking cudaDeviceSynchronize returned up to 450 ms
+            # after the device had finished (device time per step is constant to 0.1 %, tools/e2e_jitter.py), more often with
+            # NVML queries in flight on another thread
+            done = torch.cuda.Event()
+            done.record()
+            while not done.query():
+                pass
 
         for _ in range(max(1, args.warmup)):  # the first calls grow the allocator pools (multi-GB trajectory and workspace blocks)
             e2e_step()
         import gc
         gc.collect()  # autograd graphs of the warm-up steps released now, not by a collection inside the timed region
+        gc.freeze()   # ... and the long-lived objects built so far (the ensemble, torch, numpy) leave the collector's
+                      # working set: a full collection in the middle of a step stalled the launches by hundreds of ms
         barrier()
         n_e2e = args.steps
         e2e_step_ms = []

@@ -134,6 +134,32 @@ def test_batch_of_designs_equals_one_by_one():
     assert (st["status"] == 0).all() and (st["steps"] > 0).all()
 
 
+def test_launch_order_history_does_not_change_results():
+    """the solver orders the forward / adjoint launches of a batch it has evaluated before by that evaluation's step counts
+    (DynamicSolver.adjoint_launch_options, lib_forward): a scheduling hint only -- values and gradients of the second
+    evaluation are bitwise those of the first, and the hint is really taken (more designs than SMs / forward slots)"""
+    P = _problem(simulation_time=0.004, n_timepoints=4)
+    s = P.setup()
+    B = 300
+    hs, vs = P.random_ensemble(B, noise=0.05)
+    out = []
+    for rep in range(2):
+        d = [hs.clone().cuda().requires_grad_(True), vs.clone().cuda().requires_grad_(True)]
+        if rep == 1:
+            opt_a, order_a = s.adjoint_launch_options(B)
+            assert order_a is not None and order_a.numel() == B and opt_a.design_order
+            prev = s.last_adjoint_stats.steps_device()
+            assert bool((prev[order_a.long()][:-1] >= prev[order_a.long()][1:]).all())  # longest first by the previous adjoint
+        J = P.target_kinetic_energy(d, batch=B, fused=True)
+        J.sum().backward()
+        out.append((J.detach().clone(), d[0].grad.clone(), d[1].grad.clone()))
+    assert (s.last_adjoint_stats.numpy()["status"] == 0).all()
+    for a, b in zip(out[0], out[1]):
+        assert torch.equal(a, b)
+    # another batch size: no history to use
+    assert s.adjoint_launch_options(B + 1)[1] is None
+
+
 def test_expand_fields_kernel_matches_torch_postprocessing():
     from difflexmm_b200 import _abi
     P = _problem()

@@ -124,6 +124,17 @@ class tabulated_drive(DriveSignal):
         return f, torch.zeros_like(t)
 
 
+def tabulate_drive(excited_blocks_fn, times, loading_vector):
+    """An arbitrary scalar signal `excited_blocks_fn(t)` (a Python closure with captured constants, as the reference's
+    problems pass to `build_constrained_kinematics`) as a `tabulated_drive`: the closure is sampled at `times` on the host and
+    the kernels interpolate linearly between the samples (`jnp.interp` semantics, constant beyond the ends).  This is an
+    approximation whose error is the interpolation error of the chosen grid -- choose it as fine as the signal demands; its
+    parameters are not differentiable.  Closures that cannot be tabulated (state dependent) stay out of scope."""
+    times = np.asarray(times, dtype=np.float64).reshape(-1)
+    values = np.array([float(excited_blocks_fn(float(t))) for t in times], dtype=np.float64)
+    return tabulated_drive(times, values, loading_vector)
+
+
 class LoadSignal:
     """external force on the loaded DOFs, load_vec[l]*s(t) with captured constants."""
     kind = _abi.DFX_LOAD_NONE

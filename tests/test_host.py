@@ -117,6 +117,21 @@ def test_gradients_flow_from_the_design_to_the_leaves():
     assert hs.grad is not None and torch.isfinite(hs.grad).all() and hs.grad.abs().sum() > 0
 
 
+def test_arbitrary_scalar_drive_can_be_tabulated():
+    """a Python closure as the driving signal (what the reference accepts) enters through loading.tabulate_drive"""
+    import math
+    import torch
+    from difflexmm_b200.loading import tabulate_drive, tabulated_drive
+    f = lambda t: 2.0 * math.sin(40.0 * t) ** 2 if t > 0.001 else 0.0  # noqa: E731
+    times = np.linspace(0.0, 0.05, 2001)
+    d = tabulate_drive(f, times, [1.0, 0.0])
+    assert isinstance(d, tabulated_drive) and d.kind == _abi.DFX_DRIVE_TABLE and len(d.values) == 2001
+    t = torch.tensor([0.0, 0.0123, 0.03, 0.07], dtype=torch.float64)
+    s0, s1 = d.channels(t)
+    ref = torch.tensor([f(0.0), f(0.0123), f(0.03), f(0.05)], dtype=torch.float64)  # constant beyond the last sample
+    assert torch.allclose(s0, ref, atol=2e-6) and float(s1.abs().max()) == 0.0
+
+
 def test_vocabulary_is_closed_and_loud():
     g = QuadGeometry(4, 3, spacing=15., bond_length=2.25)
     g.compute_geometry()

@@ -118,6 +118,70 @@ def test_distance_contact_rhs_matches_the_literal_restatement():
     assert branches == {"hinge", "edge"}
 
 
+def test_full_size_rhs_and_augmented_rhs_match_the_literal_autograd():
+    """the independent derivation at FULL size: on the cfg1 / cfg3 lattice (quads 24 x 16, 712 bonds, contact window moved so
+    that contact is active, pulse drive running) the closed-form RHS and augmented RHS of the C++ oracle (force, H w, t_bar
+    and every parameter cotangent) against torch autograd of the literal energy (oracle/ref_literal.py), at a random state"""
+    import torch
+    from difflexmm_b200.problems import QuadsFocusing
+    from oracle import ref_literal as L
+    P = QuadsFocusing(min_angle=20 * math.pi / 180, cutoff_angle=60 * math.pi / 180)
+    spec, drive = P.lower()
+    hs, vs = P.random_ensemble(1, noise=0.15, seed0=3)
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs((hs[0], vs[0]))
+    lv = {k: v.numpy() for k, v in leaves.items()}
+    orc = Oracle(spec)
+    ps = orc.params(1, lv, pb, dpd)
+    T = lambda x: torch.as_tensor(np.asarray(x), dtype=torch.float64)  # noqa: E731
+    names = ("amplitude", "loading_rate", "input_delay")
+    v0 = T(spec.drive_vec0)
+
+    def cfn(t, **p):  # loading.pulse_drive written out: amplitude (1 - cos(2 pi rate tau)) / 2 inside one period
+        tau = t - p["input_delay"]
+        on = (tau > 0.) & (tau < p["loading_rate"] ** -1)
+        return p["amplitude"] * torch.where(on, (1 - torch.cos(2 * math.pi * p["loading_rate"] * tau)) / 2, torch.zeros((), dtype=torch.float64)) * v0
+
+    prob = L.Problem(spec.n_blocks, spec.n_npb, spec.bond_nodes, spec.constrained_dofs, bond_energy="ligament", use_contact=True,
+                     constrained_DOFs_fn=cfn, damped_blocks=spec.damped_blocks)
+    cp = P.control_params((hs[0], vs[0]), "cpu")
+    Pd = dict(block_centroids=T(cp.geometrical_params.block_centroids), centroid_node_vectors=T(lv["centroid_node_vectors"]),
+              k_stretch=T(lv["k_stretch"]), k_shear=T(lv["k_shear"]), k_rot=T(lv["k_rot"]), reference_vector=T(lv["reference_vector"]),
+              inertia=T(lv["inertia"]), damping=T(lv["damping"]), min_angle=T(lv["contact"][0]), cutoff_angle=T(lv["contact"][1]),
+              k_contact=T(lv["contact"][2]), constraint_params={n: T(lv["drive"][i]) for i, n in enumerate(names)}, loading_params={})
+    rng = np.random.default_rng(0)
+    nf = spec.n_free
+    y = np.concatenate([0.05 * rng.standard_normal(nf), 5 * rng.standard_normal(nf)])
+    tq = 0.012  # inside the pulse
+    a = orc.rhs(ps, y, tq)
+    lnames, lleaves = L.flatten_leaves(Pd)
+    ybar = rng.standard_normal(2 * nf)
+    with torch.enable_grad():
+        yy, tt = T(y).requires_grad_(True), torch.tensor(tq, dtype=torch.float64, requires_grad=True)
+        ll = [T(x).clone().requires_grad_(True) for x in lleaves]
+        ydot = prob.rhs(yy, tt, L._rebuild(Pd, lnames, ll), create_graph=True)
+        grads = torch.autograd.grad(ydot, [yy, tt] + ll, grad_outputs=T(ybar), allow_unused=True)
+    b = ydot.detach().numpy()
+    # the 1/x contact energy amplifies round-off near its asymptote: agreement relative to the largest entry
+    assert np.abs(a - b).max() <= 1e-10 * np.abs(b).max()
+    lit = {n: (np.zeros(tuple(x.shape)) if gq is None else gq.numpy()) for n, gq, x in zip(lnames, grads[2:], ll)}
+    z = np.zeros(orc.aug_size(ps))
+    z[:2 * nf], z[2 * nf:4 * nf] = y, ybar
+    out = orc.aug_rhs(ps, z, -tq)
+    close = lambda got, ref, what: (np.abs(got - ref).max() <= 1e-9 * max(1.0, np.abs(ref).max()), what)  # noqa: E731
+    checks = [close(out[2 * nf:4 * nf], grads[0].numpy(), "y_bar"), close(out[4 * nf], grads[1].item(), "t_bar")]
+    o = 4 * nf + 1
+    nn, nb = spec.n_blocks * spec.n_npb, spec.n_bonds
+    for name, size in (("centroid_node_vectors", 2 * nn), ("reference_vector", 2 * nb), ("k_stretch", 1), ("k_shear", 1), ("k_rot", 1),
+                       ("damping", 3 * len(spec.damped_blocks)), ("inertia", nf)):
+        checks.append(close(out[o:o + size], lit[name].reshape(-1), name))
+        o += size
+    checks.append(close(out[o:o + 3], np.array([lit["min_angle"], lit["cutoff_angle"], lit["k_contact"]]).reshape(-1), "contact"))
+    o += 3
+    checks.append(close(out[o:o + 3], np.array([lit["constraint_params." + n] for n in names]).reshape(-1), "drive"))
+    assert all(ok for ok, _ in checks), [w for ok, w in checks if not ok]
+    assert np.abs(lit["k_contact"]).max() > 0 and np.abs(out[o:o + 3]).max() > 0  # contact active, drive running
+
+
 def _rotated_square_chain(n1_cells):
     from difflexmm_b200.geometry import RotatedSquareGeometry
     geo = RotatedSquareGeometry(n1_cells=n1_cells, n2_cells=1, spacing=1.0)

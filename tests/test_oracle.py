@@ -118,17 +118,25 @@ def test_distance_contact_rhs_matches_the_literal_restatement():
     assert branches == {"hinge", "edge"}
 
 
-def test_full_size_rhs_and_augmented_rhs_match_the_literal_autograd():
-    """the independent derivation at FULL size: on the cfg1 / cfg3 lattice (quads 24 x 16, 712 bonds, contact window moved so
-    that contact is active, pulse drive running) the closed-form RHS and augmented RHS of the C++ oracle (force, H w, t_bar
-    and every parameter cotangent) against torch autograd of the literal energy (oracle/ref_literal.py), at a random state"""
+@pytest.mark.parametrize("lattice", ["cfg1_quads_24x16", "cfg2_kagome_20x12"])
+def test_full_size_rhs_and_augmented_rhs_match_the_literal_autograd(lattice):
+    """the independent derivation at FULL size: on the cfg1 / cfg3 lattice (quads 24 x 16, 712 bonds) and the cfg2 lattice
+    (kagome 20 x 12), contact window moved so that contact is active, pulse drive running: the closed-form RHS and augmented
+    RHS of the C++ oracle (force, H w, t_bar and every parameter cotangent) against torch autograd of the literal energy
+    (oracle/ref_literal.py), at a random state"""
     import torch
-    from difflexmm_b200.problems import QuadsFocusing
+    from difflexmm_b200.problems import KagomeFocusing, QuadsFocusing
     from oracle import ref_literal as L
-    P = QuadsFocusing(min_angle=20 * math.pi / 180, cutoff_angle=60 * math.pi / 180)
+    # contact windows that contain the rest void angles (quads 40 / 140 degrees, kagome 120 degrees)
+    P = QuadsFocusing(min_angle=20 * math.pi / 180, cutoff_angle=60 * math.pi / 180) if lattice.startswith("cfg1") else \
+        KagomeFocusing(min_angle=90 * math.pi / 180, cutoff_angle=150 * math.pi / 180)
     spec, drive = P.lower()
-    hs, vs = P.random_ensemble(1, noise=0.15, seed0=3)
-    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs((hs[0], vs[0]))
+    if lattice.startswith("cfg1"):
+        design = [d[0] for d in P.random_ensemble(1, noise=0.15, seed0=3)]
+    else:  # the regular kagome lattice with its vertices moved a little
+        g = torch.Generator().manual_seed(3)
+        design = [d + 0.3 * torch.randn(d.shape, generator=g, dtype=d.dtype) for d in P.initial_design()]
+    leaves, pb, dpd, aug, y0, ts = P.boundary_inputs(design)
     lv = {k: v.numpy() for k, v in leaves.items()}
     orc = Oracle(spec)
     ps = orc.params(1, lv, pb, dpd)
@@ -143,15 +151,16 @@ def test_full_size_rhs_and_augmented_rhs_match_the_literal_autograd():
 
     prob = L.Problem(spec.n_blocks, spec.n_npb, spec.bond_nodes, spec.constrained_dofs, bond_energy="ligament", use_contact=True,
                      constrained_DOFs_fn=cfn, damped_blocks=spec.damped_blocks)
-    cp = P.control_params((hs[0], vs[0]), "cpu")
+    cp = P.control_params(design, "cpu")
     Pd = dict(block_centroids=T(cp.geometrical_params.block_centroids), centroid_node_vectors=T(lv["centroid_node_vectors"]),
               k_stretch=T(lv["k_stretch"]), k_shear=T(lv["k_shear"]), k_rot=T(lv["k_rot"]), reference_vector=T(lv["reference_vector"]),
               inertia=T(lv["inertia"]), damping=T(lv["damping"]), min_angle=T(lv["contact"][0]), cutoff_angle=T(lv["contact"][1]),
               k_contact=T(lv["contact"][2]), constraint_params={n: T(lv["drive"][i]) for i, n in enumerate(names)}, loading_params={})
+    assert spec.drive_kind == _abi.DFX_DRIVE_PULSE and spec.contact == _abi.DFX_CONTACT_ANGLE
     rng = np.random.default_rng(0)
     nf = spec.n_free
     y = np.concatenate([0.05 * rng.standard_normal(nf), 5 * rng.standard_normal(nf)])
-    tq = 0.012  # inside the pulse
+    tq = float(lv["drive"][2]) + 0.3 / float(lv["drive"][1])  # inside the pulse
     a = orc.rhs(ps, y, tq)
     lnames, lleaves = L.flatten_leaves(Pd)
     ybar = rng.standard_normal(2 * nf)
@@ -172,7 +181,7 @@ def test_full_size_rhs_and_augmented_rhs_match_the_literal_autograd():
     o = 4 * nf + 1
     nn, nb = spec.n_blocks * spec.n_npb, spec.n_bonds
     for name, size in (("centroid_node_vectors", 2 * nn), ("reference_vector", 2 * nb), ("k_stretch", 1), ("k_shear", 1), ("k_rot", 1),
-                       ("damping", 3 * len(spec.damped_blocks)), ("inertia", nf)):
+                       ("damping", 3 * len(spec.damped_blocks) if dpd else 1), ("inertia", nf)):
         checks.append(close(out[o:o + size], lit[name].reshape(-1), name))
         o += size
     checks.append(close(out[o:o + 3], np.array([lit["min_angle"], lit["cutoff_angle"], lit["k_contact"]]).reshape(-1), "contact"))

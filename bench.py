@@ -518,7 +518,9 @@ def main():
                 "traffic": None, "traffic_profile": traffic_note, "peak_source": peak_src,
                 "note": "HBM and tensor rooflines do not bind this path (10.7 MB and 10 Gflop per design, no dense contraction)",
                 "forward_kernel": {"achieved": flops_fwd / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms}, "adjoint_ms": adj_ms,
-                "first_evaluation_without_launch_order_history": first_eval,
+                "first_evaluation_without_launch_order_history": None if first_eval is None else dict(
+                    first_eval, designs_per_s_this_rank=B / (1e-3 * (first_eval["forward_ms"] + first_eval["adjoint_ms"])),
+                    frac=(flops_adj / (first_eval["adjoint_ms"] * 1e-3) / 1e12) / peak),
                 "steps_fwd_mean": float(st_f["steps"].mean()), "steps_bwd_mean": float(st_b["steps"].mean())}
 
     cpu_baseline = None

@@ -77,10 +77,12 @@ class BatchedMMA:
     """
 
     def __init__(self, evaluate: Callable, x0, lower=None, upper=None, maximize=True, constraints: Optional[Callable] = None,
-                 constraint_tolerance: float = 1e-8, dual_iterations: int = 200):
+                 constraint_tolerance: float = 1e-8, dual_iterations: int = 200, initial_move: float = 0.5):
         """`constraints(x: (B, n)) -> (c: (B, m), jac: (B, m, K), columns: (m, K) int64)`: inequality constraints
         `c <= 0` with a fixed-width sparse Jacobian, `jac[b, i, k] = d c_i / d x[columns[i, k]]` (padding entries carry
-        zeros).  `constraint_tolerance` is the feasibility tolerance (the reference passes 1e-8 to nlopt)."""
+        zeros).  `constraint_tolerance` is the feasibility tolerance (the reference passes 1e-8 to nlopt).
+        `initial_move`: initial asymptote distance as a fraction of the bound span (nlopt's MMA uses 0.5; with wide bounds
+        and steep objectives the first candidates then sit at the move limit, 0.45 x span away from the start)."""
         self.evaluate = evaluate
         self.constraints, self.ctol, self.dual_iterations = constraints, float(constraint_tolerance), int(dual_iterations)
         self.sign = -1.0 if maximize else 1.0
@@ -91,7 +93,7 @@ class BatchedMMA:
             torch.as_tensor(v, dtype=_F64, device=dev).expand(B, n).clone()
         self.lb, self.ub = full(lower, -np.inf), full(upper, np.inf)
         span = self.ub - self.lb
-        self.sigma = torch.where(torch.isfinite(span), 0.5 * span, torch.ones_like(span))
+        self.sigma = torch.where(torch.isfinite(span), float(initial_move) * span, torch.ones_like(span))
         self.sigma_min = torch.where(torch.isfinite(span), 1e-8 * span, torch.full_like(span, 1e-12))
         self.sigma_max = torch.where(torch.isfinite(span), 10.0 * span, torch.full_like(span, np.inf))
         self.rho = torch.ones(B, dtype=_F64, device=dev)
@@ -374,7 +376,7 @@ class OptimizationProblem:
     def run_optimization_mma(self, initial_guesses, n_iterations: int, lower_bound: Optional[float] = None,
                              upper_bound: Optional[float] = None, min_void_angle: Optional[float] = None,
                              min_block_angle: Optional[float] = None, min_edge_length: Optional[float] = None,
-                             boundary_angle_constraint=False):
+                             boundary_angle_constraint=False, initial_move: float = 0.5):
         """Batched counterpart of `run_optimization_nlopt` (`problems/quads_focusing.py:546-652`): MMA, objective
         maximised, `n_iterations` evaluations per instance (`opt.set_maxeval`), scalar box bounds, and the reference's
         inequality constraints under the same switches (angle constraints when both `min_void_angle` and
@@ -396,7 +398,8 @@ class OptimizationProblem:
                     self.constraints_violation["edge_lengths"].append(c[:, dc.n_angle_rows:].amax(1).cpu().numpy())
                 return c, jac, dc.scalar_columns
 
-        opt = BatchedMMA(self.objective_and_grad, x0, lower_bound, upper_bound, maximize=True, constraints=constraints)
+        opt = BatchedMMA(self.objective_and_grad, x0, lower_bound, upper_bound, maximize=True, constraints=constraints,
+                         initial_move=initial_move)
         best_x, best_f = opt.run(n_iterations)
         self.objective_values = [h.numpy() for h in opt.history]
         self.best_designs, self.best_objectives = self.unflatten(best_x), best_f

@@ -62,6 +62,30 @@ def main():
                                    "longest first by forward steps": makespan(sb, np.argsort(-sf, kind="stable"), args.sms) / ideal,
                                    "longest first by adjoint steps": makespan(sb, np.argsort(-sb, kind="stable"), args.sms) / ideal},
            "ms_per_step_if_ideal": ms / (makespan(sb, np.argsort(-sf, kind="stable"), args.sms))}
+    # is there a better predictor of the adjoint's length inside the forward solve's statistics?
+    fs = st_f.numpy()
+    feats = {"steps": sf, "accepted": fs["accepted"].astype(np.float64), "rejected": sf - fs["accepted"].astype(np.float64),
+             "1/last_dt": 1.0 / np.maximum(fs["last_dt"], 1e-300)}
+    ysn = ys.detach()
+    nf_ = spec.n_free
+    feats["max |v|"] = ysn[:, :, nf_:].abs().amax(dim=(1, 2)).cpu().numpy()
+    feats["max |u|"] = ysn[:, :, :nf_].abs().amax(dim=(1, 2)).cpu().numpy()
+    feats["objective"] = (0.5 * ysn[:, :, nf_:] ** 2).sum(dim=(1, 2)).cpu().numpy()
+    out["corr_of_adjoint_steps_with_forward_features"] = {k: float(np.corrcoef(v, sb)[0, 1]) for k, v in feats.items()}
+    out["makespan_over_ideal_ordered_by_feature"] = {k: makespan(sb, np.argsort(-v, kind="stable"), args.sms) / ideal for k, v in feats.items()}
+    # a short adjoint pre-pass over the last k output intervals as the predictor of the full adjoint's length?
+    out["prepass_over_last_intervals"] = {}
+    for k in (3, 6, 11, 21):
+        ys_k, ts_k = ys[:, -k:].contiguous(), ts[-k:].contiguous()
+        e0.record()
+        _, _, _, st_k = lib.adjoint_objective(solver.handle, ps, ys_k, ts_k, tidx32, torch.ones(B, dtype=torch.float64, device=dev),
+                                              prob.rtol, prob.atol, aug, solver.options)
+        e1.record()
+        torch.cuda.synchronize()
+        sk = st_k.numpy()["steps"].astype(np.float64)
+        out["prepass_over_last_intervals"][f"{k - 1} intervals"] = {
+            "ms": e0.elapsed_time(e1), "corr_with_full_adjoint_steps": float(np.corrcoef(sk, sb)[0, 1]),
+            "makespan_over_ideal": makespan(sb, np.argsort(-sk, kind="stable"), args.sms) / ideal}
     out["forward"] = {"steps_mean": sf.mean(), "steps_max": sf.max(),
                       "makespan_over_ideal_296_slots": {"plain order": makespan(sf, range(B), 2 * args.sms) / (sf.sum() / (2 * args.sms)),
                                                         "longest first": makespan(sf, np.argsort(-sf, kind="stable"), 2 * args.sms) / (sf.sum() / (2 * args.sms))}}

@@ -511,11 +511,23 @@ def main():
         traffic_note = prof.get("dram_note")
     except Exception:
         pass
+    # DRAM bytes of one adjoint launch of exactly this workload (1024 designs on one GPU, full horizon) from the committed ncu
+    # capture of this build; a counter cannot be read outside a profiler, so other configurations report null
+    traffic = None
+    try:
+        if B == 1024 and world == 1 and HORIZON_SCALE == 1.0:
+            with open(os.path.join(ROOT, "profiles", "r02_adjoint_traffic.json")) as f:
+                tr = json.load(f)
+            traffic = tr["dram_bytes"]
+            traffic_note = "profiles/r02_adjoint_traffic.json (ncu capture of this build and workload): " + tr["note"]
+    except Exception:
+        pass
     roofline = {"kernel": config["adjoint_kernel"], "bound": "fp64_fma", "achieved": achieved, "peak": peak, "unit": "TFLOP/s",
                 "frac": achieved / peak, "frac_of_nominal_37.2": achieved / 37.2,
                 "frac_executed": None if exe_ratio is None else achieved * exe_ratio / peak,
                 # DRAM traffic is not measured in this run (it needs ncu); the capture of this build is cited instead
-                "traffic": None, "traffic_profile": traffic_note, "peak_source": peak_src,
+                "traffic": traffic, "traffic_unit": "DRAM bytes per launch" if traffic else None, "traffic_profile": traffic_note,
+                "peak_source": peak_src,
                 "note": "HBM and tensor rooflines do not bind this path (10.7 MB and 10 Gflop per design, no dense contraction)",
                 "forward_kernel": {"achieved": flops_fwd / (fwd_ms * 1e-3) / 1e12, "ms": fwd_ms}, "adjoint_ms": adj_ms,
                 "first_evaluation_without_launch_order_history": None if first_eval is None else dict(

@@ -40,6 +40,18 @@ int fail(int code, const char* fmt, ...) {
     if (e_ != cudaSuccess) return fail(DFX_ERR_CUDA, "%s failed: %s", #x, cudaGetErrorString(e_));    \
   } while (0)
 
+// The stream-ordered pool of the device keeps what it has allocated (release threshold = unlimited).  With the default
+// threshold of 0 every synchronisation hands the scratch of dfx_geometry_vjp (and of workspace-less solver calls) back to the
+// OS and the next call maps it again: that re-mapping stalled one end-to-end step in ten by 200 - 800 ms (tools/e2e_jitter.py).
+void keep_pool_memory(int device) {
+  cudaMemPool_t pool;
+  if (cudaDeviceGetDefaultMemPool(&pool, device) == cudaSuccess) {
+    uint64_t threshold = UINT64_MAX;
+    cudaMemPoolSetAttribute(pool, cudaMemPoolAttrReleaseThreshold, &threshold);
+  }
+  cudaGetLastError();
+}
+
 constexpr size_t kSmemBytes = 232448;  // 227 KB: the opt-in maximum of one CTA on sm_100
 constexpr int kRedDoubles = 40;
 static_assert(kRedDoubles == kRedDoublesDev, "shared-memory reduction area");
@@ -335,6 +347,7 @@ int dfx_drive_n_params(int kind) { return n_drive_params_of(kind); }
 int dfx_topology_n_free(const DfxTopology* t) { return t ? t->dev.n_free : -1; }
 
 int dfx_topology_create(const DfxTopologyDesc* d, int device, DfxTopology** out) {
+  if (device >= 0) keep_pool_memory(device);
   if (!d || !out) return fail(DFX_ERR_INVALID, "NULL argument");
   if (d->n_blocks <= 0 || d->n_npb < 2 || d->n_bonds < 0) return fail(DFX_ERR_INVALID, "bad sizes");
   if (d->bond_energy != DFX_BOND_LIGAMENT && d->bond_energy != DFX_BOND_LINEARIZED && d->bond_energy != DFX_BOND_SPRING)
@@ -777,6 +790,7 @@ extern "C" {
 
 int dfx_geometry_create(const DfxGeometryDesc* d, int device, DfxGeometry** out) {
   if (!d || !out || !d->base_nodes || !d->node_design) return fail(DFX_ERR_INVALID, "NULL argument");
+  keep_pool_memory(device);
   if (d->n_blocks <= 0 || d->n_npb < 3 || d->n_npb > kMaxPolygon || d->n_design < 0)
     return fail(DFX_ERR_INVALID, "bad geometry sizes (polygons have 3..%d vertices)", kMaxPolygon);
   const int nn = d->n_blocks * d->n_npb;
